@@ -1,0 +1,110 @@
+/* rig.h -- C ABI of the B200 panel rasteriser + near-duplicate filter (librig.so).
+ *
+ * The reference (MrGu11/reasoning_image_generation) has no FFI; its render stage is the Python method
+ *     RPMGenerator._render_elements_to_canvas(W, H, bg_color, elements, use_grid, grid_size)
+ *         -> uint8[H, W, 3] BGR                       /root/reference/src/generator.py:66-124
+ * which loops Shape.draw() over the element dicts     /root/reference/src/shapes.py:209-667.
+ * These entry points are what a ctypes binding of that method calls instead.
+ * Plain C types only; every function returns 0 or a negative RIG_E_* code; no exception, abort or
+ * CPU fallback ever happens behind this boundary -- if no CUDA device is usable the call fails.
+ *
+ * Threading: a context may be used from any thread, one call at a time (the reference calls the
+ * renderer from a watchdog daemon thread, generator.py:192-197).  The CUDA context is created by
+ * rig_create(), never at library load, so the library can be loaded before a fork().
+ */
+#ifndef RIG_H
+#define RIG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RIG_OK 0
+#define RIG_E_INVALID (-1)      /* bad argument */
+#define RIG_E_CUDA (-2)         /* CUDA runtime error; see rig_last_error */
+#define RIG_E_CAPACITY (-3)     /* batch larger than the context was created for */
+#define RIG_E_UNSUPPORTED (-4)  /* valid for the reference but outside this build's limits */
+#define RIG_E_NODEVICE (-5)     /* no usable CUDA device */
+
+#define RIG_LAYOUT_RGB 0
+#define RIG_LAYOUT_BGR 1        /* what the reference returns (cv2 order) */
+
+/* shape kinds, in the order of Shape.__init__'s `supported` tuple (shapes.py:201-202) */
+enum rig_kind {
+    RIG_SQUARE = 0, RIG_CIRCLE, RIG_TRIANGLE, RIG_DIAMOND, RIG_STAR, RIG_PENTAGON, RIG_HEXAGON,
+    RIG_PLUS, RIG_HEART, RIG_CRESCENT, RIG_ROUNDED_SQUARE, RIG_KIND_COUNT
+};
+
+/* Struct-of-arrays scene description of a batch of panels.  All pointers are BORROWED host arrays
+ * that must stay valid until the call returns.  Element i of panel p has
+ * panel_elem_begin[p] <= i < panel_elem_begin[p+1]; elements are drawn in index order.
+ * Field meaning follows the element dict the reference renderer reads (generator.py:87-94):      */
+typedef struct rig_scene {
+    int32_t n_panels;
+    int32_t n_elements;
+    int32_t grid_size;                 /* generator.py:73 (default 3) */
+    uint8_t bg_rgb[3];                 /* cfg.bg_color, one per batch (config.py:29) */
+    uint8_t reserved;
+    const uint32_t *panel_elem_begin;  /* [n_panels + 1] */
+    const uint8_t *panel_flags;        /* [n_panels] bit0 = use_grid (snap centres, draw grid lines) */
+    const uint8_t *kind;               /* [n_elements] enum rig_kind                el['kind']        */
+    const uint8_t *fill;               /* [n_elements] 0/1                          el['fill']        */
+    const uint8_t *flip;               /* [n_elements] bit0 horizontal, bit1 vertical; may be NULL
+                                          (el['flip_mode'], which the reference never sets: SURVEY B5) */
+    const int32_t *stroke;             /* [n_elements]                              int(el['stroke_width']) */
+    const int32_t *size;               /* [n_elements]                              int(el['size'])   */
+    const int32_t *angle;              /* [n_elements] degrees, clockwise positive  int(el['angle'])  */
+    const double *cx;                  /* [n_elements] raw centre as float          el['center'][0]   */
+    const double *cy;                  /* [n_elements]                              el['center'][1]   */
+    const uint8_t *rgb;                /* [3 * n_elements] fill colour R,G,B        el['color'] (after the
+                                          rand_color() draw for colourless elements)        */
+} rig_scene;
+
+typedef struct rig_ctx rig_ctx;
+
+/* Creates a context on CUDA device `device` for W x H panels, at most `max_panels` panels and
+ * `max_elements` elements per call.  W*3*8 must be a multiple of 16 and H a multiple of 8.        */
+int rig_create(int device, int W, int H, int max_panels, int max_elements, rig_ctx **out);
+void rig_destroy(rig_ctx *ctx);
+/* Message of the last failing call on this context (ctx == NULL: of the last failing rig_create). */
+const char *rig_last_error(const rig_ctx *ctx);
+
+/* Replaces the body of _render_elements_to_canvas for a whole batch: uploads the scene, rasterises,
+ * and writes n_panels images of H*W*3 bytes, panel-major, to `out`.
+ *   out_is_device = 0: `out` is host memory (pageable or pinned); the call returns after the copy.
+ *   out_is_device = 1: `out` is device memory on the context's device; the call returns after the
+ *                      kernels are enqueued on `stream` (a cudaStream_t, or NULL for the context's
+ *                      own stream); use rig_sync() before reading.
+ *   out_layout: RIG_LAYOUT_RGB or RIG_LAYOUT_BGR.                                                  */
+int rig_render_batch(rig_ctx *ctx, const rig_scene *scene, uint8_t *out, int out_is_device, int out_layout,
+                     void *stream);
+
+/* Two-step form used when the scene stays resident in HBM (bench.py `value`):
+ * rig_scene_upload packs + copies the scene to the device once; rig_render_resident rasterises the
+ * resident scene into device memory.                                                               */
+int rig_scene_upload(rig_ctx *ctx, const rig_scene *scene, int out_layout, void *stream);
+int rig_render_resident(rig_ctx *ctx, uint8_t *out_device, void *stream);
+
+int rig_sync(rig_ctx *ctx);
+
+/* Counters of the last render on this context (for bench.py's gpu_launches / diagnostics). */
+typedef struct rig_stats {
+    uint64_t kernel_launches;   /* kernels launched by this library since rig_create */
+    uint32_t records;           /* draw records produced by the last render */
+    uint32_t aux_units;         /* 16-byte aux units produced by the last render */
+    uint32_t overflow;          /* 1 if the last render ran out of record space (result invalid) */
+    uint32_t reserved;
+} rig_stats;
+int rig_get_stats(rig_ctx *ctx, rig_stats *out);
+
+/* Debug/test hook: copies the shape tables the device prologue uses (see rig_shapes.h) to `out`
+ * (`size` must equal the value returned when out == NULL).  Needs no GPU.                          */
+size_t rig_debug_shape_tables(void *out, size_t size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIG_H */
