@@ -100,6 +100,27 @@ typedef struct rig_stats {
 } rig_stats;
 int rig_get_stats(rig_ctx *ctx, rig_stats *out);
 
+/* ---- near-duplicate filter ---------------------------------------------------------------------
+ * The reference has no cross-sample duplicate filter (its README mentions one; the code has none --
+ * SURVEY section 0, D2/D3), so there is no reference interface to cite: the semantics are defined by
+ * this repository (oracle/dedup_oracle.py) and are "parity unpinned".
+ *   hash : Y = (77R + 150G + 29B) >> 8, block sums over a 16 x 16 grid, bit b = (256 * S_b > sum S)
+ *          -> rig_hash_words() = 4 uint64 per image, block b in word b/64, bit b%64
+ *   drop : sample j is dropped iff some i < j has popcount(h_i xor h_j) <= threshold               */
+int rig_hash_words(void);
+/* imgs_dev: n images of H*W*3 bytes on the device (as written by rig_render_*), hashes_dev: n*4 uint64 */
+int rig_hash_batch(rig_ctx *ctx, const uint8_t *imgs_dev, int n, int layout, uint64_t *hashes_dev, void *stream);
+/* Scans rows [row_begin, row_end) of the upper-triangular pair matrix over all n_total hashes and
+ * sets drop_flags_dev[j] = 1 for every hit (i, j), i < j.  Flags are only ever set, never cleared,
+ * so ranks that own disjoint row blocks can share or max-reduce one flag array.  hits_dev (may be
+ * NULL) accumulates the number of hit pairs found.                                                 */
+int rig_dedup(rig_ctx *ctx, const uint64_t *all_hashes_dev, uint64_t n_total, uint64_t row_begin, uint64_t row_end,
+              int threshold, uint8_t *drop_flags_dev, uint64_t *hits_dev, void *stream);
+
+/* Page-locked host memory for scene / output buffers (plain cudaMallocHost / cudaFreeHost). */
+int rig_pinned_alloc(size_t bytes, void **out);
+void rig_pinned_free(void *p);
+
 /* Debug/test hook: copies the shape tables the device prologue uses (see rig_shapes.h) to `out`
  * (`size` must equal the value returned when out == NULL).  Needs no GPU.                          */
 size_t rig_debug_shape_tables(void *out, size_t size);

@@ -54,7 +54,7 @@ class RigStats(ctypes.Structure):
 EXPORTS = (
     'rig_create', 'rig_destroy', 'rig_last_error', 'rig_render_batch', 'rig_scene_upload',
     'rig_render_resident', 'rig_sync', 'rig_get_stats', 'rig_debug_shape_tables',
-    'rig_hash_batch', 'rig_dedup', 'rig_hash_words',
+    'rig_hash_batch', 'rig_dedup', 'rig_hash_words', 'rig_pinned_alloc', 'rig_pinned_free',
 )
 
 _lib = None
@@ -90,5 +90,15 @@ def load() -> ctypes.CDLL:
     lib.rig_get_stats.restype = ctypes.c_int
     lib.rig_debug_shape_tables.argtypes = [vp, ctypes.c_size_t]
     lib.rig_debug_shape_tables.restype = ctypes.c_size_t
+    lib.rig_hash_words.argtypes = []
+    lib.rig_hash_words.restype = ctypes.c_int
+    lib.rig_hash_batch.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp]
+    lib.rig_hash_batch.restype = ctypes.c_int
+    lib.rig_dedup.argtypes = [vp, vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, vp, vp, vp]
+    lib.rig_dedup.restype = ctypes.c_int
+    lib.rig_pinned_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+    lib.rig_pinned_alloc.restype = ctypes.c_int
+    lib.rig_pinned_free.argtypes = [vp]
+    lib.rig_pinned_free.restype = None
     _lib = lib
     return lib

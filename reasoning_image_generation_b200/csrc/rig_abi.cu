@@ -1,0 +1,482 @@
+// rig_abi.cu -- the extern "C" boundary declared in include/rig.h: context, uploads, chunked launches.
+//
+// Host flow of one render: pack the borrowed SoA scene into 40-byte device elements (libm cos/sin of
+// the integer angle, centre truncation / grid snap), copy them to HBM, then for every chunk of
+// panels run k_expand (elements -> draw records in an L2-sized arena) and k_raster (records ->
+// pixels, TMA bulk stores).  With a host destination the chunks are double-buffered through two
+// device staging buffers so the D2H copy of chunk i overlaps the rendering of chunk i+1.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "rig_host.h"
+#include "rig_kernels.cuh"
+#include "rig_dedup.cuh"
+
+using namespace rig;
+
+namespace {
+
+thread_local char g_create_err[512] = "";
+
+struct Chunk {
+    uint32_t p0, p1, e0, e1;
+};
+
+}  // namespace
+
+struct rig_ctx {
+    int device = 0, W = 0, H = 0, max_panels = 0, max_elements = 0;
+    int sm_count = 0, raster_warps = 0;
+    size_t raster_smem = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    ShapeTables *d_tables = nullptr;
+    DElem *d_elems = nullptr, *h_elems = nullptr;
+    uint32_t *d_begin = nullptr;
+    uint8_t *d_flags = nullptr;
+    ElemHdr *d_hdrs = nullptr;
+    Rec *d_recs = nullptr;
+    Q16 *d_aux = nullptr;
+    uint32_t rec_cap = 0, aux_cap = 0;
+    uint32_t *d_counters = nullptr;   // CTR_COUNT words
+    uint32_t *d_overflow = nullptr;   // sticky across the chunks of one render
+    uint8_t *d_stage[2] = {nullptr, nullptr};
+    size_t stage_panels = 0;
+    uint32_t *d_sums = nullptr;       // per-image block sums of the hash stage
+    size_t sums_cap = 0;
+    // resident scene
+    int n_panels = 0, n_elements = 0, grid_size = 3, layout = RIG_LAYOUT_RGB;
+    uint32_t bg = 0x00ffffffu;
+    std::vector<uint32_t> h_begin;
+    std::vector<uint32_t> nominal_recs, nominal_aux;   // per element, one copy
+    std::vector<Chunk> chunks;
+    double budget_frac = 0.6;
+    size_t chunk_panel_limit = 4096;
+    rig_stats stats = {};
+    bool pending_overflow_check = false;
+    char err[512] = "";
+};
+
+namespace {
+
+int fail(rig_ctx *c, int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c ? c->err : g_create_err, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(ctx, call)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(ctx, RIG_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// records / aux units of one element assuming a single wrap copy (used only to size chunks)
+void nominal_counts(int kind, int fill, int stroke, uint32_t &nrec, uint32_t &naux)
+{
+    const int t = stroke < 1 ? 1 : stroke;
+    if (kind == K_CIRCLE) {
+        nrec = (fill ? 1 : 0) + ring_recs(MAX_RING_VERTS - 1, t);
+        naux = ring_aux(MAX_RING_VERTS - 1, t);
+    } else if (kind == K_CRESCENT) {
+        nrec = 1 + 2 * ring_recs(MAX_RING_VERTS - 1, t) + 4;
+        naux = 2 * ring_aux(MAX_RING_VERTS - 1, t);
+    } else {
+        const int n = kind_nverts(kind), l = kind_loops(kind);
+        nrec = l * ((fill ? n + 1 : 0) + n * stroke_recs(t));
+        naux = l * ((fill ? n : 0) + n * stroke_aux(t));
+    }
+}
+
+void plan_chunks(rig_ctx *c, size_t panel_limit)
+{
+    c->chunks.clear();
+    const double rb = c->rec_cap * c->budget_frac, ab = c->aux_cap * c->budget_frac;
+    uint32_t p0 = 0;
+    double r = 0, a = 0;
+    for (uint32_t p = 0; p < (uint32_t)c->n_panels; p++) {
+        double pr = 0, pa = 0;
+        for (uint32_t e = c->h_begin[p]; e < c->h_begin[p + 1]; e++) { pr += c->nominal_recs[e]; pa += c->nominal_aux[e]; }
+        if (p > p0 && (r + pr > rb || a + pa > ab || p - p0 >= panel_limit)) {
+            c->chunks.push_back({p0, p, c->h_begin[p0], c->h_begin[p]});
+            p0 = p; r = a = 0;
+        }
+        r += pr; a += pa;
+    }
+    if ((uint32_t)c->n_panels > p0) c->chunks.push_back({p0, (uint32_t)c->n_panels, c->h_begin[p0], c->h_begin[c->n_panels]});
+}
+
+int validate_scene(rig_ctx *c, const rig_scene *s)
+{
+    if (!s) return fail(c, RIG_E_INVALID, "scene is NULL");
+    if (s->n_panels < 0 || s->n_elements < 0) return fail(c, RIG_E_INVALID, "negative panel/element count");
+    if (s->n_panels > c->max_panels) return fail(c, RIG_E_CAPACITY, "%d panels > max_panels %d", s->n_panels, c->max_panels);
+    if (s->n_elements > c->max_elements) return fail(c, RIG_E_CAPACITY, "%d elements > max_elements %d", s->n_elements, c->max_elements);
+    if (s->n_panels && (!s->panel_elem_begin)) return fail(c, RIG_E_INVALID, "panel_elem_begin is NULL");
+    if (s->n_elements && (!s->kind || !s->fill || !s->stroke || !s->size || !s->angle || !s->cx || !s->cy || !s->rgb))
+        return fail(c, RIG_E_INVALID, "an element array is NULL");
+    if (s->grid_size < 0 || s->grid_size > 64) return fail(c, RIG_E_INVALID, "grid_size %d out of range", s->grid_size);
+    if (s->n_panels) {
+        if (s->panel_elem_begin[0] != 0 || s->panel_elem_begin[s->n_panels] != (uint32_t)s->n_elements)
+            return fail(c, RIG_E_INVALID, "panel_elem_begin must start at 0 and end at n_elements");
+        for (int p = 0; p < s->n_panels; p++)
+            if (s->panel_elem_begin[p] > s->panel_elem_begin[p + 1]) return fail(c, RIG_E_INVALID, "panel_elem_begin is not monotone");
+    }
+    return RIG_OK;
+}
+
+int launch_chunk(rig_ctx *c, const Chunk &ch, uint8_t *out_dev, cudaStream_t st)
+{
+    CK(c, cudaMemsetAsync(c->d_counters, 0, CTR_COUNT * sizeof(uint32_t), st));
+    const uint32_t ne = ch.e1 - ch.e0;
+    if (ne) {
+        k_expand<<<(ne + EXPAND_WARPS - 1) / EXPAND_WARPS, EXPAND_WARPS * 32, 0, st>>>(
+            c->d_elems, ch.e0, ch.e1, c->d_tables, c->W, c->H, c->d_hdrs, c->d_recs, c->rec_cap, c->d_aux, c->aux_cap,
+            c->d_counters);
+        c->stats.kernel_launches++;
+    }
+    RasterParams P;
+    P.panel_begin = c->d_begin; P.panel_flags = c->d_flags; P.hdrs = c->d_hdrs; P.recs = c->d_recs; P.aux = c->d_aux;
+    P.tables = c->d_tables; P.out = out_dev; P.counters = c->d_counters; P.p0 = ch.p0; P.n_panels = ch.p1 - ch.p0;
+    P.W = c->W; P.H = c->H; P.grid_size = c->grid_size; P.bg = c->bg;
+    const uint32_t bands = P.n_panels * (uint32_t)(c->H / BAND_ROWS);
+    const uint32_t want = (bands + CLAIM_BANDS * c->raster_warps - 1) / (CLAIM_BANDS * c->raster_warps);
+    const uint32_t grid = std::max(1u, std::min((uint32_t)c->sm_count, want));
+    k_raster<<<grid, c->raster_warps * 32, c->raster_smem, st>>>(P);
+    c->stats.kernel_launches++;
+    k_collect_overflow<<<1, 32, 0, st>>>(c->d_counters, c->d_overflow);
+    c->stats.kernel_launches++;
+    CK(c, cudaGetLastError());
+    return RIG_OK;
+}
+
+int check_overflow(rig_ctx *c)
+{
+    uint32_t h[4] = {0, 0, 0, 0};
+    CK(c, cudaMemcpy(h, c->d_overflow, sizeof h, cudaMemcpyDeviceToHost));
+    c->pending_overflow_check = false;
+    c->stats.overflow = h[0];
+    c->stats.records = h[1];
+    c->stats.aux_units = h[2];
+    return h[0] ? 1 : 0;
+}
+
+int upload_scene(rig_ctx *c, const rig_scene *s, int layout, cudaStream_t st)
+{
+    int rc = validate_scene(c, s);
+    if (rc) return rc;
+    if (layout != RIG_LAYOUT_RGB && layout != RIG_LAYOUT_BGR) return fail(c, RIG_E_INVALID, "bad out_layout %d", layout);
+    char msg[256] = "";
+    rc = pack_elements(*s, c->W, c->H, layout == RIG_LAYOUT_BGR, c->h_elems, msg, sizeof msg);
+    if (rc) return fail(c, rc, "%s", msg);
+    c->n_panels = s->n_panels; c->n_elements = s->n_elements;
+    c->grid_size = s->grid_size > 0 ? s->grid_size : 3;
+    c->layout = layout;
+    c->bg = layout == RIG_LAYOUT_BGR ? ((uint32_t)s->bg_rgb[2] | (s->bg_rgb[1] << 8) | (s->bg_rgb[0] << 16))
+                                     : ((uint32_t)s->bg_rgb[0] | (s->bg_rgb[1] << 8) | (s->bg_rgb[2] << 16));
+    c->h_begin.assign(s->panel_elem_begin, s->panel_elem_begin + s->n_panels + 1);
+    if (s->n_panels == 0) c->h_begin.assign(1, 0);
+    c->nominal_recs.resize(s->n_elements);
+    c->nominal_aux.resize(s->n_elements);
+    for (int i = 0; i < s->n_elements; i++) nominal_counts(s->kind[i], s->fill[i], s->stroke[i], c->nominal_recs[i], c->nominal_aux[i]);
+    if (s->n_elements) CK(c, cudaMemcpyAsync(c->d_elems, c->h_elems, sizeof(DElem) * s->n_elements, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(c->d_begin, c->h_begin.data(), sizeof(uint32_t) * (s->n_panels + 1), cudaMemcpyHostToDevice, st));
+    if (s->n_panels) {
+        if (s->panel_flags) CK(c, cudaMemcpyAsync(c->d_flags, s->panel_flags, s->n_panels, cudaMemcpyHostToDevice, st));
+        else CK(c, cudaMemsetAsync(c->d_flags, 0, s->n_panels, st));
+    }
+    // h_elems / h_begin are reused by the next upload: the copies above must have left the host
+    CK(c, cudaStreamSynchronize(st));
+    c->budget_frac = 0.6;
+    plan_chunks(c, c->chunk_panel_limit);
+    return RIG_OK;
+}
+
+int render_device(rig_ctx *c, uint8_t *out_dev, cudaStream_t st)
+{
+    CK(c, cudaMemsetAsync(c->d_overflow, 0, 4 * sizeof(uint32_t), st));
+    const size_t img = (size_t)c->W * c->H * 3;
+    for (const Chunk &ch : c->chunks) {
+        int rc = launch_chunk(c, ch, out_dev + (size_t)ch.p0 * img, st);
+        if (rc) return rc;
+    }
+    c->pending_overflow_check = true;
+    return RIG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *rig_last_error(const rig_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+int rig_create(int device, int W, int H, int max_panels, int max_elements, rig_ctx **out)
+{
+    if (!out) return fail(nullptr, RIG_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (W <= 0 || H <= 0 || W % 4 || (3 * W * BAND_ROWS) % 16 || H % BAND_ROWS || W > 4096 || H > 4096)
+        return fail(nullptr, RIG_E_INVALID, "unsupported canvas %dx%d (W %% 4 == 0, H %% %d == 0, <= 4096)", W, H, BAND_ROWS);
+    if (max_panels <= 0 || max_elements <= 0) return fail(nullptr, RIG_E_INVALID, "max_panels/max_elements must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, RIG_E_NODEVICE, "no usable CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, RIG_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    rig_ctx *c = new rig_ctx();
+    c->device = device; c->W = W; c->H = H; c->max_panels = max_panels; c->max_elements = max_elements;
+    auto bail = [&](int code) {
+        snprintf(g_create_err, sizeof g_create_err, "%s", c->err);
+        rig_destroy(c);
+        return code;
+    };
+#define CKC(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            fail(c, RIG_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                   \
+            return bail(RIG_E_CUDA);                                                               \
+        }                                                                                          \
+    } while (0)
+    CKC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 9) {
+        fail(c, RIG_E_UNSUPPORTED, "device %d is sm_%d%d; the kernels need bulk async copies (sm_90+; built for sm_100a)", device, prop.major, prop.minor);
+        return bail(RIG_E_UNSUPPORTED);
+    }
+    c->sm_count = prop.multiProcessorCount;
+    const size_t smem_max = prop.sharedMemPerBlockOptin;
+    int warps = 16;
+    while (warps > 1 && raster_smem_bytes(W, warps) > smem_max) warps--;
+    if (raster_smem_bytes(W, warps) > smem_max) {
+        fail(c, RIG_E_UNSUPPORTED, "canvas width %d needs %zu B of shared memory per band set; the device offers %zu", W, raster_smem_bytes(W, warps), smem_max);
+        return bail(RIG_E_UNSUPPORTED);
+    }
+    c->raster_warps = warps;
+    c->raster_smem = raster_smem_bytes(W, warps);
+    CKC(cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->raster_smem));
+    CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CKC(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+        CKC(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+    }
+    ShapeTables T;
+    fill_shape_tables(T);
+    CKC(cudaMalloc(&c->d_tables, sizeof T));
+    CKC(cudaMemcpy(c->d_tables, &T, sizeof T, cudaMemcpyHostToDevice));
+    CKC(cudaMalloc(&c->d_elems, sizeof(DElem) * (size_t)max_elements));
+    CKC(cudaMallocHost(&c->h_elems, sizeof(DElem) * (size_t)max_elements));
+    CKC(cudaMalloc(&c->d_begin, sizeof(uint32_t) * ((size_t)max_panels + 1)));
+    CKC(cudaMalloc(&c->d_flags, (size_t)max_panels));
+    CKC(cudaMalloc(&c->d_hdrs, sizeof(ElemHdr) * (size_t)max_elements));
+    // record arena: large enough for the worst single panel, small enough to stay L2-resident
+    const uint64_t want_rec = std::min<uint64_t>(std::max<uint64_t>((uint64_t)max_elements * 640, 1u << 16), 2u << 20);
+    c->rec_cap = (uint32_t)want_rec;
+    c->aux_cap = (uint32_t)want_rec;
+    CKC(cudaMalloc(&c->d_recs, sizeof(Rec) * (size_t)c->rec_cap));
+    CKC(cudaMalloc(&c->d_aux, sizeof(Q16) * (size_t)c->aux_cap));
+    CKC(cudaMalloc(&c->d_counters, CTR_COUNT * sizeof(uint32_t)));
+    CKC(cudaMalloc(&c->d_overflow, 4 * sizeof(uint32_t)));
+    CKC(cudaMemset(c->d_overflow, 0, 4 * sizeof(uint32_t)));
+#undef CKC
+    *out = c;
+    return RIG_OK;
+}
+
+void rig_destroy(rig_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    cudaFree(c->d_tables); cudaFree(c->d_elems); cudaFreeHost(c->h_elems); cudaFree(c->d_begin); cudaFree(c->d_flags);
+    cudaFree(c->d_hdrs); cudaFree(c->d_recs); cudaFree(c->d_aux); cudaFree(c->d_counters); cudaFree(c->d_overflow);
+    cudaFree(c->d_stage[0]); cudaFree(c->d_stage[1]); cudaFree(c->d_sums);
+    for (int i = 0; i < 2; i++) {
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+    }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+int rig_scene_upload(rig_ctx *c, const rig_scene *scene, int out_layout, void *stream)
+{
+    if (!c) return RIG_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    return upload_scene(c, scene, out_layout, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int rig_render_resident(rig_ctx *c, uint8_t *out_device, void *stream)
+{
+    if (!c) return RIG_E_INVALID;
+    if (!out_device && c->n_panels) return fail(c, RIG_E_INVALID, "out_device is NULL");
+    if (((uintptr_t)out_device) % 16) return fail(c, RIG_E_INVALID, "out_device must be 16-byte aligned");
+    CK(c, cudaSetDevice(c->device));
+    return render_device(c, out_device, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int rig_sync(rig_ctx *c)
+{
+    if (!c) return RIG_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaStreamSynchronize(c->copy_stream));
+    if (c->pending_overflow_check) {
+        CK(c, cudaDeviceSynchronize());
+        int o = check_overflow(c);
+        if (o < 0) return o;
+        if (o) {
+            c->budget_frac *= 0.5;   // the next rig_render_resident uses smaller chunks
+            plan_chunks(c, c->chunk_panel_limit);
+            return fail(c, RIG_E_CAPACITY, "draw-record arena overflowed (%u records in the render); chunks were halved, render again", c->stats.records);
+        }
+    }
+    return RIG_OK;
+}
+
+int rig_render_batch(rig_ctx *c, const rig_scene *scene, uint8_t *out, int out_is_device, int out_layout, void *stream)
+{
+    if (!c) return RIG_E_INVALID;
+    if (!out && scene && scene->n_panels) return fail(c, RIG_E_INVALID, "out is NULL");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    int rc = upload_scene(c, scene, out_layout, st);
+    if (rc) return rc;
+    if (out_is_device) {
+        if (((uintptr_t)out) % 16) return fail(c, RIG_E_INVALID, "out must be 16-byte aligned");
+        return render_device(c, out, st);
+    }
+    // host destination: staged, double-buffered D2H
+    const size_t img = (size_t)c->W * c->H * 3;
+    for (int attempt = 0; attempt < 6; attempt++) {
+        const size_t stage_limit = std::max<size_t>(1, std::min<size_t>(512, (size_t)c->n_panels));
+        if (c->stage_panels < stage_limit) {
+            CK(c, cudaStreamSynchronize(c->copy_stream));
+            for (int i = 0; i < 2; i++) {
+                if (c->d_stage[i]) CK(c, cudaFree(c->d_stage[i]));
+                c->d_stage[i] = nullptr;
+                CK(c, cudaMalloc(&c->d_stage[i], stage_limit * img));
+            }
+            c->stage_panels = stage_limit;
+        }
+        plan_chunks(c, std::min(c->stage_panels, c->chunk_panel_limit));
+        CK(c, cudaMemsetAsync(c->d_overflow, 0, 4 * sizeof(uint32_t), st));
+        int k = 0;
+        for (const Chunk &ch : c->chunks) {
+            const int b = k & 1;
+            if (k >= 2) CK(c, cudaStreamWaitEvent(st, c->ev_copied[b], 0));
+            rc = launch_chunk(c, ch, c->d_stage[b], st);
+            if (rc) return rc;
+            CK(c, cudaEventRecord(c->ev_done[b], st));
+            CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
+            CK(c, cudaMemcpyAsync(out + (size_t)ch.p0 * img, c->d_stage[b], (size_t)(ch.p1 - ch.p0) * img, cudaMemcpyDeviceToHost, c->copy_stream));
+            CK(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
+            k++;
+        }
+        CK(c, cudaStreamSynchronize(st));
+        CK(c, cudaStreamSynchronize(c->copy_stream));
+        int o = check_overflow(c);
+        if (o < 0) return o;
+        if (!o) return RIG_OK;
+        c->budget_frac *= 0.5;   // wrap copies made some chunk larger than planned: retry with smaller chunks
+    }
+    return fail(c, RIG_E_CAPACITY, "draw-record arena overflowed even with single-panel chunks");
+}
+
+int rig_get_stats(rig_ctx *c, rig_stats *out)
+{
+    if (!c || !out) return RIG_E_INVALID;
+    *out = c->stats;
+    return RIG_OK;
+}
+
+int rig_hash_words(void) { return HASH_WORDS; }
+
+int rig_hash_batch(rig_ctx *c, const uint8_t *imgs_dev, int n, int layout, uint64_t *hashes_dev, void *stream)
+{
+    if (!c) return RIG_E_INVALID;
+    if (n < 0 || (n && (!imgs_dev || !hashes_dev))) return fail(c, RIG_E_INVALID, "bad arguments to rig_hash_batch");
+    if (layout != RIG_LAYOUT_RGB && layout != RIG_LAYOUT_BGR) return fail(c, RIG_E_INVALID, "bad layout %d", layout);
+    if (c->W % (16 * HASH_GRID) || c->H % HASH_GRID)
+        return fail(c, RIG_E_UNSUPPORTED, "hashing needs W %% %d == 0 and H %% %d == 0", 16 * HASH_GRID, HASH_GRID);
+    if (((uintptr_t)imgs_dev) % 16) return fail(c, RIG_E_INVALID, "imgs_dev must be 16-byte aligned");
+    if (n == 0) return RIG_OK;
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if (c->sums_cap < (size_t)n) {
+        CK(c, cudaStreamSynchronize(st));
+        if (c->d_sums) CK(c, cudaFree(c->d_sums));
+        c->d_sums = nullptr;
+        CK(c, cudaMalloc(&c->d_sums, sizeof(uint32_t) * 256 * (size_t)n));
+        c->sums_cap = (size_t)n;
+    }
+    const int r_idx = layout == RIG_LAYOUT_RGB ? 0 : 2, b_idx = 2 - r_idx;
+    k_block_sums<<<(unsigned)n * HASH_GRID, 256, 0, st>>>(imgs_dev, c->W, c->H, r_idx, b_idx, c->d_sums);
+    k_hash_bits<<<((unsigned)n * 32 + 255) / 256, 256, 0, st>>>(c->d_sums, n, hashes_dev);
+    c->stats.kernel_launches += 2;
+    CK(c, cudaGetLastError());
+    return RIG_OK;
+}
+
+int rig_dedup(rig_ctx *c, const uint64_t *all_hashes_dev, uint64_t n_total, uint64_t row_begin, uint64_t row_end,
+              int threshold, uint8_t *drop_flags_dev, uint64_t *hits_dev, void *stream)
+{
+    if (!c) return RIG_E_INVALID;
+    if (row_begin > row_end || row_end > n_total) return fail(c, RIG_E_INVALID, "bad row range");
+    if (n_total && (!all_hashes_dev || !drop_flags_dev)) return fail(c, RIG_E_INVALID, "NULL hash / flag array");
+    if (threshold < 0 || threshold > 64 * HASH_WORDS) return fail(c, RIG_E_INVALID, "threshold out of range");
+    if (row_begin == row_end) return RIG_OK;
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const uint64_t rows = row_end - row_begin;
+    const uint64_t gy_total = (rows + DD_TI - 1) / DD_TI, gx = (n_total + DD_TJ - 1) / DD_TJ;
+    // gridDim.y is limited to 65535: walk the row range in slabs
+    for (uint64_t y0 = 0; y0 < gy_total; y0 += 65535) {
+        const uint64_t gy = std::min<uint64_t>(65535, gy_total - y0);
+        dim3 grid((unsigned)gx, (unsigned)gy);
+        k_hamming<<<grid, DD_TI, 0, st>>>(all_hashes_dev, n_total, row_begin + y0 * DD_TI, row_end, threshold, drop_flags_dev,
+                                          (unsigned long long *)hits_dev);
+        c->stats.kernel_launches++;
+    }
+    CK(c, cudaGetLastError());
+    return RIG_OK;
+}
+
+int rig_pinned_alloc(size_t bytes, void **out)
+{
+    if (!out) return RIG_E_INVALID;
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(nullptr, RIG_E_CUDA, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return RIG_OK;
+}
+
+void rig_pinned_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+size_t rig_debug_shape_tables(void *out, size_t size)
+{
+    if (out && size == sizeof(ShapeTables)) {
+        ShapeTables T;
+        fill_shape_tables(T);
+        memcpy(out, &T, sizeof T);
+    }
+    return sizeof(ShapeTables);
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// rig_dedup.cuh -- near-duplicate filter: packed perceptual hash + all-pairs popcount Hamming scan.
+//
+// The reference has NO cross-sample duplicate filter; this stage is new
+// functionality defined by this repository (oracle/dedup_oracle.py is its CPU statement).  It is
+// integer work on the INT/POPC pipes -- no tensor cores:
+//   hash  : Y = (77 R + 150 G + 29 B) >> 8; S_b = sum of Y over block b of a 16 x 16 grid;
+//           T = sum_b S_b; bit b = (256 * S_b > T)  ->  256 bits = 4 x uint64 per image
+//   filter: sample j is dropped iff some i < j has popc(h_i xor h_j) <= threshold
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rig {
+
+constexpr int HASH_GRID = 16;                       // 16 x 16 blocks
+constexpr int HASH_WORDS = HASH_GRID * HASH_GRID / 64;   // uint64 words per hash
+
+// One CTA per (image, block-row).  256 threads; a thread reads 16 consecutive pixels (48 bytes).
+// r_idx / b_idx: byte offsets of R and B inside a pixel (layout RGB: 0,2; BGR: 2,0).
+__global__ void __launch_bounds__(256)
+k_block_sums(const uint8_t *__restrict__ imgs, int W, int H, int r_idx, int b_idx, uint32_t *__restrict__ sums)
+{
+    __shared__ uint32_t acc[HASH_GRID];
+    const int img = blockIdx.x / HASH_GRID, by = blockIdx.x % HASH_GRID;
+    const int bh = H / HASH_GRID, bw = W / HASH_GRID;
+    if (threadIdx.x < HASH_GRID) acc[threadIdx.x] = 0;
+    __syncthreads();
+    const int groups_per_row = W / 16;
+    const uint8_t *base = imgs + ((size_t)img * H + (size_t)by * bh) * (size_t)W * 3;
+    const int total = bh * groups_per_row;
+    for (int g = threadIdx.x; g < total; g += blockDim.x) {
+        const int row = g / groups_per_row, gx = g % groups_per_row;
+        const uint4 *p = (const uint4 *)(base + ((size_t)row * W + (size_t)gx * 16) * 3);
+        uint4 v[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+        const uint8_t *b = (const uint8_t *)v;
+        // a 16-pixel group can straddle two blocks only if bw < 16; W/16 >= 16 is required by the host
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) s += (77u * b[3 * k + r_idx] + 150u * b[3 * k + 1] + 29u * b[3 * k + b_idx]) >> 8;
+        atomicAdd(&acc[(gx * 16) / bw], s);
+    }
+    __syncthreads();
+    if (threadIdx.x < HASH_GRID) sums[(size_t)img * HASH_GRID * HASH_GRID + by * HASH_GRID + threadIdx.x] = acc[threadIdx.x];
+}
+
+// One warp per image: sums -> 256-bit hash
+__global__ void k_hash_bits(const uint32_t *__restrict__ sums, int n, uint64_t *__restrict__ hashes)
+{
+    const int img = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (img >= n) return;
+    const uint32_t *s = sums + (size_t)img * 256;
+    uint32_t v[8];
+    uint64_t t = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { v[k] = s[k * 32 + lane]; t += v[k]; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint32_t bits = __ballot_sync(0xffffffffu, 256ull * v[k] > t);
+        if (lane == 0) {
+            // block index b = 32k + lane -> word b / 64, bit b % 64
+            uint32_t *w = (uint32_t *)(hashes + (size_t)img * HASH_WORDS);
+            w[k] = bits;
+        }
+    }
+}
+
+// All-pairs scan.  CTA = 256 rows x one column tile of TJ hashes staged in shared memory; a thread
+// keeps its row hash in registers and walks the tile (every lane reads the same shared address:
+// broadcast).  The first 64 bits reject almost every pair with 2 POPCs; the remaining 192 bits are
+// only examined when some lane of the warp is still under the threshold.
+constexpr int DD_TI = 256;
+constexpr int DD_TJ = 1024;
+
+__global__ void __launch_bounds__(DD_TI)
+k_hamming(const uint64_t *__restrict__ h, unsigned long long n, unsigned long long row_begin, unsigned long long row_end,
+          int thr, uint8_t *__restrict__ drop, unsigned long long *__restrict__ hits)
+{
+    __shared__ uint64_t tile[DD_TJ * HASH_WORDS];
+    const unsigned long long i0 = row_begin + (unsigned long long)blockIdx.y * DD_TI;
+    const unsigned long long j0 = (unsigned long long)blockIdx.x * DD_TJ;
+    if (j0 + DD_TJ <= i0 + 1 || i0 >= row_end) return;   // tile entirely at or below the diagonal
+    const unsigned long long jn = (n - j0 < (unsigned long long)DD_TJ) ? n - j0 : DD_TJ;
+    for (unsigned long long k = threadIdx.x; k < jn * HASH_WORDS; k += blockDim.x) tile[k] = h[j0 * HASH_WORDS + k];
+    __syncthreads();
+    const unsigned long long i = i0 + threadIdx.x;
+    const bool live = i < row_end && i < n;
+    uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    if (live) { a0 = h[i * 4]; a1 = h[i * 4 + 1]; a2 = h[i * 4 + 2]; a3 = h[i * 4 + 3]; }
+    unsigned long long found = 0;
+    for (unsigned long long jj = 0; jj < jn; jj++) {
+        const uint64_t *t = tile + jj * HASH_WORDS;
+        int d = __popcll(a0 ^ t[0]);
+        bool cand = live && d <= thr && (j0 + jj) > i;
+        if (__any_sync(0xffffffffu, cand)) {
+            if (cand) {
+                d += __popcll(a1 ^ t[1]) + __popcll(a2 ^ t[2]) + __popcll(a3 ^ t[3]);
+                if (d <= thr) { drop[j0 + jj] = 1; found++; }
+            }
+        }
+    }
+    if (hits && found) atomicAdd(hits, found);
+}
+
+}  // namespace rig

@@ -1,0 +1,231 @@
+// rig_kernels.cuh -- the two sm_100a kernels of the render path.
+//
+//   k_expand  one warp per element: float64 vertex prologue (rotate / translate / wrap copies fused
+//             in), then one lane per polygon edge / stroke segment writes 32-byte draw records.
+//   k_raster  persistent warps; each warp claims bands of 8 canvas rows, keeps the band in shared
+//             memory (3*W*8 bytes, packed RGB), replays the panel's records in draw order with
+//             lanes spread over the iterations that fall inside the band, and hands the finished
+//             band to the TMA engine (cp.async.bulk shared -> global, one contiguous 12 KB write at
+//             W = 512).  Bands no primitive touches are never built: the TMA engine writes them
+//             straight from a constant template held once per CTA, so background pixels cost one
+//             instruction per 12 KB.
+//
+// The roofline that bounds k_raster is HBM write bandwidth: 3*W*H bytes per panel leave the SM
+// exactly once, as full 128-byte lines, and nothing is read back.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "rig_expand.h"
+#include "rig_raster.h"
+
+namespace rig {
+
+constexpr int BAND_ROWS = 8;
+constexpr int EXPAND_WARPS = 8;
+constexpr int CLAIM_BANDS = 4;   // bands claimed per atomic
+
+enum Counter { CTR_REC = 0, CTR_AUX = 1, CTR_OVERFLOW = 2, CTR_WORK = 3, CTR_COUNT = 8 };
+
+struct WarpSync {
+    __device__ __forceinline__ void operator()() const { __syncwarp(); }
+};
+
+__global__ void __launch_bounds__(EXPAND_WARPS * 32)
+k_expand(const DElem *__restrict__ elems, uint32_t e0, uint32_t e1, const ShapeTables *__restrict__ T, int W, int H,
+         ElemHdr *__restrict__ hdrs, Rec *__restrict__ recs, uint32_t rec_cap, Q16 *__restrict__ aux, uint32_t aux_cap,
+         uint32_t *__restrict__ counters)
+{
+    __shared__ ExpandScratch scratch[EXPAND_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t e = e0 + blockIdx.x * EXPAND_WARPS + warp;
+    if (e >= e1) return;
+    const DElem el = elems[e];
+    ExpandScratch &S = scratch[warp];
+    ElemPlan plan = expand_plan<32>(el, *T, W, H, lane, S, WarpSync());
+    uint32_t r0 = 0, a0 = 0;
+    if (lane == 0) {
+        r0 = atomicAdd(&counters[CTR_REC], plan.nrec);
+        a0 = atomicAdd(&counters[CTR_AUX], plan.naux);
+    }
+    r0 = __shfl_sync(0xffffffffu, r0, 0);
+    a0 = __shfl_sync(0xffffffffu, a0, 0);
+    const bool fits = (uint64_t)r0 + plan.nrec <= rec_cap && (uint64_t)a0 + plan.naux <= aux_cap;
+    if (lane == 0) {
+        ElemHdr h;
+        h.rec_begin = r0;
+        h.nrec = fits ? plan.nrec : 0;
+        h.ymin = (int16_t)(fits ? plan.ymin : 1);
+        h.ymax = (int16_t)(fits ? plan.ymax : 0);
+        h.pad = 0;
+        hdrs[e] = h;
+        if (!fits) atomicExch(&counters[CTR_OVERFLOW], 1u);
+    }
+    if (!fits) return;
+    expand_emit<32>(el, plan, *T, W, H, lane, S, recs, r0, aux, a0, WarpSync());
+}
+
+// folds one chunk's counters into the per-render totals: [0] overflow flag, [1] records, [2] aux units
+__global__ void k_collect_overflow(const uint32_t *__restrict__ counters, uint32_t *__restrict__ totals)
+{
+    if (threadIdx.x == 0) {
+        totals[0] |= counters[CTR_OVERFLOW];
+        totals[1] += counters[CTR_REC];
+        totals[2] += counters[CTR_AUX];
+    }
+}
+
+// ---- TMA bulk store helpers (shared::cta -> global) ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                 "cp.async.bulk.commit_group;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct RasterOps {
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ void append(RasterScratch &S, int32_t v) const
+    {
+        int i = atomicAdd(&S.count, 1);
+        if (i < 64) S.cross[i] = v;
+    }
+};
+
+struct RasterParams {
+    const uint32_t *panel_begin;   // [n_panels + 1] element offsets (absolute)
+    const uint8_t *panel_flags;    // [n_panels]
+    const ElemHdr *hdrs;           // indexed by absolute element id
+    const Rec *recs;
+    const Q16 *aux;
+    const ShapeTables *tables;
+    uint8_t *out;                  // image of panel p0 starts at out
+    uint32_t *counters;
+    uint32_t p0, n_panels;         // panels [p0, p0 + n_panels) of the resident scene
+    int W, H, grid_size;
+    uint32_t bg;                   // c0 | c1<<8 | c2<<16
+};
+
+// dynamic shared memory layout: [template plain][template grid][warp bands ...][RasterScratch per warp][filter 64]
+__global__ void __launch_bounds__(512, 1) k_raster(const RasterParams P)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t band_bytes = (uint32_t)(3 * P.W * BAND_ROWS);
+    uint8_t *tmpl0 = smem, *tmpl1 = smem + band_bytes;
+    uint8_t *mine = smem + (size_t)(2 + warp) * band_bytes;
+    RasterScratch *scratch = (RasterScratch *)(smem + (size_t)(2 + nwarps) * band_bytes);
+    uint8_t *filter = (uint8_t *)(scratch + nwarps);
+    RasterScratch &S = scratch[warp];
+
+    // ---- CTA prologue: constant templates + filter table
+    {
+        const uint32_t c0 = P.bg & 0xff, c1 = (P.bg >> 8) & 0xff, c2 = (P.bg >> 16) & 0xff;
+        // 12 bytes = 4 pixels; three 32-bit words repeat
+        const uint32_t w0 = c0 | (c1 << 8) | (c2 << 16) | (c0 << 24);
+        const uint32_t w1 = c1 | (c2 << 8) | (c0 << 16) | (c1 << 24);
+        const uint32_t w2 = c2 | (c0 << 8) | (c1 << 16) | (c2 << 24);
+        uint32_t *t0 = (uint32_t *)tmpl0, *t1 = (uint32_t *)tmpl1;
+        for (uint32_t i = threadIdx.x; i < band_bytes / 4; i += blockDim.x) {
+            uint32_t m = i % 3, v = m == 0 ? w0 : (m == 1 ? w1 : w2);
+            t0[i] = v;
+            t1[i] = v;
+        }
+        if (threadIdx.x < 64) filter[threadIdx.x] = P.tables->filter[threadIdx.x];
+        __syncthreads();
+        for (int g = 1; g < P.grid_size; g++) {
+            int x = dround(ddiv((double)(g * P.W), (double)P.grid_size));
+            if ((unsigned)x < (unsigned)P.W && threadIdx.x < BAND_ROWS) put3(tmpl1 + (threadIdx.x * P.W + x) * 3, 0u);
+        }
+        fence_async_smem();
+        __syncthreads();
+    }
+    // rows of the horizontal grid lines
+    const int bands_per_panel = P.H / BAND_ROWS;
+    const uint32_t total_bands = P.n_panels * (uint32_t)bands_per_panel;
+    bool dirty = false;   // my band buffer has an outstanding bulk read
+    RasterOps ops;
+
+    for (;;) {
+        uint32_t first = 0;
+        if (lane == 0) first = atomicAdd(&P.counters[CTR_WORK], (uint32_t)CLAIM_BANDS);
+        first = __shfl_sync(0xffffffffu, first, 0);
+        if (first >= total_bands) break;
+        for (uint32_t bi = first; bi < first + CLAIM_BANDS && bi < total_bands; bi++) {
+            const uint32_t pl = bi / bands_per_panel, panel = P.p0 + pl;
+            const int band = (int)(bi % bands_per_panel);
+            Band B;
+            B.r0 = band * BAND_ROWS; B.r1 = B.r0 + BAND_ROWS - 1; B.W = P.W; B.H = P.H; B.buf = mine;
+            uint8_t *gdst = P.out + ((size_t)pl * P.H + B.r0) * (size_t)P.W * 3;
+            const uint32_t eb = P.panel_begin[panel], ee = P.panel_begin[panel + 1];
+            const bool use_grid = P.panel_flags[panel] & 1;
+            // ---- is anything drawn into this band?
+            bool any = false;
+            for (uint32_t e = eb + lane; e < ee; e += 32) {
+                ElemHdr h = P.hdrs[e];
+                any |= h.ymin <= B.r1 && h.ymax >= B.r0;
+            }
+            if (use_grid) {
+                for (int g = 1; g < P.grid_size; g++) {
+                    int y = dround(ddiv((double)(g * P.H), (double)P.grid_size));
+                    any |= y >= B.r0 && y <= B.r1;
+                }
+            }
+            any = __any_sync(0xffffffffu, any);
+            if (!any) {
+                if (lane == 0) bulk_store(gdst, use_grid ? tmpl1 : tmpl0, band_bytes);
+                continue;
+            }
+            // ---- build the band in shared memory
+            if (dirty) {
+                if (lane == 0) bulk_wait_read();
+                __syncwarp();
+            }
+            {
+                const uint4 *src = (const uint4 *)tmpl0;
+                uint4 *dst = (uint4 *)mine;
+                for (uint32_t i = lane; i < band_bytes / 16; i += 32) dst[i] = src[i];
+            }
+            __syncwarp();
+            for (uint32_t e = eb; e < ee; e++) {
+                const ElemHdr h = P.hdrs[e];
+                if (h.ymin > B.r1 || h.ymax < B.r0) continue;
+                for (uint32_t base = 0; base < h.nrec; base += 32) {
+                    bool hit = false;
+                    if (base + lane < h.nrec) {
+                        const uint2 hd = *(const uint2 *)&P.recs[h.rec_begin + base + lane];
+                        int ymin = (int16_t)(hd.x >> 16), ymax = (int16_t)(hd.y & 0xffff);
+                        hit = ymin <= B.r1 && ymax >= B.r0;
+                    }
+                    uint32_t m = __ballot_sync(0xffffffffu, hit);
+                    while (m) {
+                        int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint4 *rp = (const uint4 *)&P.recs[h.rec_begin + base + j];
+                        uint4 lo = rp[0], hi = rp[1];
+                        Rec r;
+                        r.w[0] = lo.x; r.w[1] = lo.y; r.w[2] = lo.z; r.w[3] = lo.w;
+                        r.w[4] = hi.x; r.w[5] = hi.y; r.w[6] = hi.z; r.w[7] = hi.w;
+                        exec_record<32>(r, P.aux, filter, B, lane, S, ops);
+                        __syncwarp();
+                    }
+                }
+            }
+            if (use_grid) draw_grid<32>(B, P.grid_size, lane);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) bulk_store(gdst, mine, band_bytes);
+            dirty = true;
+        }
+    }
+    if (lane == 0) bulk_wait_read();
+}
+
+inline size_t raster_smem_bytes(int W, int nwarps)
+{
+    return (size_t)(2 + nwarps) * 3 * W * BAND_ROWS + (size_t)nwarps * sizeof(RasterScratch) + 64;
+}
+
+}  // namespace rig
