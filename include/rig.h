@@ -96,9 +96,15 @@ typedef struct rig_stats {
     uint32_t records;           /* draw records produced by the last render */
     uint32_t aux_units;         /* 16-byte aux units produced by the last render */
     uint32_t overflow;          /* 1 if the last render ran out of record space (result invalid) */
-    uint32_t reserved;
+    uint32_t timed_launches;    /* k_raster launches covered by raster_ms / expand_ms */
+    double expand_ms;           /* summed CUDA-event time of k_expand since rig_set_profiling(ctx, 1) */
+    double raster_ms;           /* summed CUDA-event time of k_raster since rig_set_profiling(ctx, 1) */
+    uint64_t timed_panels;      /* panels rendered by those launches */
 } rig_stats;
 int rig_get_stats(rig_ctx *ctx, rig_stats *out);
+/* on != 0: bracket every k_expand / k_raster launch with CUDA events on the launching stream and sum
+ * their durations (resolved at rig_sync); turning it on resets the sums.                            */
+int rig_set_profiling(rig_ctx *ctx, int on);
 
 /* ---- near-duplicate filter ---------------------------------------------------------------------
  * The reference has no cross-sample duplicate filter (its README mentions one; the code has none --

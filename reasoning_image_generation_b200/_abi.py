@@ -46,14 +46,17 @@ class RigStats(ctypes.Structure):
         ('records', ctypes.c_uint32),
         ('aux_units', ctypes.c_uint32),
         ('overflow', ctypes.c_uint32),
-        ('reserved', ctypes.c_uint32),
+        ('timed_launches', ctypes.c_uint32),
+        ('expand_ms', ctypes.c_double),
+        ('raster_ms', ctypes.c_double),
+        ('timed_panels', ctypes.c_uint64),
     ]
 
 
 # every symbol include/rig.h declares; tests check that the built library exports all of them
 EXPORTS = (
     'rig_create', 'rig_destroy', 'rig_last_error', 'rig_render_batch', 'rig_scene_upload',
-    'rig_render_resident', 'rig_sync', 'rig_get_stats', 'rig_debug_shape_tables',
+    'rig_render_resident', 'rig_sync', 'rig_get_stats', 'rig_set_profiling', 'rig_debug_shape_tables',
     'rig_hash_batch', 'rig_dedup', 'rig_hash_words', 'rig_pinned_alloc', 'rig_pinned_free',
 )
 
@@ -88,6 +91,8 @@ def load() -> ctypes.CDLL:
     lib.rig_sync.restype = ctypes.c_int
     lib.rig_get_stats.argtypes = [vp, ctypes.POINTER(RigStats)]
     lib.rig_get_stats.restype = ctypes.c_int
+    lib.rig_set_profiling.argtypes = [vp, ctypes.c_int]
+    lib.rig_set_profiling.restype = ctypes.c_int
     lib.rig_debug_shape_tables.argtypes = [vp, ctypes.c_size_t]
     lib.rig_debug_shape_tables.restype = ctypes.c_size_t
     lib.rig_hash_words.argtypes = []

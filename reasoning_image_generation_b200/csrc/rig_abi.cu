@@ -59,6 +59,9 @@ struct rig_ctx {
     size_t chunk_panel_limit = 4096;
     rig_stats stats = {};
     bool pending_overflow_check = false;
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool, ev_used;   // profiling events: triples (before expand, between, after raster)
+    std::vector<uint32_t> ev_panels;
     char err[512] = "";
 };
 
@@ -134,16 +137,45 @@ int validate_scene(rig_ctx *c, const rig_scene *s)
     return RIG_OK;
 }
 
+cudaEvent_t prof_event(rig_ctx *c, cudaStream_t st)
+{
+    cudaEvent_t e = nullptr;
+    if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    cudaEventRecord(e, st);
+    c->ev_used.push_back(e);
+    return e;
+}
+
+void resolve_profiling(rig_ctx *c)
+{
+    for (size_t i = 0; i + 2 < c->ev_used.size() + 0 && i / 3 < c->ev_panels.size(); i += 3) {
+        float a = 0, b = 0;
+        if (cudaEventElapsedTime(&a, c->ev_used[i], c->ev_used[i + 1]) == cudaSuccess &&
+            cudaEventElapsedTime(&b, c->ev_used[i + 1], c->ev_used[i + 2]) == cudaSuccess) {
+            c->stats.expand_ms += a;
+            c->stats.raster_ms += b;
+            c->stats.timed_launches++;
+            c->stats.timed_panels += c->ev_panels[i / 3];
+        }
+    }
+    for (cudaEvent_t e : c->ev_used) c->ev_pool.push_back(e);
+    c->ev_used.clear();
+    c->ev_panels.clear();
+}
+
 int launch_chunk(rig_ctx *c, const Chunk &ch, uint8_t *out_dev, cudaStream_t st)
 {
     CK(c, cudaMemsetAsync(c->d_counters, 0, CTR_COUNT * sizeof(uint32_t), st));
     const uint32_t ne = ch.e1 - ch.e0;
+    if (c->profiling) prof_event(c, st);
     if (ne) {
         k_expand<<<(ne + EXPAND_WARPS - 1) / EXPAND_WARPS, EXPAND_WARPS * 32, 0, st>>>(
             c->d_elems, ch.e0, ch.e1, c->d_tables, c->W, c->H, c->d_hdrs, c->d_recs, c->rec_cap, c->d_aux, c->aux_cap,
             c->d_counters);
         c->stats.kernel_launches++;
     }
+    if (c->profiling) prof_event(c, st);
     RasterParams P;
     P.panel_begin = c->d_begin; P.panel_flags = c->d_flags; P.hdrs = c->d_hdrs; P.recs = c->d_recs; P.aux = c->d_aux;
     P.tables = c->d_tables; P.out = out_dev; P.counters = c->d_counters; P.p0 = ch.p0; P.n_panels = ch.p1 - ch.p0;
@@ -153,6 +185,7 @@ int launch_chunk(rig_ctx *c, const Chunk &ch, uint8_t *out_dev, cudaStream_t st)
     const uint32_t grid = std::max(1u, std::min((uint32_t)c->sm_count, want));
     k_raster<<<grid, c->raster_warps * 32, c->raster_smem, st>>>(P);
     c->stats.kernel_launches++;
+    if (c->profiling) { prof_event(c, st); c->ev_panels.push_back(ch.p1 - ch.p0); }
     k_collect_overflow<<<1, 32, 0, st>>>(c->d_counters, c->d_overflow);
     c->stats.kernel_launches++;
     CK(c, cudaGetLastError());
@@ -303,6 +336,8 @@ void rig_destroy(rig_ctx *c)
     cudaFree(c->d_tables); cudaFree(c->d_elems); cudaFreeHost(c->h_elems); cudaFree(c->d_begin); cudaFree(c->d_flags);
     cudaFree(c->d_hdrs); cudaFree(c->d_recs); cudaFree(c->d_aux); cudaFree(c->d_counters); cudaFree(c->d_overflow);
     cudaFree(c->d_stage[0]); cudaFree(c->d_stage[1]); cudaFree(c->d_sums);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_used) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
@@ -334,6 +369,10 @@ int rig_sync(rig_ctx *c)
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
     CK(c, cudaStreamSynchronize(c->copy_stream));
+    if (c->profiling) {
+        CK(c, cudaDeviceSynchronize());
+        resolve_profiling(c);
+    }
     if (c->pending_overflow_check) {
         CK(c, cudaDeviceSynchronize());
         int o = check_overflow(c);
@@ -388,12 +427,25 @@ int rig_render_batch(rig_ctx *c, const rig_scene *scene, uint8_t *out, int out_i
         }
         CK(c, cudaStreamSynchronize(st));
         CK(c, cudaStreamSynchronize(c->copy_stream));
+        if (c->profiling) resolve_profiling(c);
         int o = check_overflow(c);
         if (o < 0) return o;
         if (!o) return RIG_OK;
         c->budget_frac *= 0.5;   // wrap copies made some chunk larger than planned: retry with smaller chunks
     }
     return fail(c, RIG_E_CAPACITY, "draw-record arena overflowed even with single-panel chunks");
+}
+
+int rig_set_profiling(rig_ctx *c, int on)
+{
+    if (!c) return RIG_E_INVALID;
+    c->profiling = on != 0;
+    if (on) {
+        c->stats.expand_ms = c->stats.raster_ms = 0;
+        c->stats.timed_launches = 0;
+        c->stats.timed_panels = 0;
+    }
+    return RIG_OK;
 }
 
 int rig_get_stats(rig_ctx *c, rig_stats *out)

@@ -141,7 +141,11 @@ class Renderer:
         st = _abi.RigStats()
         self._check(self._lib.rig_get_stats(self._h, ctypes.byref(st)))
         return dict(kernel_launches=int(st.kernel_launches), records=int(st.records), aux_units=int(st.aux_units),
-                    overflow=int(st.overflow))
+                    overflow=int(st.overflow), timed_launches=int(st.timed_launches), expand_ms=float(st.expand_ms),
+                    raster_ms=float(st.raster_ms), timed_panels=int(st.timed_panels))
+
+    def set_profiling(self, on: bool):
+        self._check(self._lib.rig_set_profiling(self._h, 1 if on else 0))
 
     # -- near-duplicate filter (device pointers in, device pointers out) --------------------
     def hash_batch(self, imgs_ptr: int, n: int, hashes_ptr: int, layout: str = 'bgr', stream: int = 0):

@@ -1,0 +1,69 @@
+"""The product's per-lane code (csrc/rig_core.h, rig_shapes.h, rig_expand.h, rig_raster.h) compiled for the
+host and run serially (tests/cpu_emul/emul.cpp) against fixtures rendered by the live reference.  This is the
+no-GPU check of the arithmetic the kernels execute; the GPU tests repeat it through librig.so."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import emul_render_scene, restore_rng
+from reasoning_image_generation_b200.scene import SceneBuilder
+from reasoning_image_generation_b200.synth import scene_to_elements, synthetic_scene
+from oracle import ref_render
+
+
+def _scene(c):
+    sb = SceneBuilder(c['W'], c['H'], c['bg'], c['grid_size'])
+    sb.add_panel(c['elements'], c['use_grid'])
+    return sb.finish()
+
+
+@pytest.mark.parametrize('band_rows', [8, 1, 512])
+def test_sequence_goldens_bit_exact(emul_lib, golden_seq, band_rows):
+    panels, pix = golden_seq
+    step = 1 if band_rows == 8 else 4
+    for c, want in list(zip(panels, pix))[::step]:
+        restore_rng(c)
+        rc, out, nrec, err = emul_render_scene(emul_lib, _scene(c), band_rows)
+        assert rc == 0, err
+        assert (out[0] == want).all(), [e['kind'] for e in c['elements']]
+
+
+def test_kind_goldens_bit_exact(emul_lib, golden_kinds):
+    panels, pix = golden_kinds
+    for c, want in zip(panels, pix):
+        restore_rng(c)
+        rc, out, nrec, err = emul_render_scene(emul_lib, _scene(c), 8)
+        assert rc == 0, err
+        assert (out[0] == want).all(), [(e['kind'], e['center'], e['angle']) for e in c['elements']]
+
+
+def test_synthetic_scene_matches_oracle(emul_lib):
+    sc = synthetic_scene(120, seed=5)
+    rc, out, nrec, err = emul_render_scene(emul_lib, sc, 8)
+    assert rc == 0, err
+    be = ref_render.CBackend()
+    for p in range(sc.n_panels):
+        els, ug = scene_to_elements(sc, p)
+        ref = ref_render.render_panel(512, 512, (255, 255, 255), els, ug, 3, backend=be)
+        assert (ref == out[p]).all(), p
+
+
+def test_rgb_layout_is_channel_reversed_bgr(emul_lib):
+    sc = synthetic_scene(6, seed=2)
+    _, bgr, _, _ = emul_render_scene(emul_lib, sc, 8, layout=1)
+    _, rgb, _, _ = emul_render_scene(emul_lib, sc, 8, layout=0)
+    assert (bgr[..., ::-1] == rgb).all()
+
+
+def test_bresenham_closed_form(emul_lib):
+    for dx in range(0, 150):
+        for dy in range(0, dx + 1):
+            assert emul_lib.emul_selftest_line8(dx, dy) == 0, (dx, dy)
+
+
+def test_unsupported_inputs_are_rejected(emul_lib):
+    sb = SceneBuilder()
+    sb.add_panel([dict(kind='square', size=100, fill=True, stroke_width=9, center=(1, 1), angle=0, color=(1, 2, 3))])
+    rc, _, _, err = emul_render_scene(emul_lib, sb.finish(), 8)
+    assert rc == -4 and 'stroke_width' in err

@@ -28,7 +28,7 @@ for p in range(256):
         if bad < 6: print('panel', p, 'differs in', d, 'px', [(e['kind'], e['size'], e['fill'], e['stroke_width'], e['center'], e['angle']) for e in els], ug)
 print('parity: checked', checked, 'bad', bad)
 ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-st = torch.cuda.current_stream().cuda_stream
+ts = torch.cuda.Stream(); torch.cuda.set_stream(ts); st = ts.cuda_stream; assert st != 0
 for rep in range(3):
     r.render_resident(out.data_ptr(), stream=st)
 torch.cuda.synchronize()
@@ -39,6 +39,10 @@ for rep in range(K):
 ev1.record(); torch.cuda.synchronize(); r.sync()
 ms = ev0.elapsed_time(ev1) / K
 print(f'resident render: {ms:.3f} ms per {n} panels -> {n/ms*1e3:.0f} img/s, {n*786432/ms/1e6:.1f} GB/s')
+t0 = time.time()
+for rep in range(K): r.render_resident(out.data_ptr(), stream=st)
+torch.cuda.synchronize(); wall = (time.time() - t0) / K * 1e3
+print(f'  wall-clock cross-check: {wall:.3f} ms')
 # empty scene (pure template stores)
 from reasoning_image_generation_b200.scene import Scene
 emp = Scene(512, 512, (255,255,255), 3, np.zeros(n+1, np.uint32), np.zeros(n, np.uint8), *[np.zeros(0, t) for t in (np.uint8, np.uint8, np.uint8, np.int32, np.int32, np.int32, np.float64, np.float64, np.uint8)])
