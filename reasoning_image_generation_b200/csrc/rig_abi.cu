@@ -37,8 +37,10 @@ struct rig_ctx {
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     ShapeTables *d_tables = nullptr;
     DElem *d_elems = nullptr, *h_elems = nullptr;
-    uint32_t *d_begin = nullptr;
+    uint32_t *d_begin = nullptr, *d_order = nullptr;
     uint8_t *d_flags = nullptr;
+    std::vector<uint32_t> h_order;
+    std::vector<double> panel_cost;
     ElemHdr *d_hdrs = nullptr;
     Rec *d_recs = nullptr;
     Q16 *d_aux = nullptr;
@@ -56,7 +58,7 @@ struct rig_ctx {
     std::vector<uint32_t> nominal_recs, nominal_aux;   // per element, one copy
     std::vector<Chunk> chunks;
     double budget_frac = 0.6;
-    size_t chunk_panel_limit = 4096;
+    size_t chunk_panel_limit = 1u << 20;
     rig_stats stats = {};
     bool pending_overflow_check = false;
     bool profiling = false;
@@ -89,14 +91,14 @@ void nominal_counts(int kind, int fill, int stroke, uint32_t &nrec, uint32_t &na
     const int t = stroke < 1 ? 1 : stroke;
     if (kind == K_CIRCLE) {
         nrec = (fill ? 1 : 0) + ring_recs(MAX_RING_VERTS - 1, t);
-        naux = ring_aux(MAX_RING_VERTS - 1, t);
+        naux = 0;
     } else if (kind == K_CRESCENT) {
         nrec = 1 + 2 * ring_recs(MAX_RING_VERTS - 1, t) + 4;
-        naux = 2 * ring_aux(MAX_RING_VERTS - 1, t);
+        naux = 0;
     } else {
         const int n = kind_nverts(kind), l = kind_loops(kind);
         nrec = l * ((fill ? n + 1 : 0) + n * stroke_recs(t));
-        naux = l * ((fill ? n : 0) + n * stroke_aux(t));
+        naux = l * (fill ? n : 0);
     }
 }
 
@@ -116,6 +118,28 @@ void plan_chunks(rig_ctx *c, size_t panel_limit)
         r += pr; a += pa;
     }
     if ((uint32_t)c->n_panels > p0) c->chunks.push_back({p0, (uint32_t)c->n_panels, c->h_begin[p0], c->h_begin[c->n_panels]});
+    // longest-processing-time-first inside each chunk: the persistent raster warps claim bands in this
+    // order, so the heavy panels start first and the launch does not end on one slow band
+    c->panel_cost.resize(c->n_panels);
+    c->h_order.resize(c->n_panels);
+    for (uint32_t p = 0; p < (uint32_t)c->n_panels; p++) {
+        double pr = 0;
+        for (uint32_t e = c->h_begin[p]; e < c->h_begin[p + 1]; e++) pr += c->nominal_recs[e];
+        c->panel_cost[p] = pr;
+        c->h_order[p] = p;
+    }
+    for (const Chunk &ch : c->chunks)
+        std::stable_sort(c->h_order.begin() + ch.p0, c->h_order.begin() + ch.p1,
+                         [&](uint32_t a, uint32_t b) { return c->panel_cost[a] > c->panel_cost[b]; });
+}
+
+int upload_order(rig_ctx *c, cudaStream_t st)
+{
+    if (c->n_panels) {
+        CK(c, cudaMemcpyAsync(c->d_order, c->h_order.data(), sizeof(uint32_t) * c->n_panels, cudaMemcpyHostToDevice, st));
+        CK(c, cudaStreamSynchronize(st));
+    }
+    return RIG_OK;
 }
 
 int validate_scene(rig_ctx *c, const rig_scene *s)
@@ -177,11 +201,11 @@ int launch_chunk(rig_ctx *c, const Chunk &ch, uint8_t *out_dev, cudaStream_t st)
     }
     if (c->profiling) prof_event(c, st);
     RasterParams P;
-    P.panel_begin = c->d_begin; P.panel_flags = c->d_flags; P.hdrs = c->d_hdrs; P.recs = c->d_recs; P.aux = c->d_aux;
+    P.panel_begin = c->d_begin; P.panel_flags = c->d_flags; P.order = c->d_order; P.hdrs = c->d_hdrs; P.recs = c->d_recs; P.aux = c->d_aux;
     P.tables = c->d_tables; P.out = out_dev; P.counters = c->d_counters; P.p0 = ch.p0; P.n_panels = ch.p1 - ch.p0;
     P.W = c->W; P.H = c->H; P.grid_size = c->grid_size; P.bg = c->bg;
     const uint32_t bands = P.n_panels * (uint32_t)(c->H / BAND_ROWS);
-    const uint32_t want = (bands + CLAIM_BANDS * c->raster_warps - 1) / (CLAIM_BANDS * c->raster_warps);
+    const uint32_t want = (bands + c->raster_warps - 1) / c->raster_warps;
     const uint32_t grid = std::max(1u, std::min((uint32_t)c->sm_count, want));
     k_raster<<<grid, c->raster_warps * 32, c->raster_smem, st>>>(P);
     c->stats.kernel_launches++;
@@ -231,7 +255,7 @@ int upload_scene(rig_ctx *c, const rig_scene *s, int layout, cudaStream_t st)
     CK(c, cudaStreamSynchronize(st));
     c->budget_frac = 0.6;
     plan_chunks(c, c->chunk_panel_limit);
-    return RIG_OK;
+    return upload_order(c, st);
 }
 
 int render_device(rig_ctx *c, uint8_t *out_dev, cudaStream_t st)
@@ -312,11 +336,12 @@ int rig_create(int device, int W, int H, int max_panels, int max_elements, rig_c
     CKC(cudaMallocHost(&c->h_elems, sizeof(DElem) * (size_t)max_elements));
     CKC(cudaMalloc(&c->d_begin, sizeof(uint32_t) * ((size_t)max_panels + 1)));
     CKC(cudaMalloc(&c->d_flags, (size_t)max_panels));
+    CKC(cudaMalloc(&c->d_order, sizeof(uint32_t) * (size_t)max_panels));
     CKC(cudaMalloc(&c->d_hdrs, sizeof(ElemHdr) * (size_t)max_elements));
-    // record arena: large enough for the worst single panel, small enough to stay L2-resident
-    const uint64_t want_rec = std::min<uint64_t>(std::max<uint64_t>((uint64_t)max_elements * 640, 1u << 16), 2u << 20);
+    // record arena: sized so a whole batch is one chunk (one launch tail per batch), capped at 1 GB
+    const uint64_t want_rec = std::min<uint64_t>(std::max<uint64_t>((uint64_t)max_elements * 1100, 1u << 16), 32u << 20);
     c->rec_cap = (uint32_t)want_rec;
-    c->aux_cap = (uint32_t)want_rec;
+    c->aux_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((uint64_t)max_elements * 128, 1u << 16), 16u << 20);
     CKC(cudaMalloc(&c->d_recs, sizeof(Rec) * (size_t)c->rec_cap));
     CKC(cudaMalloc(&c->d_aux, sizeof(Q16) * (size_t)c->aux_cap));
     CKC(cudaMalloc(&c->d_counters, CTR_COUNT * sizeof(uint32_t)));
@@ -333,7 +358,7 @@ void rig_destroy(rig_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-    cudaFree(c->d_tables); cudaFree(c->d_elems); cudaFreeHost(c->h_elems); cudaFree(c->d_begin); cudaFree(c->d_flags);
+    cudaFree(c->d_tables); cudaFree(c->d_elems); cudaFreeHost(c->h_elems); cudaFree(c->d_begin); cudaFree(c->d_order); cudaFree(c->d_flags);
     cudaFree(c->d_hdrs); cudaFree(c->d_recs); cudaFree(c->d_aux); cudaFree(c->d_counters); cudaFree(c->d_overflow);
     cudaFree(c->d_stage[0]); cudaFree(c->d_stage[1]); cudaFree(c->d_sums);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -380,6 +405,8 @@ int rig_sync(rig_ctx *c)
         if (o) {
             c->budget_frac *= 0.5;   // the next rig_render_resident uses smaller chunks
             plan_chunks(c, c->chunk_panel_limit);
+            int rc2 = upload_order(c, c->stream);
+            if (rc2) return rc2;
             return fail(c, RIG_E_CAPACITY, "draw-record arena overflowed (%u records in the render); chunks were halved, render again", c->stats.records);
         }
     }
@@ -412,6 +439,8 @@ int rig_render_batch(rig_ctx *c, const rig_scene *scene, uint8_t *out, int out_i
             c->stage_panels = stage_limit;
         }
         plan_chunks(c, std::min(c->stage_panels, c->chunk_panel_limit));
+        rc = upload_order(c, st);
+        if (rc) return rc;
         CK(c, cudaMemsetAsync(c->d_overflow, 0, 4 * sizeof(uint32_t), st));
         int k = 0;
         for (const Chunk &ch : c->chunks) {

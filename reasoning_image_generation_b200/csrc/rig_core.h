@@ -20,9 +20,13 @@
 
 #if defined(__CUDACC__)
 #define RIG_HD __host__ __device__ __forceinline__
+// the big set-up routines are real functions on the device: inlining them at every call site made
+// k_expand 935 KB of SASS and 59 % of its issue slots instruction-fetch stalls (profiles/r1_notes.md)
+#define RIG_FN static __host__ __device__ __noinline__
 #else
 #include <math.h>
 #define RIG_HD inline
+#define RIG_FN inline
 #endif
 
 namespace rig {
@@ -85,6 +89,19 @@ RIG_HD int dround(double a)
 #endif
 }
 RIG_HD long long dtrunc(double a) { return (long long)a; }
+// n / d truncated toward zero, for |n| < 2^53 and d != 0.  On the device the 64-bit integer divide
+// is a long emulation sequence; the correctly rounded double quotient truncates to the same integer
+// (a non-integer n/d is at least 1/|d| away from an integer, the rounding error is below |n| 2^-53 / |d|).
+RIG_HD long long idiv(long long n, long long d)
+{
+#ifdef __CUDA_ARCH__
+    return (long long)__ddiv_rn((double)n, (double)d);
+#else
+    return n / d;
+#endif
+}
+// x / 65536 and x * 65536 are exact power-of-two scalings
+RIG_HD double dscale_down16(double a) { return dmul(a, 1.0 / 65536.0); }
 
 struct P2L {
     long long x, y;
@@ -108,8 +125,10 @@ enum RecType : uint32_t {
     REC_LINEAA = 2,    // 3-tap filtered line
     REC_DISC = 3,      // filled LINE_8 circle
     REC_CRESCENT = 4,  // disc minus disc
-    REC_CONVEX = 5,    // interior spans of an AA convex polygon (aux: 6 x 16 B)
+    REC_CONVEX = 5,    // interior spans of an AA convex polygon (header + 3 continuation slots)
     REC_POLYFILL = 6,  // even-odd scan fill (aux: nedges x 16 B)
+    REC_CONT = 7,      // continuation slot of the record before it (never selected by the band scan)
+    REC_MINIPOLY = 8,  // small AA convex polygon, outline + interior, gathered per pixel
 };
 
 RIG_HD uint32_t rec_type(const Rec &r) { return r.w[0] & 0xff; }
@@ -136,7 +155,7 @@ RIG_HD void rec_head(Rec &r, uint32_t type, uint32_t flags, int ymin, int ymax, 
 }
 
 // ---- clipLine on 64-bit points (pixel units or 16.16 units) ------------------------------------
-RIG_HD bool clip_line(long long width, long long height, P2L &p1, P2L &p2)
+RIG_FN bool clip_line(long long width, long long height, P2L &p1, P2L &p2)
 {
     long long right = width - 1, bottom = height - 1;
     if (width <= 0 || height <= 0) return false;
@@ -179,7 +198,7 @@ RIG_HD bool clip_line(long long width, long long height, P2L &p1, P2L &p2)
 // ---- LINE8: OpenCV Line()/LineIterator, 8-connected, walked from the left end ------------------
 // record: w2 = u16(x0) | u16(y0)<<16 ; w3 = u16(dx) | u16(dy)<<16 (dx >= dy >= 0, major/minor)
 // flags bit0: y is the major axis; bit1: y decreases along the walk
-RIG_HD Rec make_line8(int W, int H, P2L a, P2L b, uint32_t color)
+RIG_FN Rec make_line8(int W, int H, P2L a, P2L b, uint32_t color)
 {
     P2L p1 = {(int)a.x, (int)a.y}, p2 = {(int)b.x, (int)b.y};
     if ((unsigned long long)p1.x >= (unsigned long long)W || (unsigned long long)p2.x >= (unsigned long long)W ||
@@ -244,27 +263,36 @@ struct AATables {
     uint8_t slope_corr[32];
     uint8_t filter[64];
 };
-// record: flags bit0 = y-major; hi1 = c0 (first major coordinate); w2 = F0 (16.16 minor coord of
-// iteration 0, +0.5 included); w3 = step; w4 = ecount; w5,w6 = 7 x 9-bit end-point gains
-// (ep[1], ep[2], ep[4], ep[5], ep[6], ep[7], ep[8]; ep[0] = 0, ep[3] = ep[1])
-RIG_HD Rec make_lineaa(int W, int H, P2L pt1, P2L pt2, uint32_t color, const uint8_t *slope_corr)
+// loop-invariant state of one LineAA() call (after clipping, end-point swap and slope set-up)
+struct LineAA {
+    int valid;          // 0: clipped away
+    int ymajor;         // 1: one iteration per row, 3 taps along x; 0: one per column, 3 taps along y
+    int c0;             // major coordinate of iteration 0
+    int F0, step;       // 16.16 minor coordinate of iteration 0 (+0.5 included) and its per-iteration step
+    int ecount;         // iterations are k = 0 .. ecount
+    uint64_t ep;        // 7 x 9-bit end-point gains: ep[1], ep[2], ep[4], ep[5], ep[6], ep[7], ep[8] (ep[0]=0, ep[3]=ep[1])
+    int xmin, xmax, ymin, ymax;   // canvas-clipped pixel footprint (inclusive; may be empty)
+};
+RIG_FN LineAA setup_lineaa(int W, int H, P2L pt1, P2L pt2, const uint8_t *slope_corr)
 {
+    LineAA L;
+    L.valid = 0; L.ymajor = 0; L.c0 = 0; L.F0 = 0; L.step = 0; L.ecount = -1; L.ep = 0;
+    L.xmin = L.ymin = 1; L.xmax = L.ymax = 0;
     long long dx, dy, ax, ay, i, j, step;
     int ecount, slope;
-    if (!clip_line((long long)W << XY_SHIFT, (long long)H << XY_SHIFT, pt1, pt2)) return rec_nop();
+    if (!clip_line((long long)W << XY_SHIFT, (long long)H << XY_SHIFT, pt1, pt2)) return L;
     dx = pt2.x - pt1.x;
     dy = pt2.y - pt1.y;
     j = dx < 0 ? -1 : 0;
     ax = (dx ^ j) - j;
     i = dy < 0 ? -1 : 0;
     ay = (dy ^ i) - i;
-    uint32_t flags;
     long long c0, F0;
     if (ax > ay) {
-        flags = 0;
+        L.ymajor = 0;
         dy = (dy ^ j) - j;
         if (j) { P2L t = pt1; pt1 = pt2; pt2 = t; }
-        step = (dy * XY_ONE) / (ax | 1);
+        step = idiv(dy * XY_ONE, ax | 1);
         pt2.x += XY_ONE;
         ecount = (int)((pt2.x >> XY_SHIFT) - (pt1.x >> XY_SHIFT));
         j = -(pt1.x & (XY_ONE - 1));
@@ -276,10 +304,10 @@ RIG_HD Rec make_lineaa(int W, int H, P2L pt1, P2L pt2, uint32_t color, const uin
         c0 = pt1.x >> XY_SHIFT;
         F0 = pt1.y;
     } else {
-        flags = 1;
+        L.ymajor = 1;
         dx = (dx ^ i) - i;
         if (i) { P2L t = pt1; pt1 = pt2; pt2 = t; }
-        step = (dx * XY_ONE) / (ay | 1);
+        step = idiv(dx * XY_ONE, ay | 1);
         pt2.y += XY_ONE;
         ecount = (int)((pt2.y >> XY_SHIFT) - (pt1.y >> XY_SHIFT));
         j = -(pt1.y & (XY_ONE - 1));
@@ -303,50 +331,63 @@ RIG_HD Rec make_lineaa(int W, int H, P2L pt1, P2L pt2, uint32_t color, const uin
     uint32_t ep6 = (t2 >> 8) & 0x1ff;
     uint32_t ep7 = ((t2 + t0) >> 8) & 0x1ff;
     uint32_t ep8 = (uint32_t)slope;
-    uint64_t ep = (uint64_t)ep1 | ((uint64_t)ep2 << 9) | ((uint64_t)ep4 << 18) | ((uint64_t)ep5 << 27) |
-                  ((uint64_t)ep6 << 36) | ((uint64_t)ep7 << 45) | ((uint64_t)ep8 << 54);
-    int ymin, ymax;
-    if (flags & 1) {
-        ymin = (int)c0;
-        ymax = (int)c0 + ecount;
-    } else {
-        int ya = (int)(F0 >> XY_SHIFT) - 1;
-        int yb = (int)((F0 + (long long)ecount * step) >> XY_SHIFT) - 1;
-        ymin = ya < yb ? ya : yb;
-        ymax = (ya < yb ? yb : ya) + 2;
-    }
+    L.ep = (uint64_t)ep1 | ((uint64_t)ep2 << 9) | ((uint64_t)ep4 << 18) | ((uint64_t)ep5 << 27) |
+           ((uint64_t)ep6 << 36) | ((uint64_t)ep7 << 45) | ((uint64_t)ep8 << 54);
+    L.valid = 1;
+    L.c0 = (int)c0; L.F0 = (int)F0; L.step = (int)step; L.ecount = ecount;
+    // footprint: major c0..c0+ecount, minor (pos>>16)-1 .. +1 (pos is monotone in k)
+    int ma = (int)(F0 >> XY_SHIFT) - 1;
+    int mb = (int)((F0 + (long long)ecount * step) >> XY_SHIFT) - 1;
+    int mlo = ma < mb ? ma : mb, mhi = (ma < mb ? mb : ma) + 2;
+    int jlo = (int)c0, jhi = (int)c0 + ecount;
+    if (L.ymajor) { L.ymin = jlo; L.ymax = jhi; L.xmin = mlo; L.xmax = mhi; }
+    else          { L.xmin = jlo; L.xmax = jhi; L.ymin = mlo; L.ymax = mhi; }
+    if (L.xmin < 0) L.xmin = 0;
+    if (L.ymin < 0) L.ymin = 0;
+    if (L.xmax > W - 1) L.xmax = W - 1;
+    if (L.ymax > H - 1) L.ymax = H - 1;
+    return L;
+}
+// stand-alone record: flags bit0 = y-major; hi1 = c0; w2 = F0; w3 = step; w4 = ecount; w5,w6 = ep
+RIG_HD Rec pack_lineaa(const LineAA &L, uint32_t color, int H)
+{
     Rec r = rec_nop();
-    rec_head(r, REC_LINEAA, flags, ymin, ymax, (int)c0, color, H);
-    r.w[2] = (uint32_t)(int32_t)F0;
-    r.w[3] = (uint32_t)(int32_t)step;
-    r.w[4] = (uint32_t)ecount;
-    r.w[5] = (uint32_t)ep;
-    r.w[6] = (uint32_t)(ep >> 32);
+    if (!L.valid) return r;
+    rec_head(r, REC_LINEAA, (uint32_t)L.ymajor, L.ymin, L.ymax, L.c0, color, H);
+    r.w[2] = (uint32_t)L.F0;
+    r.w[3] = (uint32_t)L.step;
+    r.w[4] = (uint32_t)L.ecount;
+    r.w[5] = (uint32_t)L.ep;
+    r.w[6] = (uint32_t)(L.ep >> 32);
     return r;
 }
-struct LineAA {
-    int ymajor, c0, F0, step, ecount;
-    uint64_t ep;
-};
+RIG_HD Rec make_lineaa(int W, int H, P2L pt1, P2L pt2, uint32_t color, const uint8_t *slope_corr)
+{
+    return pack_lineaa(setup_lineaa(W, H, pt1, pt2, slope_corr), color, H);
+}
 RIG_HD LineAA lineaa_unpack(const Rec &r)
 {
     LineAA l;
+    l.valid = 1;
     l.ymajor = rec_flags(r) & 1;
     l.c0 = rec_hi1(r);
     l.F0 = (int32_t)r.w[2];
     l.step = (int32_t)r.w[3];
     l.ecount = (int)r.w[4];
     l.ep = (uint64_t)r.w[5] | ((uint64_t)r.w[6] << 32);
+    l.xmin = l.ymin = 0; l.xmax = l.ymax = 0;
     return l;
 }
 RIG_HD int lineaa_ep(const LineAA &l, int k)
 {
-    int sc = k, ec = l.ecount - k;
-    int idx = (((sc >= 2) + 1) & (sc | 2)) * 3 + (((ec >= 2) + 1) & (ec | 2));
-    // idx: 0 1 2 3 4 5 6 7 8  -> packed slot: -,0,1,0,2,3,4,5,6
-    if (idx == 0) return 0;
+    // ep_table[3 * s + e], s/e = min(count, 2) from the start / end of the line
+    int s = k < 2 ? k : 2, e = l.ecount - k;
+    e = e < 2 ? e : 2;
+    int idx = 3 * s + e;
+    // idx: 0 1 2 3 4 5 6 7 8  -> packed field: -,0,1,0,2,3,4,5,6
     int slot = idx == 3 ? 0 : (idx < 3 ? idx - 1 : idx - 2);
-    return (int)((l.ep >> (9 * slot)) & 0x1ff);
+    int v = (int)((l.ep >> (9 * (slot < 0 ? 0 : slot))) & 0x1ff);
+    return idx == 0 ? 0 : v;
 }
 // iteration k: major coordinate, first minor coordinate of the 3 taps, and the 3 blend weights
 RIG_HD void lineaa_eval(const LineAA &l, int k, const uint8_t *filter, int &major, int &minor0, int &a0, int &a1, int &a2)
@@ -360,6 +401,18 @@ RIG_HD void lineaa_eval(const LineAA &l, int k, const uint8_t *filter, int &majo
     a1 = (ep * filter[dist] >> 8) & 0xff;
     a2 = (ep * filter[63 - dist] >> 8) & 0xff;
 }
+// blend weight this line applies to pixel (x, y), or -1 when it does not touch it (gather form)
+RIG_HD int lineaa_at(const LineAA &l, int x, int y, const uint8_t *filter)
+{
+    int k = (l.ymajor ? y : x) - l.c0;
+    if (k < 0 || k > l.ecount) return -1;
+    int pos = l.F0 + k * l.step;
+    int d = (l.ymajor ? x : y) - ((pos >> XY_SHIFT) - 1);
+    if ((unsigned)d > 2u) return -1;
+    int dist = (pos >> (XY_SHIFT - 5)) & 31;
+    int fi = d == 0 ? dist + 32 : (d == 1 ? dist : 63 - dist);
+    return (lineaa_ep(l, k) * filter[fi] >> 8) & 0xff;
+}
 RIG_HD int floor_div(int a, int b)  // b > 0
 {
     int q = a / b;
@@ -372,6 +425,8 @@ RIG_HD void lineaa_krange(const LineAA &l, int r0, int r1, int &k0, int &k1)
     if (l.ymajor) {
         k0 = r0 - l.c0;
         k1 = r1 - l.c0;
+    } else if (l.ecount < 32) {
+        k0 = 0; k1 = l.ecount;          // one pass anyway: the taps are row-tested individually
     } else {
         // need (pos>>16)-1 <= r1 and (pos>>16)+1 >= r0  <=>  lo <= pos <= hi
         int lo = (r0 - 1) << XY_SHIFT, hi = ((r1 + 2) << XY_SHIFT) - 1;
@@ -396,23 +451,23 @@ RIG_HD int blend1(int v, int c, int a)
     return v;
 }
 
-// ---- CONVEX: interior spans of FillConvexPoly(line_type = LINE_AA, shift = 16) ------------------
+// ---- interior of FillConvexPoly(line_type = LINE_AA, shift = 16) --------------------------------
 // The two-edge walk is replayed once at setup; what is kept per side is the list of
 // (first row, x at that row, dx per row) pieces, so a row's span is a closed form.
-// aux (6 x uint4 = 96 B): int32 x[8]; int32 dx[8]; int16 y[8]; pad   -- side s uses entries 4s..4s+3
-struct ConvexAux {
-    int32_t x[8];
-    int32_t dx[8];
-    int16_t y[8];
-    int16_t pad[8];
+struct ConvexChains {
+    int valid;
+    int ymin, ylast;        // rows ymin..ylast are filled (ymin may be negative)
+    int nseg[2];
+    int32_t x[8], dx[8];    // side s uses entries 4s .. 4s+3
+    int32_t y[8];
 };
-// record: w2 = aux offset (in uint4 units, relative to the aux arena); w3 = nseg0 | nseg1<<8
-// returns false (and a NOP record) when there is nothing to fill
-RIG_HD bool make_convex(int W, int H, const P2L *v, int npts, uint32_t color, uint32_t aux_off, Rec &rec, ConvexAux &aux)
+RIG_FN ConvexChains setup_convex(int W, int H, const P2L *v, int npts)
 {
     const int shift = XY_SHIFT;
     const int delta = 1 << shift >> 1;
-    rec = rec_nop();
+    ConvexChains C;
+    C.valid = 0; C.ymin = 1; C.ylast = 0; C.nseg[0] = C.nseg[1] = 0;
+    for (int i = 0; i < 8; i++) { C.x[i] = 0; C.dx[i] = 0; C.y[i] = 0; }
     long long xmin = v[0].x, xmax = v[0].x, ymin = v[0].y, ymax = v[0].y;
     int imin = 0;
     for (int i = 0; i < npts; i++) {
@@ -425,7 +480,7 @@ RIG_HD bool make_convex(int W, int H, const P2L *v, int npts, uint32_t color, ui
     xmax = (xmax + delta) >> shift;
     ymin = (ymin + delta) >> shift;
     ymax = (ymax + delta) >> shift;
-    if (npts < 3 || (int)xmax < 0 || (int)ymax < 0 || (int)xmin >= W || (int)ymin >= H) return false;
+    if (npts < 3 || (int)xmax < 0 || (int)ymax < 0 || (int)xmin >= W || (int)ymin >= H) return C;
     if (ymax > H - 1) ymax = H - 1;
 
     struct { int idx, di; long long x, dx; int ye; } edge[2];
@@ -437,10 +492,7 @@ RIG_HD bool make_convex(int W, int H, const P2L *v, int npts, uint32_t color, ui
     edge[1].di = npts - 1;
     edge[0].x = edge[1].x = -XY_ONE;
     edge[0].dx = edge[1].dx = 0;
-    int nseg[2] = {0, 0};
     int ylast = y - 1;
-    for (int i = 0; i < 8; i++) { aux.x[i] = 0; aux.dx[i] = 0; aux.y[i] = 0; aux.pad[i] = 0; }
-
     do {
         if (y < (int)ymax || y == (int)ymin) {
             for (int i = 0; i < 2; i++) {
@@ -453,14 +505,14 @@ RIG_HD bool make_convex(int W, int H, const P2L *v, int npts, uint32_t color, ui
                         if (ty > y) {
                             long long xs = v[idx0].x, xe = v[idx].x;
                             edge[i].ye = ty;
-                            edge[i].dx = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y));
+                            edge[i].dx = idiv((xe - xs) * 2 + (ty - y), 2 * (ty - y));
                             edge[i].x = xs;
                             edge[i].idx = idx;
-                            if (nseg[i] < 4) {
-                                aux.x[4 * i + nseg[i]] = (int32_t)edge[i].x;
-                                aux.dx[4 * i + nseg[i]] = (int32_t)edge[i].dx;
-                                aux.y[4 * i + nseg[i]] = (int16_t)y;
-                                nseg[i]++;
+                            if (C.nseg[i] < 4) {
+                                C.x[4 * i + C.nseg[i]] = (int32_t)edge[i].x;
+                                C.dx[4 * i + C.nseg[i]] = (int32_t)edge[i].dx;
+                                C.y[4 * i + C.nseg[i]] = y;
+                                C.nseg[i]++;
                             }
                             break;
                         }
@@ -472,7 +524,6 @@ RIG_HD bool make_convex(int W, int H, const P2L *v, int npts, uint32_t color, ui
             }
         }
         if (edges < 0) break;
-        ylast = y;
         // jump to the next row at which a side may be re-initialised
         int ynext = edge[0].ye < edge[1].ye ? edge[0].ye : edge[1].ye;
         if (ynext <= y) ynext = y + 1;
@@ -484,20 +535,25 @@ RIG_HD bool make_convex(int W, int H, const P2L *v, int npts, uint32_t color, ui
         y = ynext;
     } while (y <= (int)ymax);
 
-    if (ylast < (int)ymin || nseg[0] == 0 || nseg[1] == 0) return false;
-    rec_head(rec, REC_CONVEX, 0, (int)ymin, ylast, 0, color, H);
-    rec.w[2] = aux_off;
-    rec.w[3] = (uint32_t)nseg[0] | ((uint32_t)nseg[1] << 8);
-    return true;
+    if (ylast < (int)ymin || C.nseg[0] == 0 || C.nseg[1] == 0) return C;
+    C.valid = 1;
+    C.ymin = (int)ymin;
+    C.ylast = ylast;
+    return C;
 }
 // span of row y (inclusive pixel range, already clipped; x1 > x2 means empty)
-RIG_HD void convex_span(const ConvexAux &a, int nseg0, int nseg1, int y, int W, int &x1, int &x2)
+RIG_HD long long convex_side_x(const ConvexChains &a, int side, int y)
 {
-    int s0 = 0, s1 = 0;
-    for (int i = 1; i < nseg0; i++) if (y >= a.y[i]) s0 = i;
-    for (int i = 1; i < nseg1; i++) if (y >= a.y[4 + i]) s1 = i;
-    long long xa = (long long)a.x[s0] + (long long)(y - a.y[s0]) * a.dx[s0];
-    long long xb = (long long)a.x[4 + s1] + (long long)(y - a.y[4 + s1]) * a.dx[4 + s1];
+    const int o = 4 * side, n = a.nseg[side];
+    int32_t sx = a.x[o], sdx = a.dx[o], sy = a.y[o];
+    if (n > 1 && y >= a.y[o + 1]) { sx = a.x[o + 1]; sdx = a.dx[o + 1]; sy = a.y[o + 1]; }
+    if (n > 2 && y >= a.y[o + 2]) { sx = a.x[o + 2]; sdx = a.dx[o + 2]; sy = a.y[o + 2]; }
+    if (n > 3 && y >= a.y[o + 3]) { sx = a.x[o + 3]; sdx = a.dx[o + 3]; sy = a.y[o + 3]; }
+    return (long long)sx + (long long)(y - sy) * sdx;
+}
+RIG_HD void convex_span(const ConvexChains &a, int y, int W, int &x1, int &x2)
+{
+    long long xa = convex_side_x(a, 0, y), xb = convex_side_x(a, 1, y);
     long long xl = xa > xb ? xb : xa, xr = xa > xb ? xa : xb;
     x1 = (int)((xl + (XY_ONE - 1)) >> XY_SHIFT);
     x2 = (int)(xr >> XY_SHIFT);
@@ -508,6 +564,146 @@ RIG_HD void convex_span(const ConvexAux &a, int nseg0, int nseg1, int y, int W, 
         x1 = 1; x2 = 0;
     }
 }
+// REC_CONVEX: header slot + 3 continuation slots (quads: at most 3 pieces per side)
+//   header: w2 = nseg0 | nseg1 << 8
+//   cont 1: w2..w7 = x[0..2], x[4..6]      cont 2: w2..w7 = dx[0..2], dx[4..6]
+//   cont 3: w2..w4 = y packed as int16 pairs (y0|y1<<16, y2|y4<<16, y5|y6<<16)
+constexpr int CONVEX_SLOTS = 4;
+RIG_HD Rec rec_cont()
+{
+    Rec r = rec_nop();
+    r.w[0] = 7u /* REC_CONT */ | (1u << 16);
+    return r;
+}
+RIG_FN void pack_convex(const ConvexChains &C, uint32_t color, int H, Rec *out)
+{
+    out[0] = rec_nop();
+    for (int i = 1; i < CONVEX_SLOTS; i++) out[i] = rec_cont();
+    if (!C.valid || C.nseg[0] > 3 || C.nseg[1] > 3) return;
+    rec_head(out[0], REC_CONVEX, 0, C.ymin, C.ylast, 0, color, H);
+    out[0].w[2] = (uint32_t)C.nseg[0] | ((uint32_t)C.nseg[1] << 8);
+    for (int i = 0; i < 3; i++) {
+        out[1].w[2 + i] = (uint32_t)C.x[i];  out[1].w[5 + i] = (uint32_t)C.x[4 + i];
+        out[2].w[2 + i] = (uint32_t)C.dx[i]; out[2].w[5 + i] = (uint32_t)C.dx[4 + i];
+    }
+    const int ys[6] = {C.y[0], C.y[1], C.y[2], C.y[4], C.y[5], C.y[6]};
+    for (int i = 0; i < 3; i++)
+        out[3].w[2 + i] = (uint32_t)(uint16_t)(int16_t)ys[2 * i] | ((uint32_t)(uint16_t)(int16_t)ys[2 * i + 1] << 16);
+}
+RIG_HD ConvexChains unpack_convex(const Rec &h, const Rec &c1, const Rec &c2, const Rec &c3)
+{
+    ConvexChains C;
+    C.valid = 1;
+    C.ymin = rec_ymin(h); C.ylast = rec_ymax(h);
+    C.nseg[0] = h.w[2] & 0xff; C.nseg[1] = (h.w[2] >> 8) & 0xff;
+    for (int i = 0; i < 8; i++) { C.x[i] = 0; C.dx[i] = 0; C.y[i] = 0; }
+    for (int i = 0; i < 3; i++) {
+        C.x[i] = (int32_t)c1.w[2 + i];  C.x[4 + i] = (int32_t)c1.w[5 + i];
+        C.dx[i] = (int32_t)c2.w[2 + i]; C.dx[4 + i] = (int32_t)c2.w[5 + i];
+    }
+    C.y[0] = (int16_t)(c3.w[2] & 0xffff); C.y[1] = (int16_t)(c3.w[2] >> 16);
+    C.y[2] = (int16_t)(c3.w[3] & 0xffff); C.y[4] = (int16_t)(c3.w[3] >> 16);
+    C.y[5] = (int16_t)(c3.w[4] & 0xffff); C.y[6] = (int16_t)(c3.w[4] >> 16);
+    return C;
+}
+
+// ---- MINIPOLY: a whole small AA convex polygon (outline + interior) as one gather step ---------
+// For polygons whose footprint fits a 12 x 12 pixel box (stroke end caps, short stroke quads) the
+// warp does not replay the edges one after another; each lane takes one pixel of the box and applies,
+// in OpenCV's order, every edge's blend that lands on it and finally the interior fill.
+//   header : flags = number of edges; hi1 = x0; w2 = u16(y0) | w << 16 | h << 24
+//   edge e : cont slot 1+e: w2 = F0, w3 = step, w4,w5 = ep, w6 = u16(c0) | (ecount & 0xff) << 16 | ymajor << 24 | valid << 25
+//   spans  : cont slot 1+nedges: 12 rows x (x1, x2) as uint8 offsets from x0 (x1 > x2: empty), bytes of w2..w7
+constexpr int MINI_MAX = 12;
+constexpr int MINI_MAX_EDGES = 5;
+RIG_HD int minipoly_slots(int nedges) { return nedges + 2; }
+RIG_HD void pack_edge_slot(const LineAA &L, Rec &s)
+{
+    s = rec_cont();
+    s.w[2] = (uint32_t)L.F0;
+    s.w[3] = (uint32_t)L.step;
+    s.w[4] = (uint32_t)L.ep;
+    s.w[5] = (uint32_t)(L.ep >> 32);
+    s.w[6] = (uint32_t)(uint16_t)(int16_t)L.c0 | ((uint32_t)(L.ecount & 0xff) << 16) | ((uint32_t)(L.ymajor & 1) << 24) |
+             ((uint32_t)(L.valid && L.ecount >= 0 ? 1 : 0) << 25);
+}
+RIG_HD LineAA unpack_edge_slot(const Rec &s)
+{
+    LineAA l;
+    l.F0 = (int32_t)s.w[2];
+    l.step = (int32_t)s.w[3];
+    l.ep = (uint64_t)s.w[4] | ((uint64_t)s.w[5] << 32);
+    l.c0 = (int16_t)(s.w[6] & 0xffff);
+    l.ecount = (int)((s.w[6] >> 16) & 0xff);
+    l.ymajor = (int)((s.w[6] >> 24) & 1);
+    l.valid = (int)((s.w[6] >> 25) & 1);
+    if (!l.valid) l.ecount = -1;
+    l.xmin = l.ymin = 0; l.xmax = l.ymax = 0;
+    return l;
+}
+// Tries to express the AA convex polygon v[0..n) as a MINIPOLY at out[0 .. n+2).  Returns false (and
+// writes nothing) when its footprint is larger than the box or an edge is too long for the packing.
+RIG_FN bool pack_minipoly(int W, int H, const LineAA *E, int n, const ConvexChains &C, uint32_t color, Rec *out)
+{
+    if (n > MINI_MAX_EDGES) return false;
+    // the outline's footprint contains the interior, so it alone decides whether the box is small
+    int xmin = 1 << 30, xmax = -(1 << 30), ymin = 1 << 30, ymax = -(1 << 30);
+    for (int e = 0; e < n; e++) {
+        if (!E[e].valid) continue;
+        if (E[e].ecount > 255 || E[e].c0 < -32768 || E[e].c0 > 32767) return false;
+        if (E[e].xmin > E[e].xmax || E[e].ymin > E[e].ymax) continue;
+        if (E[e].xmin < xmin) xmin = E[e].xmin;
+        if (E[e].xmax > xmax) xmax = E[e].xmax;
+        if (E[e].ymin < ymin) ymin = E[e].ymin;
+        if (E[e].ymax > ymax) ymax = E[e].ymax;
+    }
+    int fy0 = 1, fy1 = 0;
+    if (C.valid) {
+        fy0 = C.ymin < 0 ? 0 : C.ymin;
+        fy1 = C.ylast > H - 1 ? H - 1 : C.ylast;
+        if (fy0 <= fy1) {
+            if (fy0 < ymin) ymin = fy0;
+            if (fy1 > ymax) ymax = fy1;
+        }
+    }
+    if (ymin <= ymax && (ymax - ymin + 1 > MINI_MAX || (xmin <= xmax && xmax - xmin + 1 > MINI_MAX))) return false;
+    // interior spans of the (at most MINI_MAX) rows, evaluated once
+    int sx1[MINI_MAX], sx2[MINI_MAX];
+#pragma unroll
+    for (int r = 0; r < MINI_MAX; r++) {
+        sx1[r] = 1; sx2[r] = 0;
+        const int y = ymin + r;
+        if (C.valid && ymin <= ymax && y >= fy0 && y <= fy1 && y <= ymax) {
+            convex_span(C, y, W, sx1[r], sx2[r]);
+            if (sx1[r] <= sx2[r]) {
+                if (sx1[r] < xmin) xmin = sx1[r];
+                if (sx2[r] > xmax) xmax = sx2[r];
+            }
+        }
+    }
+    if (xmin > xmax || ymin > ymax) {      // nothing visible: an empty record keeps the slot layout
+        out[0] = rec_nop();
+        for (int i = 1; i < minipoly_slots(n); i++) out[i] = rec_cont();
+        return true;
+    }
+    const int w = xmax - xmin + 1, h = ymax - ymin + 1;
+    if (w > MINI_MAX || h > MINI_MAX) return false;
+    out[0] = rec_nop();
+    rec_head(out[0], REC_MINIPOLY, (uint32_t)n, ymin, ymax, xmin, color, H);
+    out[0].w[2] = (uint32_t)(uint16_t)(int16_t)ymin | ((uint32_t)w << 16) | ((uint32_t)h << 24);
+    for (int e = 0; e < n; e++) pack_edge_slot(E[e], out[1 + e]);
+    Rec &sp = out[1 + n];
+    sp = rec_cont();
+    uint32_t words[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < MINI_MAX; r++) {
+        uint32_t b1 = 1, b2 = 0;
+        if (sx1[r] <= sx2[r]) { b1 = (uint32_t)(sx1[r] - xmin); b2 = (uint32_t)(sx2[r] - xmin); }
+        words[r >> 1] |= (b1 | (b2 << 8)) << ((r & 1) * 16);
+    }
+    for (int i = 0; i < 6; i++) sp.w[2 + i] = words[i];
+    return true;
+}
 
 // ---- POLYFILL: one scan edge of fillPoly (LINE_8, shift 0) --------------------------------------
 // aux entry (16 B): int16 y0, int16 y1, int32 x, int32 dx, int32 valid
@@ -517,7 +713,7 @@ struct PolyEdge {
     int32_t valid;
 };
 // pt0 -> pt1 are consecutive integer vertices; also returns the boundary LINE8 record
-RIG_HD PolyEdge make_polyedge(int W, int H, P2L pt0, P2L pt1, uint32_t color, Rec &boundary)
+RIG_FN PolyEdge make_polyedge(int W, int H, P2L pt0, P2L pt1, uint32_t color, Rec &boundary)
 {
     PolyEdge e;
     e.valid = 0; e.y0 = e.y1 = 0; e.x = e.dx = 0;
@@ -533,7 +729,7 @@ RIG_HD PolyEdge make_polyedge(int W, int H, P2L pt0, P2L pt1, uint32_t color, Re
         x1 = b.x << XY_SHIFT;
     }
     if (pt0.y == pt1.y) return e;
-    long long dx = (x1 - x0) / (cy1 - cy0);
+    long long dx = idiv(x1 - x0, cy1 - cy0);
     long long x;
     if (pt0.y < pt1.y) { e.y0 = (int16_t)pt0.y; e.y1 = (int16_t)pt1.y; x = x0 + (pt0.y - cy0) * dx; }
     else               { e.y0 = (int16_t)pt1.y; e.y1 = (int16_t)pt0.y; x = x1 + (pt1.y - cy1) * dx; }
@@ -578,14 +774,15 @@ RIG_HD Rec make_crescent(int H, int cx, int cy, int r, int icx, int icy, int ir,
 }
 
 // ---- ThickLine(thickness > 1, LINE_AA): quad + end caps -----------------------------------------
-// A thick AA segment is: 4 LINEAA (quad outline) + CONVEX (quad interior) and, per cap, 5 LINEAA +
-// CONVEX (EllipseEx of "radius" thickness/2 is a 90-degree-step polygon = a diamond for t <= 5).
-constexpr int RECS_PER_QUAD = 5;
-constexpr int RECS_PER_CAP = 6;
-constexpr int AUX_PER_CONVEX = 6;  // uint4 units
+// A thick AA segment is FillConvexPoly(quad) followed, per cap, by FillConvexPoly(EllipseEx polygon of
+// "radius" thickness/2 = a 90-degree-step diamond for thickness <= 4).  Slot budget (fixed, so that
+// segment i of a polyline always starts at a closed-form offset):
+//   quad : QUAD_SLOTS = 8   either 4 LINEAA + CONVEX(4)  or  MINIPOLY(4 edges) = 6 slots + 2 unused
+//   cap  : CAP_SLOTS  = 7   MINIPOLY(5 edges)
+constexpr int QUAD_SLOTS = 8;
+constexpr int CAP_SLOTS = 7;
 
-// SinTable entries used by the 90-degree ellipse: cos/sin at 0,90,180,270,360 as OpenCV's float table
-RIG_HD void cap_polygon(P2L c, long long rad, const float *sin_tab, P2L *v, int &nv)
+RIG_FN void cap_polygon(P2L c, long long rad, const float *sin_tab, P2L *v, int &nv)
 {
     // EllipseEx(center c, axes (rad,rad), angle 0, 0..360), delta = 90 for rad < 3 px
     P2L prev = {-1, -1};
@@ -597,8 +794,8 @@ RIG_HD void cap_polygon(P2L c, long long rad, const float *sin_tab, P2L *v, int 
         double px = dsub(dadd((double)c.x, dmul(x, 1.0)), dmul(y, 0.0));
         double py = dadd(dadd((double)c.y, dmul(x, 0.0)), dmul(y, 1.0));
         P2L pt;
-        pt.x = (long long)dround(ddiv(px, (double)XY_ONE)) * XY_ONE;
-        pt.y = (long long)dround(ddiv(py, (double)XY_ONE)) * XY_ONE;
+        pt.x = (long long)dround(dscale_down16(px)) * XY_ONE;
+        pt.y = (long long)dround(dscale_down16(py)) * XY_ONE;
         pt.x += dround(dsub(px, (double)pt.x));
         pt.y += dround(dsub(py, (double)pt.y));
         if (pt.x != prev.x || pt.y != prev.y) { v[nv++] = pt; prev = pt; }
@@ -606,25 +803,31 @@ RIG_HD void cap_polygon(P2L c, long long rad, const float *sin_tab, P2L *v, int 
     if (nv <= 1) { v[0] = v[1] = c; nv = 2; }
 }
 
-// Emits the records of one AA convex polygon (outline LINEAAs, then the interior) at out[0..n]
-RIG_HD void emit_convex_aa(int W, int H, const P2L *v, int n, uint32_t color, const uint8_t *slope_corr,
-                           Rec *out, uint32_t aux_off, ConvexAux *aux)
+// Records of one AA convex polygon (n <= 5 vertices) into out[0 .. budget): a MINIPOLY when it is small,
+// else (n == 4 only) 4 LINEAA + CONVEX.  Unused slots become NOPs.
+RIG_FN void emit_convex_aa(int W, int H, const P2L *v, int n, uint32_t color, const uint8_t *slope_corr, Rec *out, int budget)
 {
+    for (int i = 0; i < budget; i++) out[i] = rec_nop();
+    LineAA E[MINI_MAX_EDGES];
     P2L p0 = v[n - 1];
     for (int i = 0; i < n; i++) {
-        out[i] = make_lineaa(W, H, p0, v[i], color, slope_corr);
+        E[i] = setup_lineaa(W, H, p0, v[i], slope_corr);
         p0 = v[i];
     }
-    make_convex(W, H, v, n, color, aux_off, out[n], *aux);
+    ConvexChains C = setup_convex(W, H, v, n);
+    if (minipoly_slots(n) <= budget && pack_minipoly(W, H, E, n, C, color, out)) return;
+    if (n + CONVEX_SLOTS <= budget) {
+        for (int i = 0; i < n; i++) out[i] = pack_lineaa(E[i], color, H);
+        pack_convex(C, color, H, out + n);
+    }
 }
 
 // One ThickLine call.  p0,p1 in `shift` fractional bits (0 for polylines, 16 for circle arcs).
 // flags bit0: cap at p0, bit1: cap at p1.  Writes exactly
-//   thickness <= 1 : 1 record
-//   thickness  > 1 : RECS_PER_QUAD + RECS_PER_CAP * popcount(flags) records (+ AUX_PER_CONVEX aux each CONVEX)
-// (unused slots are NOPs) and returns the number of records written.
-RIG_HD int emit_thick_line(int W, int H, P2L p0, P2L p1, int thickness, int flags, int shift, uint32_t color,
-                           const uint8_t *slope_corr, const float *sin_tab, Rec *out, uint32_t aux_off, ConvexAux *aux)
+//   thickness <= 1 : 1 slot
+//   thickness  > 1 : QUAD_SLOTS + CAP_SLOTS * popcount(flags) slots
+RIG_FN int emit_thick_line(int W, int H, P2L p0, P2L p1, int thickness, int flags, int shift, uint32_t color,
+                           const uint8_t *slope_corr, const float *sin_tab, Rec *out)
 {
     if (thickness <= 1) {
         p0.x <<= XY_SHIFT - shift; p0.y <<= XY_SHIFT - shift;
@@ -633,7 +836,7 @@ RIG_HD int emit_thick_line(int W, int H, P2L p0, P2L p1, int thickness, int flag
         return 1;
     }
     int ncap = (flags & 1) + ((flags >> 1) & 1);
-    int nrec = RECS_PER_QUAD + RECS_PER_CAP * ncap;
+    int nrec = QUAD_SLOTS + CAP_SLOTS * ncap;
     for (int i = 0; i < nrec; i++) out[i] = rec_nop();
     if (shift == 0) {
         // OpenCV 4.13: integer end points are clipped to the canvas grown by `thickness` first
@@ -651,7 +854,6 @@ RIG_HD int emit_thick_line(int W, int H, P2L p0, P2L p1, int thickness, int flag
     int odd = thickness & 1;
     long long th = (long long)thickness << (XY_SHIFT - 1);
     int o = 0;
-    uint32_t ao = aux_off;
     if ((r < 0 ? -r : r) > 2.2204460492503131e-16) {
         r = ddiv(dadd((double)th, dmul((double)(odd * XY_ONE), 0.5)), dsqrt(r));
         long long dpx = dround(dmul(dy, r)), dpy = dround(dmul(dx, r));
@@ -660,16 +862,16 @@ RIG_HD int emit_thick_line(int W, int H, P2L p0, P2L p1, int thickness, int flag
         pt[1].x = p0.x - dpx; pt[1].y = p0.y - dpy;
         pt[2].x = p1.x - dpx; pt[2].y = p1.y - dpy;
         pt[3].x = p1.x + dpx; pt[3].y = p1.y + dpy;
-        emit_convex_aa(W, H, pt, 4, color, slope_corr, out + o, ao, aux);
+        emit_convex_aa(W, H, pt, 4, color, slope_corr, out + o, QUAD_SLOTS);
     }
-    o += RECS_PER_QUAD; ao += AUX_PER_CONVEX; aux++;
+    o += QUAD_SLOTS;
     for (int i = 0; i < 2; i++) {
         if (flags & (i + 1)) {
             P2L v[6];
             int nv;
             cap_polygon(p0, th, sin_tab, v, nv);
-            if (nv <= 5) emit_convex_aa(W, H, v, nv, color, slope_corr, out + o, ao, aux);
-            o += RECS_PER_CAP; ao += AUX_PER_CONVEX; aux++;
+            if (nv >= 2 && nv <= 5) emit_convex_aa(W, H, v, nv, color, slope_corr, out + o, CAP_SLOTS);
+            o += CAP_SLOTS;
         }
         p0 = p1;
     }

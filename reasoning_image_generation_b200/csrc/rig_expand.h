@@ -34,36 +34,42 @@ RIG_HD int popc9(uint32_t m)
     for (int i = 0; i < 9; i++) c += (m >> i) & 1;
     return c;
 }
-RIG_HD int ring_recs(int nv, int t) { return t <= 1 ? (nv - 1) : (nv - 1) * stroke_recs(t) + RECS_PER_CAP; }
-RIG_HD int ring_aux(int nv, int t) { return t <= 1 ? 0 : (2 * (nv - 1) + 1) * AUX_PER_CONVEX; }
+RIG_HD int ring_recs(int nv, int t) { return t <= 1 ? (nv - 1) : (nv - 1) * stroke_recs(t) + CAP_SLOTS; }
 
-// number of EllipseEx vertices of a circle outline of radius r px (duplicates removed)
-RIG_HD int ring_count(const float *sin_tab, int cx, int cy, int r)
+// EllipseEx vertices of a circle outline of radius r px into S[base ..], consecutive duplicates removed as
+// OpenCV does.  Lanes compute the raw polygon in parallel; the (rare: tiny radii only) compaction is serial.
+// Every lane returns the same vertex count (>= 2).
+template <int LANES, class Sync>
+RIG_HD int ring_fill(const float *sin_tab, long long cx_fx, long long cy_fx, int r, ExpandScratch &S, int base, int lane, Sync sync)
 {
-    long long rad = (long long)r << XY_SHIFT;
-    int delta = ring_delta(rad);
-    P2L prev = {-1, -1};
-    int nv = 0;
-    for (int a = 0; a < 360 + delta; a += delta) {
-        int ang = a > 360 ? 360 : a;
-        P2L p = ring_vertex(sin_tab, (long long)cx << XY_SHIFT, (long long)cy << XY_SHIFT, rad, ang);
-        if (p.x != prev.x || p.y != prev.y) { nv++; prev = p; }
+    const long long rad = (long long)r << XY_SHIFT;
+    const int delta = ring_delta(rad);
+    const int nraw = 360 / delta + 1;                      // angles 0, delta, ..., 360
+    sync();
+    for (int i = lane; i < nraw; i += LANES) {
+        P2L p = ring_vertex(sin_tab, cx_fx, cy_fx, rad, i * delta);
+        S.px[base + i] = p.x;
+        S.py[base + i] = p.y;
     }
-    return nv <= 1 ? 2 : nv;
-}
-// vertices of that outline into S (all lanes compute the same serial dedupe; it is tiny)
-RIG_HD int ring_fill(const float *sin_tab, long long cx_fx, long long cy_fx, int r, ExpandScratch &S, int base)
-{
-    long long rad = (long long)r << XY_SHIFT;
-    int delta = ring_delta(rad);
-    P2L prev = {-1, -1};
-    int nv = 0;
-    for (int a = 0; a < 360 + delta; a += delta) {
-        int ang = a > 360 ? 360 : a;
-        P2L p = ring_vertex(sin_tab, cx_fx, cy_fx, rad, ang);
-        if (p.x != prev.x || p.y != prev.y) { S.px[base + nv] = p.x; S.py[base + nv] = p.y; nv++; prev = p; }
+    sync();
+    bool dup = false;
+    for (int i = 1; i < nraw; i++) dup |= S.px[base + i] == S.px[base + i - 1] && S.py[base + i] == S.py[base + i - 1];
+    if (!dup) return nraw;
+    sync();
+    int nv = 1;                                            // all lanes run the same serial compaction
+    long long lx = S.px[base], ly = S.py[base];
+    for (int i = 1; i < nraw; i++) {
+        long long x = S.px[base + i], y = S.py[base + i];
+        if (x != lx || y != ly) {
+            if (lane == 0) { S.px[base + nv] = x; S.py[base + nv] = y; }
+            nv++; lx = x; ly = y;
+        }
     }
-    if (nv <= 1) { S.px[base] = S.px[base + 1] = cx_fx; S.py[base] = S.py[base + 1] = cy_fx; nv = 2; }
+    if (nv <= 1) {
+        if (lane == 0) { S.px[base] = S.px[base + 1] = cx_fx; S.py[base] = S.py[base + 1] = cy_fx; }
+        nv = 2;
+    }
+    sync();
     return nv;
 }
 
@@ -104,18 +110,18 @@ RIG_HD ElemPlan expand_plan(const DElem &e, const ShapeTables &T, int W, int H, 
             }
         if (e.kind == K_CIRCLE) {
             p.ncopies = popc9(p.mask);
-            p.nv_outer = ring_count(T.sin_tab, e.cx, e.cy, rad);
+            p.nv_outer = ring_fill<LANES>(T.sin_tab, (long long)e.cx << XY_SHIFT, (long long)e.cy << XY_SHIFT, rad, S, 0, lane, sync);
             p.nrec = p.ncopies * ((p.fill ? 1 : 0) + ring_recs(p.nv_outer, p.t));
-            p.naux = p.ncopies * ring_aux(p.nv_outer, p.t);
+            p.naux = 0;
         } else {
             int orad, irad, icx, icy;
             crescent_inner(e, e.cx, e.cy, orad, irad, icx, icy);
-            p.nv_outer = ring_count(T.sin_tab, e.cx, e.cy, orad);
-            p.nv_inner = ring_count(T.sin_tab, icx, icy, irad);
+            p.nv_outer = ring_fill<LANES>(T.sin_tab, (long long)e.cx << XY_SHIFT, (long long)e.cy << XY_SHIFT, orad, S, 0, lane, sync);
+            p.nv_inner = ring_fill<LANES>(T.sin_tab, (long long)icx << XY_SHIFT, (long long)icy << XY_SHIFT, irad, S, 0, lane, sync);
             int wraps = popc9(p.mask & ~(1u << 4));
             p.ncopies = wraps;
             p.nrec = (p.fill ? 1 : 0) + ring_recs(p.nv_outer, p.t) + ring_recs(p.nv_inner, p.t) + wraps;
-            p.naux = ring_aux(p.nv_outer, p.t) + ring_aux(p.nv_inner, p.t);
+            p.naux = 0;
             // the main copy is always drawn (its outlines at least)
             if (e.cy - orad - margin < lo) lo = e.cy - orad - margin;
             if (e.cy + orad + margin > hi) hi = e.cy + orad + margin;
@@ -147,7 +153,7 @@ RIG_HD ElemPlan expand_plan(const DElem &e, const ShapeTables &T, int W, int H, 
         p.mask = copy_mask(minx, maxx, miny, maxy, W, H, true);
         p.ncopies = popc9(p.mask);
         int per = (p.fill ? p.n + 1 : 0) + p.n * stroke_recs(p.t);
-        int pera = (p.fill ? p.n : 0) + p.n * stroke_aux(p.t);
+        int pera = p.fill ? p.n : 0;
         p.nrec = p.ncopies * p.loops * per;
         p.naux = p.ncopies * p.loops * pera;
         for (int b = 0; b < 9; b++)
@@ -166,22 +172,20 @@ RIG_HD ElemPlan expand_plan(const DElem &e, const ShapeTables &T, int W, int H, 
 // stroke one open ring whose vertices sit in S[base .. base+nv)
 template <int LANES>
 RIG_HD void emit_ring(const ShapeTables &T, int W, int H, int lane, const ExpandScratch &S, int base, int nv, int t,
-                      Rec *recs, uint32_t rec0, Q16 *aux4, uint32_t aux0)
+                      Rec *recs, uint32_t rec0)
 {
-    int per = stroke_recs(t), pera = stroke_aux(t);
+    int per = stroke_recs(t);
     for (int j = 1 + lane; j < nv; j += LANES) {
         P2L a = {S.px[base + j - 1], S.py[base + j - 1]}, b = {S.px[base + j], S.py[base + j]};
         int flags = j == 1 ? 3 : 2;
-        uint32_t ro = rec0 + (j == 1 ? 0 : (uint32_t)((j - 1) * per + (t > 1 ? RECS_PER_CAP : 0)));
-        uint32_t ao = aux0 + (j == 1 ? 0 : (uint32_t)((j - 1) * pera + (t > 1 ? AUX_PER_CONVEX : 0)));
-        emit_thick_line(W, H, a, b, t, flags, XY_SHIFT, 0u, T.slope_corr, T.sin_tab, recs + ro, ao,
-                        (ConvexAux *)(aux4 + ao));
+        uint32_t ro = rec0 + (j == 1 ? 0 : (uint32_t)((j - 1) * per + (t > 1 ? CAP_SLOTS : 0)));
+        emit_thick_line(W, H, a, b, t, flags, XY_SHIFT, 0u, T.slope_corr, T.sin_tab, recs + ro);
     }
 }
 
 // ---- phase 2: write the records -----------------------------------------------------------------
 // recs / aux are the arena bases; this element owns recs[rec0 .. rec0+plan.nrec) and the aux range
-// [aux0 .. aux0+plan.naux) (Q16 units; always a multiple of AUX_PER_CONVEX or polygon edges).
+// [aux0 .. aux0+plan.naux) (Q16 units: one per fillPoly scan edge).
 template <int LANES, class Sync>
 RIG_HD void expand_emit(const DElem &e, const ElemPlan &p, const ShapeTables &T, int W, int H, int lane, ExpandScratch &S,
                         Rec *recs, uint32_t rec0, Q16 *aux4, uint32_t aux0, Sync sync)
@@ -193,17 +197,15 @@ RIG_HD void expand_emit(const DElem &e, const ElemPlan &p, const ShapeTables &T,
         double half = ddiv((double)e.size, 2.0);
         int rad = dround(half);
         if (rad < 1) rad = 1;
-        int per = (p.fill ? 1 : 0) + ring_recs(p.nv_outer, t), pera = ring_aux(p.nv_outer, t);
+        int per = (p.fill ? 1 : 0) + ring_recs(p.nv_outer, t);
         int ci = 0;
         for (int b = 0; b < 9; b++) {
             if (!((p.mask >> b) & 1)) continue;
             int cx = e.cx + (b / 3 - 1) * W, cy = e.cy + (b % 3 - 1) * H;
-            uint32_t r0 = rec0 + ci * per, a0 = aux0 + ci * pera;
+            uint32_t r0 = rec0 + ci * per;
             if (p.fill && lane == 0) recs[r0] = make_disc(H, cx, cy, rad, color);
-            sync();
-            int nv = ring_fill(T.sin_tab, (long long)cx << XY_SHIFT, (long long)cy << XY_SHIFT, rad, S, 0);
-            sync();
-            emit_ring<LANES>(T, W, H, lane, S, 0, nv, t, recs, r0 + (p.fill ? 1 : 0), aux4, a0);
+            int nv = ring_fill<LANES>(T.sin_tab, (long long)cx << XY_SHIFT, (long long)cy << XY_SHIFT, rad, S, 0, lane, sync);
+            emit_ring<LANES>(T, W, H, lane, S, 0, nv, t, recs, r0 + (p.fill ? 1 : 0));
             ci++;
         }
         (void)black;
@@ -212,20 +214,16 @@ RIG_HD void expand_emit(const DElem &e, const ElemPlan &p, const ShapeTables &T,
     if (e.kind == K_CRESCENT) {
         int orad, irad, icx, icy;
         crescent_inner(e, e.cx, e.cy, orad, irad, icx, icy);
-        uint32_t r0 = rec0, a0 = aux0;
+        uint32_t r0 = rec0;
         if (p.fill) {
             if (lane == 0) recs[r0] = make_crescent(H, e.cx, e.cy, orad, icx, icy, irad, color);
             r0++;
         }
-        sync();
-        int nvo = ring_fill(T.sin_tab, (long long)e.cx << XY_SHIFT, (long long)e.cy << XY_SHIFT, orad, S, 0);
-        sync();
-        emit_ring<LANES>(T, W, H, lane, S, 0, nvo, t, recs, r0, aux4, a0);
-        r0 += ring_recs(nvo, t); a0 += ring_aux(nvo, t);
-        sync();
-        int nvi = ring_fill(T.sin_tab, (long long)icx << XY_SHIFT, (long long)icy << XY_SHIFT, irad, S, 0);
-        sync();
-        emit_ring<LANES>(T, W, H, lane, S, 0, nvi, t, recs, r0, aux4, a0);
+        int nvo = ring_fill<LANES>(T.sin_tab, (long long)e.cx << XY_SHIFT, (long long)e.cy << XY_SHIFT, orad, S, 0, lane, sync);
+        emit_ring<LANES>(T, W, H, lane, S, 0, nvo, t, recs, r0);
+        r0 += ring_recs(nvo, t);
+        int nvi = ring_fill<LANES>(T.sin_tab, (long long)icx << XY_SHIFT, (long long)icy << XY_SHIFT, irad, S, 0, lane, sync);
+        emit_ring<LANES>(T, W, H, lane, S, 0, nvi, t, recs, r0);
         r0 += ring_recs(nvi, t);
         if (lane == 0) {
             for (int b = 0; b < 9; b++) {
@@ -240,9 +238,9 @@ RIG_HD void expand_emit(const DElem &e, const ElemPlan &p, const ShapeTables &T,
     }
     // polygon kinds
     const int n = p.n;
-    const int sper = stroke_recs(t), saux = stroke_aux(t);
+    const int sper = stroke_recs(t);
     const int per = (p.fill ? n + 1 : 0) + n * sper;
-    const int pera = (p.fill ? n : 0) + n * saux;
+    const int pera = p.fill ? n : 0;
     int ci = 0;
     for (int b = 0; b < 9; b++) {
         if (!((p.mask >> b) & 1)) continue;
@@ -279,9 +277,7 @@ RIG_HD void expand_emit(const DElem &e, const ElemPlan &p, const ShapeTables &T,
             for (int i = lane; i < n; i += LANES) {
                 int i0 = i == 0 ? n - 1 : i - 1;
                 P2L q0 = {S.px[vb + i0] + ox, S.py[vb + i0] + oy}, q1 = {S.px[vb + i] + ox, S.py[vb + i] + oy};
-                uint32_t ao = a0 + (uint32_t)(i * saux);
-                emit_thick_line(W, H, q0, q1, t, 2, 0, black, T.slope_corr, T.sin_tab, recs + r0 + i * sper, ao,
-                                (ConvexAux *)(aux4 + ao));
+                emit_thick_line(W, H, q0, q1, t, 2, 0, black, T.slope_corr, T.sin_tab, recs + r0 + i * sper);
             }
         }
         ci++;

@@ -22,7 +22,7 @@ namespace rig {
 
 constexpr int BAND_ROWS = 8;
 constexpr int EXPAND_WARPS = 8;
-constexpr int CLAIM_BANDS = 4;   // bands claimed per atomic
+constexpr int MAX_CLAIM = 16;    // most bands one warp claims per atomic (guided self-scheduling)
 
 enum Counter { CTR_REC = 0, CTR_AUX = 1, CTR_OVERFLOW = 2, CTR_WORK = 3, CTR_COUNT = 8 };
 
@@ -86,17 +86,37 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct RasterOps {
+    Rec mine;            // the slot this lane loaded in the current 32-slot window
+    int j;               // lane that holds the record being executed
+    const Rec *base;     // global address of slot 0 of the window (fallback when a record leaves the window)
     __device__ __forceinline__ void sync() const { __syncwarp(); }
     __device__ __forceinline__ void append(RasterScratch &S, int32_t v) const
     {
         int i = atomicAdd(&S.count, 1);
         if (i < 64) S.cross[i] = v;
     }
+    __device__ __forceinline__ int bcast(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    __device__ __forceinline__ Rec slot(int k) const
+    {
+        Rec r;
+        const int src = j + k;
+        if (src < 32) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) r.w[i] = __shfl_sync(0xffffffffu, mine.w[i], src);
+        } else {
+            const uint4 *rp = (const uint4 *)(base + src);
+            uint4 lo = __ldg(rp), hi = __ldg(rp + 1);
+            r.w[0] = lo.x; r.w[1] = lo.y; r.w[2] = lo.z; r.w[3] = lo.w;
+            r.w[4] = hi.x; r.w[5] = hi.y; r.w[6] = hi.z; r.w[7] = hi.w;
+        }
+        return r;
+    }
 };
 
 struct RasterParams {
     const uint32_t *panel_begin;   // [n_panels + 1] element offsets (absolute)
     const uint8_t *panel_flags;    // [n_panels]
+    const uint32_t *order;         // [n_panels] panel ids, heaviest first inside each chunk (work is claimed in this order)
     const ElemHdr *hdrs;           // indexed by absolute element id
     const Rec *recs;
     const Q16 *aux;
@@ -147,14 +167,23 @@ __global__ void __launch_bounds__(512, 1) k_raster(const RasterParams P)
     const uint32_t total_bands = P.n_panels * (uint32_t)bands_per_panel;
     bool dirty = false;   // my band buffer has an outstanding bulk read
     RasterOps ops;
+    ops.mine = rec_nop(); ops.j = 0; ops.base = P.recs;
 
     for (;;) {
-        uint32_t first = 0;
-        if (lane == 0) first = atomicAdd(&P.counters[CTR_WORK], (uint32_t)CLAIM_BANDS);
+        // guided self-scheduling: large claims while much work is left, single bands at the end
+        uint32_t first = 0, take = 1;
+        if (lane == 0) {
+            const uint32_t cur = *(volatile uint32_t *)&P.counters[CTR_WORK];
+            const uint32_t left = cur < total_bands ? total_bands - cur : 0;
+            take = left / (4u * gridDim.x * (uint32_t)nwarps);
+            take = take < 1u ? 1u : (take > (uint32_t)MAX_CLAIM ? (uint32_t)MAX_CLAIM : take);
+            first = atomicAdd(&P.counters[CTR_WORK], take);
+        }
         first = __shfl_sync(0xffffffffu, first, 0);
+        take = __shfl_sync(0xffffffffu, take, 0);
         if (first >= total_bands) break;
-        for (uint32_t bi = first; bi < first + CLAIM_BANDS && bi < total_bands; bi++) {
-            const uint32_t pl = bi / bands_per_panel, panel = P.p0 + pl;
+        for (uint32_t bi = first; bi < first + take && bi < total_bands; bi++) {
+            const uint32_t panel = P.order[P.p0 + bi / bands_per_panel], pl = panel - P.p0;
             const int band = (int)(bi % bands_per_panel);
             Band B;
             B.r0 = band * BAND_ROWS; B.r1 = B.r0 + BAND_ROWS - 1; B.W = P.W; B.H = P.H; B.buf = mine;
@@ -193,21 +222,24 @@ __global__ void __launch_bounds__(512, 1) k_raster(const RasterParams P)
                 const ElemHdr h = P.hdrs[e];
                 if (h.ymin > B.r1 || h.ymax < B.r0) continue;
                 for (uint32_t base = 0; base < h.nrec; base += 32) {
+                    // every lane pulls one whole 32-byte slot (1 KB per warp, coalesced); records are
+                    // then handed round by shuffles, so a record costs no further global latency
                     bool hit = false;
+                    ops.base = P.recs + h.rec_begin + base;
                     if (base + lane < h.nrec) {
-                        const uint2 hd = *(const uint2 *)&P.recs[h.rec_begin + base + lane];
-                        int ymin = (int16_t)(hd.x >> 16), ymax = (int16_t)(hd.y & 0xffff);
-                        hit = ymin <= B.r1 && ymax >= B.r0;
+                        const uint4 *rp = (const uint4 *)(ops.base + lane);
+                        const uint4 lo = __ldg(rp), hi = __ldg(rp + 1);
+                        ops.mine.w[0] = lo.x; ops.mine.w[1] = lo.y; ops.mine.w[2] = lo.z; ops.mine.w[3] = lo.w;
+                        ops.mine.w[4] = hi.x; ops.mine.w[5] = hi.y; ops.mine.w[6] = hi.z; ops.mine.w[7] = hi.w;
+                        hit = rec_ymin(ops.mine) <= B.r1 && rec_ymax(ops.mine) >= B.r0;
+                    } else {
+                        ops.mine = rec_nop();
                     }
                     uint32_t m = __ballot_sync(0xffffffffu, hit);
                     while (m) {
-                        int j = __ffs(m) - 1;
+                        ops.j = __ffs(m) - 1;
                         m &= m - 1;
-                        const uint4 *rp = (const uint4 *)&P.recs[h.rec_begin + base + j];
-                        uint4 lo = rp[0], hi = rp[1];
-                        Rec r;
-                        r.w[0] = lo.x; r.w[1] = lo.y; r.w[2] = lo.z; r.w[3] = lo.w;
-                        r.w[4] = hi.x; r.w[5] = hi.y; r.w[6] = hi.z; r.w[7] = hi.w;
+                        const Rec r = ops.slot(0);
                         exec_record<32>(r, P.aux, filter, B, lane, S, ops);
                         __syncwarp();
                     }

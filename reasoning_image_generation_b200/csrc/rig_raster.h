@@ -7,8 +7,8 @@
 //
 // Ordering: records are applied one after another with a sync in between, so read-modify-write
 // blends see every earlier record, as in OpenCV's sequential drawing.  Inside one record no two
-// iterations touch the same pixel (LINEAA: one column/row per iteration), or all writes store the
-// same opaque colour (fills), so lanes never conflict.
+// lanes touch the same pixel: LINEAA gives each lane its own column/row, MINIPOLY gives each lane its
+// own pixel (and applies that pixel's edge blends in order), fills store one opaque colour.
 #pragma once
 #include "rig_shapes.h"
 
@@ -25,11 +25,14 @@ RIG_HD void put3(uint8_t *p, uint32_t c)
 {
     p[0] = (uint8_t)c; p[1] = (uint8_t)(c >> 8); p[2] = (uint8_t)(c >> 16);
 }
-RIG_HD void blend3(uint8_t *p, uint32_t c, int a)
+RIG_HD uint32_t get3(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16); }
+// both OpenCV blend steps on the three channels of a packed pixel
+RIG_HD uint32_t blend_px(uint32_t v, uint32_t c, int a)
 {
-    p[0] = (uint8_t)blend1(p[0], (int)(c & 0xff), a);
-    p[1] = (uint8_t)blend1(p[1], (int)((c >> 8) & 0xff), a);
-    p[2] = (uint8_t)blend1(p[2], (int)((c >> 16) & 0xff), a);
+    int v0 = blend1((int)(v & 0xff), (int)(c & 0xff), a);
+    int v1 = blend1((int)((v >> 8) & 0xff), (int)((c >> 8) & 0xff), a);
+    int v2 = blend1((int)((v >> 16) & 0xff), (int)((c >> 16) & 0xff), a);
+    return (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16);
 }
 template <int LANES>
 RIG_HD void fill_span(const Band &b, int y, int x1, int x2, uint32_t c, int lane)
@@ -43,10 +46,12 @@ struct RasterScratch {
     int32_t count;
 };
 
-// Ops: sync() orders memory between lanes; append(scratch, v) adds a crossing (any order)
+// Ops: sync() orders memory between lanes; append(scratch, v) adds a crossing (any order);
+//      slot(k) returns the k-th 32-byte slot of the current record (k = 0: the record itself);
+//      bcast(v, src) returns lane src's v (host: v).
 template <int LANES, class Ops>
 RIG_HD void exec_record(const Rec &r, const Q16 *aux, const uint8_t *filter, const Band &b, int lane,
-                        RasterScratch &S, Ops ops)
+                        RasterScratch &S, Ops &ops)
 {
     int y0 = rec_ymin(r), y1 = rec_ymax(r);
     if (y0 < b.r0) y0 = b.r0;
@@ -72,17 +77,53 @@ RIG_HD void exec_record(const Rec &r, const Q16 *aux, const uint8_t *filter, con
         for (int k = k0 + lane; k <= k1; k += LANES) {
             int major, m0, a[3];
             lineaa_eval(l, k, filter, major, m0, a[0], a[1], a[2]);
+            // the three taps are distinct pixels: read all, blend all, write all
+            uint8_t *p[3];
+            bool on[3];
+            uint32_t v[3];
             if (l.ymajor) {
-                if (major < b.r0 || major > b.r1) continue;
-                for (int i = 0; i < 3; i++)
-                    if ((unsigned)(m0 + i) < (unsigned)b.W) blend3(band_px(b, m0 + i, major), color, a[i]);
-            } else {
-                if ((unsigned)major >= (unsigned)b.W) continue;
+                bool row = major >= b.r0 && major <= b.r1;
                 for (int i = 0; i < 3; i++) {
-                    int y = m0 + i;
-                    if (y >= b.r0 && y <= b.r1) blend3(band_px(b, major, y), color, a[i]);
+                    on[i] = row && (unsigned)(m0 + i) < (unsigned)b.W;
+                    p[i] = band_px(b, on[i] ? m0 + i : 0, on[i] ? major : b.r0);
+                }
+            } else {
+                bool col = (unsigned)major < (unsigned)b.W;
+                for (int i = 0; i < 3; i++) {
+                    on[i] = col && m0 + i >= b.r0 && m0 + i <= b.r1;
+                    p[i] = band_px(b, on[i] ? major : 0, on[i] ? m0 + i : b.r0);
                 }
             }
+            for (int i = 0; i < 3; i++) v[i] = on[i] ? get3(p[i]) : 0u;
+            for (int i = 0; i < 3; i++) v[i] = blend_px(v[i], color, a[i]);
+            for (int i = 0; i < 3; i++) if (on[i]) put3(p[i], v[i]);
+        }
+        break;
+    }
+    case REC_MINIPOLY: {
+        const int n = (int)rec_flags(r);
+        const int x0 = rec_hi1(r), by0 = (int16_t)(r.w[2] & 0xffff), w = (int)((r.w[2] >> 16) & 0xff);
+        const int rows = y1 - y0 + 1, npx = rows * w;
+        const uint32_t inv = (65536u + (uint32_t)w - 1u) / (uint32_t)w;   // i / w == (i * inv) >> 16 for i < 144, w <= 12
+        const Rec sp = ops.slot(1 + n);
+        // LANES pixels of the box at a time: each lane keeps its pixel in a register while the edges are
+        // applied in OpenCV's order, then the interior fill overrides, then one store
+        for (int i0 = 0; i0 < npx; i0 += LANES) {
+            const int i = i0 + lane;
+            const bool live = i < npx;
+            const int ry = (int)(((uint32_t)(live ? i : 0) * inv) >> 16);
+            const int x = x0 + ((live ? i : 0) - ry * w), y = y0 + ry;
+            uint8_t *p = band_px(b, x, y);
+            uint32_t v = live ? get3(p) : 0u;
+            for (int e = 0; e < n; e++) {
+                const LineAA L = unpack_edge_slot(ops.slot(1 + e));
+                const int a = lineaa_at(L, x, y, filter);
+                if (live && a >= 0) v = blend_px(v, color, a);
+            }
+            const int rr = y - by0, dx = x - x0;                  // position inside the polygon's box
+            const uint32_t word = sp.w[2 + (rr >> 1)] >> ((rr & 1) * 16);
+            const int s1 = (int)(word & 0xff), s2 = (int)((word >> 8) & 0xff);
+            if (live) put3(p, (dx >= s1 && dx <= s2) ? color : v);
         }
         break;
     }
@@ -110,12 +151,21 @@ RIG_HD void exec_record(const Rec &r, const Q16 *aux, const uint8_t *filter, con
         break;
     }
     case REC_CONVEX: {
-        const ConvexAux &a = *(const ConvexAux *)(aux + r.w[2]);
-        int n0 = r.w[3] & 0xff, n1 = (r.w[3] >> 8) & 0xff;
-        for (int y = y0; y <= y1; y++) {
-            int x1, x2;
-            convex_span(a, n0, n1, y, b.W, x1, x2);
-            fill_span<LANES>(b, y, x1, x2, color, lane);
+        const ConvexChains C = unpack_convex(r, ops.slot(1), ops.slot(2), ops.slot(3));
+        // lane q (< rows) evaluates the span of row y0 + q; then lanes are spread over (row, x)
+        const int rows = y1 - y0 + 1;
+        int mx1 = 1, mx2 = 0;
+        if (LANES == 1 || lane < rows) convex_span(C, y0 + (LANES == 1 ? 0 : lane), b.W, mx1, mx2);
+        if (LANES == 1) {
+            for (int y = y0; y <= y1; y++) {
+                convex_span(C, y, b.W, mx1, mx2);
+                fill_span<1>(b, y, mx1, mx2, color, 0);
+            }
+        } else {
+            for (int q = 0; q < rows; q++) {
+                int x1 = ops.bcast(mx1, q), x2 = ops.bcast(mx2, q);
+                fill_span<LANES>(b, y0 + q, x1, x2, color, lane);
+            }
         }
         break;
     }
@@ -143,6 +193,10 @@ RIG_HD void exec_record(const Rec &r, const Q16 *aux, const uint8_t *filter, con
             int x1 = (int)(((long long)lo + (XY_ONE - 1)) >> XY_SHIFT), x2 = hi >> XY_SHIFT;
             if (x1 < 0) x1 = 0;
             if (x2 > b.W - 1) x2 = b.W - 1;
+            if (cnt == 2) {
+                fill_span<LANES>(b, y, x1, x2, color, lane);   // one pair: the span between the two crossings
+                continue;
+            }
             for (int x = x1 + lane; x <= x2; x += LANES) {
                 int X = x << XY_SHIFT, L = 0, E = 0;
                 for (int i = 0; i < cnt; i++) {

@@ -62,7 +62,7 @@ RIG_HD int kind_nverts(int kind)
 }
 
 // centre-relative, unrotated vertex i of loop `loop`
-RIG_HD void unit_vertex(const ShapeTables &T, int kind, int loop, int i, int s, double &x, double &y)
+RIG_FN void unit_vertex(const ShapeTables &T, int kind, int loop, int i, int s, double &x, double &y)
 {
     const double half = ddiv((double)s, 2.0);
     switch (kind) {
@@ -141,15 +141,15 @@ RIG_HD int ring_delta(long long rad_fx)
     int d = (int)((rad_fx + (XY_ONE >> 1)) >> XY_SHIFT);
     return d < 3 ? 90 : d < 10 ? 30 : d < 15 ? 18 : 5;
 }
-RIG_HD P2L ring_vertex(const float *sin_tab, long long cx_fx, long long cy_fx, long long rad_fx, int angle_deg)
+RIG_FN P2L ring_vertex(const float *sin_tab, long long cx_fx, long long cy_fx, long long rad_fx, int angle_deg)
 {
     double x = dmul((double)rad_fx, (double)sin_tab[450 - angle_deg]);
     double y = dmul((double)rad_fx, (double)sin_tab[angle_deg]);
     double px = dsub(dadd((double)cx_fx, dmul(x, 1.0)), dmul(y, 0.0));
     double py = dadd(dadd((double)cy_fx, dmul(x, 0.0)), dmul(y, 1.0));
     P2L pt;
-    pt.x = (long long)dround(ddiv(px, (double)XY_ONE)) * XY_ONE;
-    pt.y = (long long)dround(ddiv(py, (double)XY_ONE)) * XY_ONE;
+    pt.x = (long long)dround(dscale_down16(px)) * XY_ONE;
+    pt.y = (long long)dround(dscale_down16(py)) * XY_ONE;
     pt.x += dround(dsub(px, (double)pt.x));
     pt.y += dround(dsub(py, (double)pt.y));
     return pt;
@@ -168,8 +168,7 @@ RIG_HD uint32_t copy_mask(int minx, int maxx, int miny, int maxy, int W, int H, 
     return m;
 }
 
-// records / aux units of one stroked segment
-RIG_HD int stroke_recs(int t) { return t <= 1 ? 1 : RECS_PER_QUAD + RECS_PER_CAP; }
-RIG_HD int stroke_aux(int t) { return t <= 1 ? 0 : 2 * AUX_PER_CONVEX; }
+// record slots of one stroked segment
+RIG_HD int stroke_recs(int t) { return t <= 1 ? 1 : QUAD_SLOTS + CAP_SLOTS; }
 
 }  // namespace rig

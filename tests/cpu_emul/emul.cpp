@@ -14,6 +14,9 @@
 using namespace rig;
 
 struct HostOps {
+    const Rec *cur = nullptr;
+    Rec slot(int k) const { return cur[k]; }
+    int bcast(int v, int) const { return v; }
     void sync() const {}
     void append(RasterScratch &S, int32_t v) const
     {
@@ -47,7 +50,7 @@ extern "C" int emul_render(const rig_scene *scene, int W, int H, int band_rows, 
         for (uint32_t i = scene->panel_elem_begin[p]; i < scene->panel_elem_begin[p + 1]; i++) {
             ElemPlan plan = expand_plan<1>(elems[i], T, W, H, 0, ES, NoSync());
             uint32_t r0 = (uint32_t)recs.size(), a0 = (uint32_t)aux.size();
-            recs.resize(r0 + plan.nrec, rec_nop());
+            recs.resize(r0 + plan.nrec + 8, rec_nop());
             aux.resize(a0 + plan.naux + 1);
             expand_emit<1>(elems[i], plan, T, W, H, 0, ES, recs.data(), r0, aux.data(), a0, NoSync());
             ElemHdr h;
@@ -68,8 +71,11 @@ extern "C" int emul_render(const rig_scene *scene, int W, int H, int band_rows, 
                 for (int x = 0; x < W; x++) put3(band_px(b, x, y), bg);
             for (size_t e = 0; e < hdrs.size(); e++) {
                 if (hdrs[e].ymin > b.r1 || hdrs[e].ymax < b.r0) continue;
-                for (uint32_t k = 0; k < hdrs[e].nrec; k++)
-                    exec_record<1>(recs[hdrs[e].rec_begin + k], aux.data(), T.filter, b, 0, RS, HostOps());
+                for (uint32_t k = 0; k < hdrs[e].nrec; k++) {
+                    HostOps ops;
+                    ops.cur = &recs[hdrs[e].rec_begin + k];
+                    exec_record<1>(recs[hdrs[e].rec_begin + k], aux.data(), T.filter, b, 0, RS, ops);
+                }
             }
             if (use_grid) draw_grid<1>(b, gs, 0);
         }

@@ -27,6 +27,7 @@ for p in range(256):
         bad += 1
         if bad < 6: print('panel', p, 'differs in', d, 'px', [(e['kind'], e['size'], e['fill'], e['stroke_width'], e['center'], e['angle']) for e in els], ug)
 print('parity: checked', checked, 'bad', bad)
+r.set_profiling(True)
 ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts); st = ts.cuda_stream; assert st != 0
 for rep in range(3):
@@ -43,6 +44,9 @@ t0 = time.time()
 for rep in range(K): r.render_resident(out.data_ptr(), stream=st)
 torch.cuda.synchronize(); wall = (time.time() - t0) / K * 1e3
 print(f'  wall-clock cross-check: {wall:.3f} ms')
+r.sync(); stt = r.stats(); nl = max(stt['timed_launches'], 1)
+print(f"  split per render: expand {stt['expand_ms']/ (K*2+3):.3f} ms, raster {stt['raster_ms']/(K*2+3):.3f} ms over {stt['timed_launches']} chunk launches")
+r.set_profiling(False)
 # empty scene (pure template stores)
 from reasoning_image_generation_b200.scene import Scene
 emp = Scene(512, 512, (255,255,255), 3, np.zeros(n+1, np.uint32), np.zeros(n, np.uint8), *[np.zeros(0, t) for t in (np.uint8, np.uint8, np.uint8, np.int32, np.int32, np.int32, np.float64, np.float64, np.uint8)])
