@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'librig.so')
+LIB_PATH = os.environ.get('RIG_LIB') or os.path.join(_HERE, 'librig.so')
 
 RIG_OK = 0
 RIG_E_INVALID, RIG_E_CUDA, RIG_E_CAPACITY, RIG_E_UNSUPPORTED, RIG_E_NODEVICE = -1, -2, -3, -4, -5

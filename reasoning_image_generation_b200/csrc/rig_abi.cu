@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -58,6 +59,7 @@ struct rig_ctx {
     std::vector<uint32_t> nominal_recs, nominal_aux;   // per element, one copy
     std::vector<Chunk> chunks;
     double budget_frac = 0.6;
+    uint32_t max_claim = 16, heavy_div = 4;   // RIG_MAX_CLAIM / RIG_HEAVY_DIV override (tuning)
     size_t chunk_panel_limit = 1u << 20;
     rig_stats stats = {};
     bool pending_overflow_check = false;
@@ -204,6 +206,18 @@ int launch_chunk(rig_ctx *c, const Chunk &ch, uint8_t *out_dev, cudaStream_t st)
     P.panel_begin = c->d_begin; P.panel_flags = c->d_flags; P.order = c->d_order; P.hdrs = c->d_hdrs; P.recs = c->d_recs; P.aux = c->d_aux;
     P.tables = c->d_tables; P.out = out_dev; P.counters = c->d_counters; P.p0 = ch.p0; P.n_panels = ch.p1 - ch.p0;
     P.W = c->W; P.H = c->H; P.grid_size = c->grid_size; P.bg = c->bg;
+    P.max_claim = c->max_claim;
+    {
+        // panels are ordered heaviest first: those costing >= 2x the chunk's mean are handed out band by band
+        double sum = 0;
+        for (uint32_t p = ch.p0; p < ch.p1; p++) sum += c->panel_cost[p];
+        const double mean = sum / std::max(1u, ch.p1 - ch.p0);
+        uint32_t heavy = 0;
+        while (heavy < ch.p1 - ch.p0 && heavy < (ch.p1 - ch.p0) / std::max(1u, c->heavy_div) &&
+               c->panel_cost[c->h_order[ch.p0 + heavy]] >= 2.0 * mean && c->panel_cost[c->h_order[ch.p0 + heavy]] > 0)
+            heavy++;
+        P.heavy_bands = c->heavy_div ? heavy * (uint32_t)(c->H / BAND_ROWS) : 0u;
+    }
     const uint32_t bands = P.n_panels * (uint32_t)(c->H / BAND_ROWS);
     const uint32_t want = (bands + c->raster_warps - 1) / c->raster_warps;
     const uint32_t grid = std::max(1u, std::min((uint32_t)c->sm_count, want));
@@ -313,14 +327,17 @@ int rig_create(int device, int W, int H, int max_panels, int max_elements, rig_c
     }
     c->sm_count = prop.multiProcessorCount;
     const size_t smem_max = prop.sharedMemPerBlockOptin;
-    int warps = 16;
+    int warps = RASTER_MAX_WARPS;
     while (warps > 1 && raster_smem_bytes(W, warps) > smem_max) warps--;
     if (raster_smem_bytes(W, warps) > smem_max) {
         fail(c, RIG_E_UNSUPPORTED, "canvas width %d needs %zu B of shared memory per band set; the device offers %zu", W, raster_smem_bytes(W, warps), smem_max);
         return bail(RIG_E_UNSUPPORTED);
     }
     c->raster_warps = warps;
-    c->raster_smem = raster_smem_bytes(W, warps);
+    if (const char *e = getenv("RIG_MAX_CLAIM")) c->max_claim = (uint32_t)std::max(1, atoi(e));
+    if (const char *e = getenv("RIG_HEAVY_DIV")) c->heavy_div = (uint32_t)std::max(0, atoi(e));
+    if (const char *e = getenv("RIG_WARPS")) { int w = atoi(e); if (w >= 1 && w <= warps) c->raster_warps = w; }
+    c->raster_smem = raster_smem_bytes(W, c->raster_warps);
     CKC(cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->raster_smem));
     CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));

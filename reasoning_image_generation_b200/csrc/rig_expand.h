@@ -284,4 +284,31 @@ RIG_HD void expand_emit(const DElem &e, const ElemPlan &p, const ShapeTables &T,
     }
 }
 
+// ---- window summaries ---------------------------------------------------------------------------
+// An element's slots are scanned by every band it overlaps.  To let a band skip the 32-slot windows
+// that hold nothing for it, the element's arena range starts with one 4-byte (ymin | ymax << 16) row
+// range per window, packed 8 to a slot:   [summary slots][payload slots ...]
+RIG_HD uint32_t summary_slots(uint32_t nrec) { return ((nrec + 31u) / 32u + 7u) / 8u; }
+
+template <int LANES>
+RIG_HD void write_summaries(Rec *recs, uint32_t sum_begin, uint32_t payload_begin, uint32_t nrec, int lane)
+{
+    uint32_t *sum = (uint32_t *)(recs + sum_begin);
+    const uint32_t nwin = (nrec + 31u) / 32u, cap = summary_slots(nrec) * 8u;
+    for (uint32_t w = lane; w < cap; w += LANES) {
+        int lo = 1, hi = 0;
+        if (w < nwin) {
+            lo = 1 << 20; hi = -(1 << 20);
+            const uint32_t end = (w + 1) * 32u < nrec ? (w + 1) * 32u : nrec;
+            for (uint32_t k = w * 32u; k < end; k++) {
+                const Rec &r = recs[payload_begin + k];
+                const int a = rec_ymin(r), b = rec_ymax(r);
+                if (a <= b) { lo = a < lo ? a : lo; hi = b > hi ? b : hi; }
+            }
+            if (lo > hi) { lo = 1; hi = 0; }
+        }
+        sum[w] = (uint32_t)(uint16_t)(int16_t)lo | ((uint32_t)(uint16_t)(int16_t)hi << 16);
+    }
+}
+
 }  // namespace rig

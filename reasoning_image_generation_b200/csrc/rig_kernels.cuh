@@ -20,9 +20,12 @@
 
 namespace rig {
 
-constexpr int BAND_ROWS = 8;
+#ifndef RIG_BAND_ROWS
+#define RIG_BAND_ROWS 4
+#endif
+constexpr int BAND_ROWS = RIG_BAND_ROWS;
+constexpr int RASTER_MAX_WARPS = BAND_ROWS >= 8 ? 16 : 32;
 constexpr int EXPAND_WARPS = 8;
-constexpr int MAX_CLAIM = 16;    // most bands one warp claims per atomic (guided self-scheduling)
 
 enum Counter { CTR_REC = 0, CTR_AUX = 1, CTR_OVERFLOW = 2, CTR_WORK = 3, CTR_COUNT = 8 };
 
@@ -43,25 +46,28 @@ k_expand(const DElem *__restrict__ elems, uint32_t e0, uint32_t e1, const ShapeT
     ExpandScratch &S = scratch[warp];
     ElemPlan plan = expand_plan<32>(el, *T, W, H, lane, S, WarpSync());
     uint32_t r0 = 0, a0 = 0;
+    const uint32_t nsum = summary_slots(plan.nrec);
     if (lane == 0) {
-        r0 = atomicAdd(&counters[CTR_REC], plan.nrec);
+        r0 = atomicAdd(&counters[CTR_REC], plan.nrec + nsum);
         a0 = atomicAdd(&counters[CTR_AUX], plan.naux);
     }
     r0 = __shfl_sync(0xffffffffu, r0, 0);
     a0 = __shfl_sync(0xffffffffu, a0, 0);
-    const bool fits = (uint64_t)r0 + plan.nrec <= rec_cap && (uint64_t)a0 + plan.naux <= aux_cap;
+    const bool fits = (uint64_t)r0 + plan.nrec + nsum <= rec_cap && (uint64_t)a0 + plan.naux <= aux_cap;
     if (lane == 0) {
         ElemHdr h;
         h.rec_begin = r0;
         h.nrec = fits ? plan.nrec : 0;
         h.ymin = (int16_t)(fits ? plan.ymin : 1);
         h.ymax = (int16_t)(fits ? plan.ymax : 0);
-        h.pad = 0;
+        h.nsum = nsum;
         hdrs[e] = h;
         if (!fits) atomicExch(&counters[CTR_OVERFLOW], 1u);
     }
     if (!fits) return;
-    expand_emit<32>(el, plan, *T, W, H, lane, S, recs, r0, aux, a0, WarpSync());
+    expand_emit<32>(el, plan, *T, W, H, lane, S, recs, r0 + nsum, aux, a0, WarpSync());
+    __syncwarp();
+    write_summaries<32>(recs, r0, r0 + nsum, plan.nrec, lane);
 }
 
 // folds one chunk's counters into the per-render totals: [0] overflow flag, [1] records, [2] aux units
@@ -96,6 +102,21 @@ struct RasterOps {
         if (i < 64) S.cross[i] = v;
     }
     __device__ __forceinline__ int bcast(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    __device__ __forceinline__ int reduce_add(int v) const { return __reduce_add_sync(0xffffffffu, v); }
+    __device__ __forceinline__ int reduce_min(int v) const { return __reduce_min_sync(0xffffffffu, v); }
+    __device__ __forceinline__ int reduce_max(int v) const { return __reduce_max_sync(0xffffffffu, v); }
+    __device__ __forceinline__ Rec slot_part(int k, int lo, int hi) const
+    {
+        Rec r;
+        const int src = j + k;
+        if (src < 32) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) r.w[i] = (i >= lo && i <= hi) ? __shfl_sync(0xffffffffu, mine.w[i], src) : 0u;
+        } else {
+            r = slot(k);
+        }
+        return r;
+    }
     __device__ __forceinline__ Rec slot(int k) const
     {
         Rec r;
@@ -126,10 +147,11 @@ struct RasterParams {
     uint32_t p0, n_panels;         // panels [p0, p0 + n_panels) of the resident scene
     int W, H, grid_size;
     uint32_t bg;                   // c0 | c1<<8 | c2<<16
+    uint32_t max_claim, heavy_bands; // scheduling: largest claim; the first heavy_bands bands (costliest panels) are claimed singly
 };
 
 // dynamic shared memory layout: [template plain][template grid][warp bands ...][RasterScratch per warp][filter 64]
-__global__ void __launch_bounds__(512, 1) k_raster(const RasterParams P)
+__global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const RasterParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -176,7 +198,8 @@ __global__ void __launch_bounds__(512, 1) k_raster(const RasterParams P)
             const uint32_t cur = *(volatile uint32_t *)&P.counters[CTR_WORK];
             const uint32_t left = cur < total_bands ? total_bands - cur : 0;
             take = left / (4u * gridDim.x * (uint32_t)nwarps);
-            take = take < 1u ? 1u : (take > (uint32_t)MAX_CLAIM ? (uint32_t)MAX_CLAIM : take);
+            take = take < 1u ? 1u : (take > P.max_claim ? P.max_claim : take);
+            if (cur < P.heavy_bands) take = 1u;      // panels are sorted heaviest first: spread those band by band
             first = atomicAdd(&P.counters[CTR_WORK], take);
         }
         first = __shfl_sync(0xffffffffu, first, 0);
@@ -221,27 +244,41 @@ __global__ void __launch_bounds__(512, 1) k_raster(const RasterParams P)
             for (uint32_t e = eb; e < ee; e++) {
                 const ElemHdr h = P.hdrs[e];
                 if (h.ymin > B.r1 || h.ymax < B.r0) continue;
-                for (uint32_t base = 0; base < h.nrec; base += 32) {
-                    // every lane pulls one whole 32-byte slot (1 KB per warp, coalesced); records are
-                    // then handed round by shuffles, so a record costs no further global latency
-                    bool hit = false;
-                    ops.base = P.recs + h.rec_begin + base;
-                    if (base + lane < h.nrec) {
-                        const uint4 *rp = (const uint4 *)(ops.base + lane);
-                        const uint4 lo = __ldg(rp), hi = __ldg(rp + 1);
-                        ops.mine.w[0] = lo.x; ops.mine.w[1] = lo.y; ops.mine.w[2] = lo.z; ops.mine.w[3] = lo.w;
-                        ops.mine.w[4] = hi.x; ops.mine.w[5] = hi.y; ops.mine.w[6] = hi.z; ops.mine.w[7] = hi.w;
-                        hit = rec_ymin(ops.mine) <= B.r1 && rec_ymax(ops.mine) >= B.r0;
-                    } else {
-                        ops.mine = rec_nop();
+                const uint32_t *sums = (const uint32_t *)(P.recs + h.rec_begin);
+                const Rec *payload = P.recs + h.rec_begin + h.nsum;
+                const uint32_t nwin = (h.nrec + 31u) / 32u;
+                for (uint32_t wb = 0; wb < nwin; wb += 32) {
+                    // one 4-byte row range per 32-slot window: skip the windows that hold nothing for this band
+                    bool wh = false;
+                    if (wb + lane < nwin) {
+                        const uint32_t sv = __ldg(sums + wb + lane);
+                        wh = (int16_t)(sv & 0xffff) <= B.r1 && (int16_t)(sv >> 16) >= B.r0;
                     }
-                    uint32_t m = __ballot_sync(0xffffffffu, hit);
-                    while (m) {
-                        ops.j = __ffs(m) - 1;
-                        m &= m - 1;
-                        const Rec r = ops.slot(0);
-                        exec_record<32>(r, P.aux, filter, B, lane, S, ops);
-                        __syncwarp();
+                    uint32_t wm = __ballot_sync(0xffffffffu, wh);
+                    while (wm) {
+                        const uint32_t base = (wb + (uint32_t)(__ffs(wm) - 1)) * 32u;
+                        wm &= wm - 1;
+                        // every lane pulls one whole 32-byte slot (1 KB per warp, coalesced); records are
+                        // then handed round by shuffles, so a record costs no further global latency
+                        bool hit = false;
+                        ops.base = payload + base;
+                        if (base + lane < h.nrec) {
+                            const uint4 *rp = (const uint4 *)(ops.base + lane);
+                            const uint4 lo = __ldg(rp), hi = __ldg(rp + 1);
+                            ops.mine.w[0] = lo.x; ops.mine.w[1] = lo.y; ops.mine.w[2] = lo.z; ops.mine.w[3] = lo.w;
+                            ops.mine.w[4] = hi.x; ops.mine.w[5] = hi.y; ops.mine.w[6] = hi.z; ops.mine.w[7] = hi.w;
+                            hit = rec_ymin(ops.mine) <= B.r1 && rec_ymax(ops.mine) >= B.r0;
+                        } else {
+                            ops.mine = rec_nop();
+                        }
+                        uint32_t m = __ballot_sync(0xffffffffu, hit);
+                        while (m) {
+                            ops.j = __ffs(m) - 1;
+                            m &= m - 1;
+                            const Rec r = ops.slot(0);
+                            exec_record<32>(r, P.aux, filter, B, lane, S, ops);
+                            __syncwarp();
+                        }
                     }
                 }
             }

@@ -29,6 +29,16 @@ RIG_HD uint32_t get3(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1]
 // both OpenCV blend steps on the three channels of a packed pixel
 RIG_HD uint32_t blend_px(uint32_t v, uint32_t c, int a)
 {
+    if (c == 0u) {
+        // black ink (every stroke of the reference): ((0 - v) * a + 127) >> 8 == -((v * a + 128) >> 8), and the
+        // three channels fit 16-bit lanes (v * a <= 65025), so both blend steps run on packed words
+        uint32_t lo = v & 0x00ff00ffu, hi = (v >> 8) & 0xffu;
+        lo -= ((lo * (uint32_t)a + 0x00800080u) >> 8) & 0x00ff00ffu;
+        hi -= (hi * (uint32_t)a + 0x80u) >> 8;
+        lo -= ((lo * (uint32_t)a + 0x00800080u) >> 8) & 0x00ff00ffu;
+        hi -= (hi * (uint32_t)a + 0x80u) >> 8;
+        return lo | (hi << 8);
+    }
     int v0 = blend1((int)(v & 0xff), (int)(c & 0xff), a);
     int v1 = blend1((int)((v >> 8) & 0xff), (int)((c >> 8) & 0xff), a);
     int v2 = blend1((int)((v >> 16) & 0xff), (int)((c >> 16) & 0xff), a);
@@ -47,7 +57,8 @@ struct RasterScratch {
 };
 
 // Ops: sync() orders memory between lanes; append(scratch, v) adds a crossing (any order);
-//      slot(k) returns the k-th 32-byte slot of the current record (k = 0: the record itself);
+//      slot(k) returns the k-th 32-byte slot of the current record (k = 0: the record itself),
+//      slot_part(k, lo, hi) the same with only words lo..hi filled in;
 //      bcast(v, src) returns lane src's v (host: v).
 template <int LANES, class Ops>
 RIG_HD void exec_record(const Rec &r, const Q16 *aux, const uint8_t *filter, const Band &b, int lane,
@@ -105,7 +116,7 @@ RIG_HD void exec_record(const Rec &r, const Q16 *aux, const uint8_t *filter, con
         const int x0 = rec_hi1(r), by0 = (int16_t)(r.w[2] & 0xffff), w = (int)((r.w[2] >> 16) & 0xff);
         const int rows = y1 - y0 + 1, npx = rows * w;
         const uint32_t inv = (65536u + (uint32_t)w - 1u) / (uint32_t)w;   // i / w == (i * inv) >> 16 for i < 144, w <= 12
-        const Rec sp = ops.slot(1 + n);
+        const Rec sp = ops.slot_part(1 + n, 2, 7);
         // LANES pixels of the box at a time: each lane keeps its pixel in a register while the edges are
         // applied in OpenCV's order, then the interior fill overrides, then one store
         for (int i0 = 0; i0 < npx; i0 += LANES) {
@@ -116,7 +127,7 @@ RIG_HD void exec_record(const Rec &r, const Q16 *aux, const uint8_t *filter, con
             uint8_t *p = band_px(b, x, y);
             uint32_t v = live ? get3(p) : 0u;
             for (int e = 0; e < n; e++) {
-                const LineAA L = unpack_edge_slot(ops.slot(1 + e));
+                const LineAA L = unpack_edge_slot(ops.slot_part(1 + e, 2, 6));
                 const int a = lineaa_at(L, x, y, filter);
                 if (live && a >= 0) v = blend_px(v, color, a);
             }
@@ -151,7 +162,7 @@ RIG_HD void exec_record(const Rec &r, const Q16 *aux, const uint8_t *filter, con
         break;
     }
     case REC_CONVEX: {
-        const ConvexChains C = unpack_convex(r, ops.slot(1), ops.slot(2), ops.slot(3));
+        const ConvexChains C = unpack_convex(r, ops.slot_part(1, 2, 7), ops.slot_part(2, 2, 7), ops.slot_part(3, 2, 4));
         // lane q (< rows) evaluates the span of row y0 + q; then lanes are spread over (row, x)
         const int rows = y1 - y0 + 1;
         int mx1 = 1, mx2 = 0;

@@ -42,9 +42,9 @@ static_assert(sizeof(DElem) == 40, "DElem layout");
 
 // what the expand kernel leaves for the rasteriser, per element
 struct ElemHdr {
-    uint32_t rec_begin, nrec;
+    uint32_t rec_begin, nrec; // arena range: nsum summary slots at rec_begin, then nrec payload slots
     int16_t ymin, ymax;       // union of the records' row ranges (ymin > ymax: nothing visible)
-    uint32_t pad;
+    uint32_t nsum;
 };
 
 RIG_HD int kind_loops(int kind) { return kind == K_PLUS ? 2 : 1; }

@@ -16,7 +16,16 @@ using namespace rig;
 struct HostOps {
     const Rec *cur = nullptr;
     Rec slot(int k) const { return cur[k]; }
+    Rec slot_part(int k, int lo, int hi) const
+    {
+        Rec r = rec_nop();
+        for (int i = lo; i <= hi; i++) r.w[i] = cur[k].w[i];
+        return r;
+    }
     int bcast(int v, int) const { return v; }
+    int reduce_add(int v) const { return v; }
+    int reduce_min(int v) const { return v; }
+    int reduce_max(int v) const { return v; }
     void sync() const {}
     void append(RasterScratch &S, int32_t v) const
     {
@@ -24,6 +33,8 @@ struct HostOps {
         S.count++;
     }
 };
+unsigned long long g_exec_count[16];
+unsigned long long g_window_loads, g_band_nonempty, g_bands;
 struct NoSync {
     void operator()() const {}
 };
@@ -50,11 +61,13 @@ extern "C" int emul_render(const rig_scene *scene, int W, int H, int band_rows, 
         for (uint32_t i = scene->panel_elem_begin[p]; i < scene->panel_elem_begin[p + 1]; i++) {
             ElemPlan plan = expand_plan<1>(elems[i], T, W, H, 0, ES, NoSync());
             uint32_t r0 = (uint32_t)recs.size(), a0 = (uint32_t)aux.size();
-            recs.resize(r0 + plan.nrec + 8, rec_nop());
+            const uint32_t nsum = summary_slots(plan.nrec);
+            recs.resize(r0 + nsum + plan.nrec + 8, rec_nop());
             aux.resize(a0 + plan.naux + 1);
-            expand_emit<1>(elems[i], plan, T, W, H, 0, ES, recs.data(), r0, aux.data(), a0, NoSync());
+            expand_emit<1>(elems[i], plan, T, W, H, 0, ES, recs.data(), r0 + nsum, aux.data(), a0, NoSync());
+            write_summaries<1>(recs.data(), r0, r0 + nsum, plan.nrec, 0);
             ElemHdr h;
-            h.rec_begin = r0; h.nrec = plan.nrec; h.ymin = (int16_t)plan.ymin; h.ymax = (int16_t)plan.ymax; h.pad = 0;
+            h.rec_begin = r0; h.nrec = plan.nrec; h.ymin = (int16_t)plan.ymin; h.ymax = (int16_t)plan.ymax; h.nsum = nsum;
             hdrs.push_back(h);
         }
         total += (uint32_t)recs.size();
@@ -71,10 +84,16 @@ extern "C" int emul_render(const rig_scene *scene, int W, int H, int band_rows, 
                 for (int x = 0; x < W; x++) put3(band_px(b, x, y), bg);
             for (size_t e = 0; e < hdrs.size(); e++) {
                 if (hdrs[e].ymin > b.r1 || hdrs[e].ymax < b.r0) continue;
+                const uint32_t *sums = (const uint32_t *)&recs[hdrs[e].rec_begin];
+                const uint32_t pb = hdrs[e].rec_begin + hdrs[e].nsum;
                 for (uint32_t k = 0; k < hdrs[e].nrec; k++) {
+                    const uint32_t sv = sums[k / 32];
+                    if ((int16_t)(sv & 0xffff) > b.r1 || (int16_t)(sv >> 16) < b.r0) continue;   // window skipped
+                    if (k % 32 == 0 || true) {}
                     HostOps ops;
-                    ops.cur = &recs[hdrs[e].rec_begin + k];
-                    exec_record<1>(recs[hdrs[e].rec_begin + k], aux.data(), T.filter, b, 0, RS, ops);
+                    ops.cur = &recs[pb + k];
+                    { const Rec &rr = recs[pb + k]; if (rec_ymin(rr) <= b.r1 && rec_ymax(rr) >= b.r0) g_exec_count[rec_type(rr) & 15]++; }
+                    exec_record<1>(recs[pb + k], aux.data(), T.filter, b, 0, RS, ops);
                 }
             }
             if (use_grid) draw_grid<1>(b, gs, 0);
@@ -83,6 +102,8 @@ extern "C" int emul_render(const rig_scene *scene, int W, int H, int band_rows, 
     if (nrec_out) *nrec_out = total;
     return 0;
 }
+
+extern "C" void emul_counts(unsigned long long *out) { for (int i = 0; i < 16; i++) { out[i] = g_exec_count[i]; g_exec_count[i] = 0; } }
 
 extern "C" size_t emul_shape_tables(void *out, size_t size)
 {
