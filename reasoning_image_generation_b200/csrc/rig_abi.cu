@@ -6,6 +6,7 @@
 // pixels, TMA bulk stores).  With a host destination the chunks are double-buffered through two
 // device staging buffers so the D2H copy of chunk i overlaps the rendering of chunk i+1.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -38,7 +39,8 @@ struct rig_ctx {
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     ShapeTables *d_tables = nullptr;
     DElem *d_elems = nullptr, *h_elems = nullptr;
-    uint32_t *d_begin = nullptr, *d_order = nullptr;
+    uint32_t *d_begin = nullptr, *d_order = nullptr, *d_eorder = nullptr;
+    std::vector<uint32_t> h_eorder;
     uint8_t *d_flags = nullptr;
     std::vector<uint32_t> h_order;
     std::vector<double> panel_cost;
@@ -130,15 +132,22 @@ void plan_chunks(rig_ctx *c, size_t panel_limit)
         c->panel_cost[p] = pr;
         c->h_order[p] = p;
     }
-    for (const Chunk &ch : c->chunks)
+    c->h_eorder.resize(c->n_elements);
+    for (uint32_t e = 0; e < (uint32_t)c->n_elements; e++) c->h_eorder[e] = e;
+    for (const Chunk &ch : c->chunks) {
         std::stable_sort(c->h_order.begin() + ch.p0, c->h_order.begin() + ch.p1,
                          [&](uint32_t a, uint32_t b) { return c->panel_cost[a] > c->panel_cost[b]; });
+        std::stable_sort(c->h_eorder.begin() + ch.e0, c->h_eorder.begin() + ch.e1,
+                         [&](uint32_t a, uint32_t b) { return c->nominal_recs[a] > c->nominal_recs[b]; });
+    }
 }
 
 int upload_order(rig_ctx *c, cudaStream_t st)
 {
     if (c->n_panels) {
         CK(c, cudaMemcpyAsync(c->d_order, c->h_order.data(), sizeof(uint32_t) * c->n_panels, cudaMemcpyHostToDevice, st));
+        if (c->n_elements)
+            CK(c, cudaMemcpyAsync(c->d_eorder, c->h_eorder.data(), sizeof(uint32_t) * c->n_elements, cudaMemcpyHostToDevice, st));
         CK(c, cudaStreamSynchronize(st));
     }
     return RIG_OK;
@@ -153,7 +162,7 @@ int validate_scene(rig_ctx *c, const rig_scene *s)
     if (s->n_panels && (!s->panel_elem_begin)) return fail(c, RIG_E_INVALID, "panel_elem_begin is NULL");
     if (s->n_elements && (!s->kind || !s->fill || !s->stroke || !s->size || !s->angle || !s->cx || !s->cy || !s->rgb))
         return fail(c, RIG_E_INVALID, "an element array is NULL");
-    if (s->grid_size < 0 || s->grid_size > 64) return fail(c, RIG_E_INVALID, "grid_size %d out of range", s->grid_size);
+    if (s->grid_size < 0 || s->grid_size > 16) return fail(c, s->grid_size < 0 ? RIG_E_INVALID : RIG_E_UNSUPPORTED, "grid_size %d out of range (1..16)", s->grid_size);
     if (s->n_panels) {
         if (s->panel_elem_begin[0] != 0 || s->panel_elem_begin[s->n_panels] != (uint32_t)s->n_elements)
             return fail(c, RIG_E_INVALID, "panel_elem_begin must start at 0 and end at n_elements");
@@ -197,7 +206,7 @@ int launch_chunk(rig_ctx *c, const Chunk &ch, uint8_t *out_dev, cudaStream_t st)
     if (c->profiling) prof_event(c, st);
     if (ne) {
         k_expand<<<(ne + EXPAND_WARPS - 1) / EXPAND_WARPS, EXPAND_WARPS * 32, 0, st>>>(
-            c->d_elems, ch.e0, ch.e1, c->d_tables, c->W, c->H, c->d_hdrs, c->d_recs, c->rec_cap, c->d_aux, c->aux_cap,
+            c->d_elems, c->d_eorder, ch.e0, ch.e1, c->d_tables, c->W, c->H, c->d_hdrs, c->d_recs, c->rec_cap, c->d_aux, c->aux_cap,
             c->d_counters);
         c->stats.kernel_launches++;
     }
@@ -207,6 +216,13 @@ int launch_chunk(rig_ctx *c, const Chunk &ch, uint8_t *out_dev, cudaStream_t st)
     P.tables = c->d_tables; P.out = out_dev; P.counters = c->d_counters; P.p0 = ch.p0; P.n_panels = ch.p1 - ch.p0;
     P.W = c->W; P.H = c->H; P.grid_size = c->grid_size; P.bg = c->bg;
     P.max_claim = c->max_claim;
+    P.n_grid = c->grid_size - 1;
+    for (int g = 1; g < c->grid_size && g <= 16; g++) {
+        // int(round(i * W / grid_size)): Python rounds the float quotient half-to-even (generator.py:117,121)
+        volatile double qx = (double)(g * c->W) / (double)c->grid_size, qy = (double)(g * c->H) / (double)c->grid_size;
+        P.grid_x[g - 1] = (int16_t)nearbyint(qx);
+        P.grid_y[g - 1] = (int16_t)nearbyint(qy);
+    }
     {
         // panels are ordered heaviest first: those costing >= 2x the chunk's mean are handed out band by band
         double sum = 0;
@@ -354,6 +370,7 @@ int rig_create(int device, int W, int H, int max_panels, int max_elements, rig_c
     CKC(cudaMalloc(&c->d_begin, sizeof(uint32_t) * ((size_t)max_panels + 1)));
     CKC(cudaMalloc(&c->d_flags, (size_t)max_panels));
     CKC(cudaMalloc(&c->d_order, sizeof(uint32_t) * (size_t)max_panels));
+    CKC(cudaMalloc(&c->d_eorder, sizeof(uint32_t) * (size_t)max_elements));
     CKC(cudaMalloc(&c->d_hdrs, sizeof(ElemHdr) * (size_t)max_elements));
     // record arena: sized so a whole batch is one chunk (one launch tail per batch), capped at 1 GB
     const uint64_t want_rec = std::min<uint64_t>(std::max<uint64_t>((uint64_t)max_elements * 1100, 1u << 16), 32u << 20);
@@ -375,7 +392,7 @@ void rig_destroy(rig_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-    cudaFree(c->d_tables); cudaFree(c->d_elems); cudaFreeHost(c->h_elems); cudaFree(c->d_begin); cudaFree(c->d_order); cudaFree(c->d_flags);
+    cudaFree(c->d_tables); cudaFree(c->d_elems); cudaFreeHost(c->h_elems); cudaFree(c->d_begin); cudaFree(c->d_order); cudaFree(c->d_eorder); cudaFree(c->d_flags);
     cudaFree(c->d_hdrs); cudaFree(c->d_recs); cudaFree(c->d_aux); cudaFree(c->d_counters); cudaFree(c->d_overflow);
     cudaFree(c->d_stage[0]); cudaFree(c->d_stage[1]); cudaFree(c->d_sums);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -508,8 +525,11 @@ int rig_hash_batch(rig_ctx *c, const uint8_t *imgs_dev, int n, int layout, uint6
     if (!c) return RIG_E_INVALID;
     if (n < 0 || (n && (!imgs_dev || !hashes_dev))) return fail(c, RIG_E_INVALID, "bad arguments to rig_hash_batch");
     if (layout != RIG_LAYOUT_RGB && layout != RIG_LAYOUT_BGR) return fail(c, RIG_E_INVALID, "bad layout %d", layout);
-    if (c->W % (16 * HASH_GRID) || c->H % HASH_GRID)
-        return fail(c, RIG_E_UNSUPPORTED, "hashing needs W %% %d == 0 and H %% %d == 0", 16 * HASH_GRID, HASH_GRID);
+    {
+        const int lpb = c->W / HASH_GRID / 4;     // lanes per hash block in k_block_sums
+        if (c->W % (16 * HASH_GRID) || c->H % HASH_GRID || (lpb & (lpb - 1)))
+            return fail(c, RIG_E_UNSUPPORTED, "hashing needs W %% %d == 0, W / 64 a power of two and H %% %d == 0", 16 * HASH_GRID, HASH_GRID);
+    }
     if (((uintptr_t)imgs_dev) % 16) return fail(c, RIG_E_INVALID, "imgs_dev must be 16-byte aligned");
     if (n == 0) return RIG_OK;
     CK(c, cudaSetDevice(c->device));
@@ -521,8 +541,8 @@ int rig_hash_batch(rig_ctx *c, const uint8_t *imgs_dev, int n, int layout, uint6
         CK(c, cudaMalloc(&c->d_sums, sizeof(uint32_t) * 256 * (size_t)n));
         c->sums_cap = (size_t)n;
     }
-    const int r_idx = layout == RIG_LAYOUT_RGB ? 0 : 2, b_idx = 2 - r_idx;
-    k_block_sums<<<(unsigned)n * HASH_GRID, 256, 0, st>>>(imgs_dev, c->W, c->H, r_idx, b_idx, c->d_sums);
+    const uint32_t coef = layout == RIG_LAYOUT_RGB ? (77u | (150u << 8) | (29u << 16)) : (29u | (150u << 8) | (77u << 16));
+    k_block_sums<<<(unsigned)n * HASH_GRID, 256, 0, st>>>(imgs_dev, c->W, c->H, coef, c->d_sums);
     k_hash_bits<<<((unsigned)n * 32 + 255) / 256, 256, 0, st>>>(c->d_sums, n, hashes_dev);
     c->stats.kernel_launches += 2;
     CK(c, cudaGetLastError());

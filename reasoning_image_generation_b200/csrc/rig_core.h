@@ -668,19 +668,19 @@ RIG_FN bool pack_minipoly(int W, int H, const LineAA *E, int n, const ConvexChai
     }
     if (ymin <= ymax && (ymax - ymin + 1 > MINI_MAX || (xmin <= xmax && xmax - xmin + 1 > MINI_MAX))) return false;
     // interior spans of the (at most MINI_MAX) rows, evaluated once
+    // packed as (x1, x2) byte pairs relative to a provisional origin; the origin can only move left
+    // by the interior, which lies inside the outline footprint, so it is fixed up afterwards
     int sx1[MINI_MAX], sx2[MINI_MAX];
-#pragma unroll
-    for (int r = 0; r < MINI_MAX; r++) {
-        sx1[r] = 1; sx2[r] = 0;
-        const int y = ymin + r;
-        if (C.valid && ymin <= ymax && y >= fy0 && y <= fy1 && y <= ymax) {
+    for (int r = 0; r < MINI_MAX; r++) { sx1[r] = 1; sx2[r] = 0; }
+    if (C.valid && ymin <= ymax)
+        for (int y = fy0; y <= fy1; y++) {
+            const int r = y - ymin;
             convex_span(C, y, W, sx1[r], sx2[r]);
             if (sx1[r] <= sx2[r]) {
                 if (sx1[r] < xmin) xmin = sx1[r];
                 if (sx2[r] > xmax) xmax = sx2[r];
             }
         }
-    }
     if (xmin > xmax || ymin > ymax) {      // nothing visible: an empty record keeps the slot layout
         out[0] = rec_nop();
         for (int i = 1; i < minipoly_slots(n); i++) out[i] = rec_cont();
@@ -695,7 +695,6 @@ RIG_FN bool pack_minipoly(int W, int H, const LineAA *E, int n, const ConvexChai
     Rec &sp = out[1 + n];
     sp = rec_cont();
     uint32_t words[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
     for (int r = 0; r < MINI_MAX; r++) {
         uint32_t b1 = 1, b2 = 0;
         if (sx1[r] <= sx2[r]) { b1 = (uint32_t)(sx1[r] - xmin); b2 = (uint32_t)(sx2[r] - xmin); }
@@ -784,30 +783,24 @@ constexpr int CAP_SLOTS = 7;
 
 RIG_FN void cap_polygon(P2L c, long long rad, const float *sin_tab, P2L *v, int &nv)
 {
-    // EllipseEx(center c, axes (rad,rad), angle 0, 0..360), delta = 90 for rad < 3 px
-    P2L prev = {-1, -1};
-    nv = 0;
-    for (int a = 0; a <= 360; a += 90) {
-        double x = dmul((double)rad, (double)sin_tab[450 - a]);
-        double y = dmul((double)rad, (double)sin_tab[a]);
-        // alpha = cos(0) = 1.0f, beta = sin(0) = 0.0f
-        double px = dsub(dadd((double)c.x, dmul(x, 1.0)), dmul(y, 0.0));
-        double py = dadd(dadd((double)c.y, dmul(x, 0.0)), dmul(y, 1.0));
-        P2L pt;
-        pt.x = (long long)dround(dscale_down16(px)) * XY_ONE;
-        pt.y = (long long)dround(dscale_down16(py)) * XY_ONE;
-        pt.x += dround(dsub(px, (double)pt.x));
-        pt.y += dround(dsub(py, (double)pt.y));
-        if (pt.x != prev.x || pt.y != prev.y) { v[nv++] = pt; prev = pt; }
-    }
-    if (nv <= 1) { v[0] = v[1] = c; nv = 2; }
+    // EllipseEx(center c, axes (rad,rad), angle 0, 0..360) with delta = 90 (rad < 3 px): the polygon
+    // c + rad * (cos, sin) at 0, 90, 180, 270, 360 degrees.  SinTable is exactly 0 / +-1 / -0 at those
+    // angles, so every product and sum of the double-precision EllipseEx arithmetic is exact and the
+    // sub-pixel re-rounding is the identity: the vertices are c.x +- rad, c.y +- rad as integers.
+    (void)sin_tab;
+    if (rad == 0) { v[0] = v[1] = c; nv = 2; return; }
+    v[0].x = c.x + rad; v[0].y = c.y;
+    v[1].x = c.x;       v[1].y = c.y + rad;
+    v[2].x = c.x - rad; v[2].y = c.y;
+    v[3].x = c.x;       v[3].y = c.y - rad;
+    v[4] = v[0];
+    nv = 5;
 }
 
 // Records of one AA convex polygon (n <= 5 vertices) into out[0 .. budget): a MINIPOLY when it is small,
 // else (n == 4 only) 4 LINEAA + CONVEX.  Unused slots become NOPs.
 RIG_FN void emit_convex_aa(int W, int H, const P2L *v, int n, uint32_t color, const uint8_t *slope_corr, Rec *out, int budget)
 {
-    for (int i = 0; i < budget; i++) out[i] = rec_nop();
     LineAA E[MINI_MAX_EDGES];
     P2L p0 = v[n - 1];
     for (int i = 0; i < n; i++) {
@@ -815,11 +808,14 @@ RIG_FN void emit_convex_aa(int W, int H, const P2L *v, int n, uint32_t color, co
         p0 = v[i];
     }
     ConvexChains C = setup_convex(W, H, v, n);
-    if (minipoly_slots(n) <= budget && pack_minipoly(W, H, E, n, C, color, out)) return;
-    if (n + CONVEX_SLOTS <= budget) {
+    int used = 0;
+    if (minipoly_slots(n) <= budget && pack_minipoly(W, H, E, n, C, color, out)) used = minipoly_slots(n);
+    else if (n + CONVEX_SLOTS <= budget) {
         for (int i = 0; i < n; i++) out[i] = pack_lineaa(E[i], color, H);
         pack_convex(C, color, H, out + n);
+        used = n + CONVEX_SLOTS;
     }
+    for (int i = used; i < budget; i++) out[i] = rec_nop();      // every slot is written exactly once
 }
 
 // One ThickLine call.  p0,p1 in `shift` fractional bits (0 for polylines, 16 for circle arcs).
@@ -837,11 +833,13 @@ RIG_FN int emit_thick_line(int W, int H, P2L p0, P2L p1, int thickness, int flag
     }
     int ncap = (flags & 1) + ((flags >> 1) & 1);
     int nrec = QUAD_SLOTS + CAP_SLOTS * ncap;
-    for (int i = 0; i < nrec; i++) out[i] = rec_nop();
     if (shift == 0) {
         // OpenCV 4.13: integer end points are clipped to the canvas grown by `thickness` first
         P2L a = {p0.x + thickness, p0.y + thickness}, b = {p1.x + thickness, p1.y + thickness};
-        if (!clip_line((long long)W + 2 * thickness, (long long)H + 2 * thickness, a, b)) return nrec;
+        if (!clip_line((long long)W + 2 * thickness, (long long)H + 2 * thickness, a, b)) {
+            for (int i = 0; i < nrec; i++) out[i] = rec_nop();
+            return nrec;
+        }
         p0.x = a.x - thickness; p0.y = a.y - thickness;
         p1.x = b.x - thickness; p1.y = b.y - thickness;
     }
@@ -863,6 +861,8 @@ RIG_FN int emit_thick_line(int W, int H, P2L p0, P2L p1, int thickness, int flag
         pt[2].x = p1.x - dpx; pt[2].y = p1.y - dpy;
         pt[3].x = p1.x + dpx; pt[3].y = p1.y + dpy;
         emit_convex_aa(W, H, pt, 4, color, slope_corr, out + o, QUAD_SLOTS);
+    } else {
+        for (int i = 0; i < QUAD_SLOTS; i++) out[o + i] = rec_nop();
     }
     o += QUAD_SLOTS;
     for (int i = 0; i < 2; i++) {
@@ -871,6 +871,7 @@ RIG_FN int emit_thick_line(int W, int H, P2L p0, P2L p1, int thickness, int flag
             int nv;
             cap_polygon(p0, th, sin_tab, v, nv);
             if (nv >= 2 && nv <= 5) emit_convex_aa(W, H, v, nv, color, slope_corr, out + o, CAP_SLOTS);
+            else for (int i = 0; i < CAP_SLOTS; i++) out[o + i] = rec_nop();
             o += CAP_SLOTS;
         }
         p0 = p1;

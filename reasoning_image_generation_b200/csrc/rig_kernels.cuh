@@ -21,11 +21,14 @@
 namespace rig {
 
 #ifndef RIG_BAND_ROWS
-#define RIG_BAND_ROWS 4
+#define RIG_BAND_ROWS 8
 #endif
 constexpr int BAND_ROWS = RIG_BAND_ROWS;
 constexpr int RASTER_MAX_WARPS = BAND_ROWS >= 8 ? 16 : 32;
-constexpr int EXPAND_WARPS = 8;
+#ifndef RIG_EXPAND_WARPS
+#define RIG_EXPAND_WARPS 1
+#endif
+constexpr int EXPAND_WARPS = RIG_EXPAND_WARPS;   // 1: a CTA never waits for its slowest element
 
 enum Counter { CTR_REC = 0, CTR_AUX = 1, CTR_OVERFLOW = 2, CTR_WORK = 3, CTR_COUNT = 8 };
 
@@ -34,14 +37,16 @@ struct WarpSync {
 };
 
 __global__ void __launch_bounds__(EXPAND_WARPS * 32)
-k_expand(const DElem *__restrict__ elems, uint32_t e0, uint32_t e1, const ShapeTables *__restrict__ T, int W, int H,
+k_expand(const DElem *__restrict__ elems, const uint32_t *__restrict__ eorder, uint32_t e0, uint32_t e1,
+         const ShapeTables *__restrict__ T, int W, int H,
          ElemHdr *__restrict__ hdrs, Rec *__restrict__ recs, uint32_t rec_cap, Q16 *__restrict__ aux, uint32_t aux_cap,
          uint32_t *__restrict__ counters)
 {
     __shared__ ExpandScratch scratch[EXPAND_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t e = e0 + blockIdx.x * EXPAND_WARPS + warp;
-    if (e >= e1) return;
+    const uint32_t ei = e0 + blockIdx.x * EXPAND_WARPS + warp;
+    if (ei >= e1) return;
+    const uint32_t e = eorder[ei];      // costliest elements of the chunk first
     const DElem el = elems[e];
     ExpandScratch &S = scratch[warp];
     ElemPlan plan = expand_plan<32>(el, *T, W, H, lane, S, WarpSync());
@@ -146,6 +151,8 @@ struct RasterParams {
     uint32_t *counters;
     uint32_t p0, n_panels;         // panels [p0, p0 + n_panels) of the resident scene
     int W, H, grid_size;
+    int n_grid;                    // grid lines per direction (grid_size - 1, at most 15)
+    int16_t grid_x[16], grid_y[16]; // int(round(i * W / grid_size)) etc. (generator.py:117,121), computed on the host
     uint32_t bg;                   // c0 | c1<<8 | c2<<16
     uint32_t max_claim, heavy_bands; // scheduling: largest claim; the first heavy_bands bands (costliest panels) are claimed singly
 };
@@ -177,8 +184,8 @@ __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const Raste
         }
         if (threadIdx.x < 64) filter[threadIdx.x] = P.tables->filter[threadIdx.x];
         __syncthreads();
-        for (int g = 1; g < P.grid_size; g++) {
-            int x = dround(ddiv((double)(g * P.W), (double)P.grid_size));
+        for (int g = 0; g < P.n_grid; g++) {
+            const int x = P.grid_x[g];
             if ((unsigned)x < (unsigned)P.W && threadIdx.x < BAND_ROWS) put3(tmpl1 + (threadIdx.x * P.W + x) * 3, 0u);
         }
         fence_async_smem();
@@ -188,6 +195,10 @@ __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const Raste
     const int bands_per_panel = P.H / BAND_ROWS;
     const uint32_t total_bands = P.n_panels * (uint32_t)bands_per_panel;
     bool dirty = false;   // my band buffer has an outstanding bulk read
+    uint32_t cur_slot = 0xffffffffu, panel = 0, eb = 0, ee = 0;
+    bool use_grid = false;
+    ElemHdr myh;
+    myh.rec_begin = 0; myh.nrec = 0; myh.ymin = 1; myh.ymax = 0; myh.nsum = 0;
     RasterOps ops;
     ops.mine = rec_nop(); ops.j = 0; ops.base = P.recs;
 
@@ -206,26 +217,33 @@ __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const Raste
         take = __shfl_sync(0xffffffffu, take, 0);
         if (first >= total_bands) break;
         for (uint32_t bi = first; bi < first + take && bi < total_bands; bi++) {
-            const uint32_t panel = P.order[P.p0 + bi / bands_per_panel], pl = panel - P.p0;
-            const int band = (int)(bi % bands_per_panel);
+            // panel metadata is fetched once per panel, not once per band: consecutive claims mostly stay in one panel
+            const uint32_t slot = bi / bands_per_panel;
+            if (slot != cur_slot) {
+                cur_slot = slot;
+                panel = P.order[P.p0 + slot];
+                eb = P.panel_begin[panel];
+                ee = P.panel_begin[panel + 1];
+                use_grid = P.panel_flags[panel] & 1;
+                myh.rec_begin = 0; myh.nrec = 0; myh.ymin = 1; myh.ymax = 0; myh.nsum = 0;
+                if (eb + lane < ee) myh = P.hdrs[eb + lane];     // lane e keeps the header of the panel's e-th element
+            }
+            const uint32_t pl = panel - P.p0;
+            const int band = (int)(bi - slot * bands_per_panel);
             Band B;
             B.r0 = band * BAND_ROWS; B.r1 = B.r0 + BAND_ROWS - 1; B.W = P.W; B.H = P.H; B.buf = mine;
             uint8_t *gdst = P.out + ((size_t)pl * P.H + B.r0) * (size_t)P.W * 3;
-            const uint32_t eb = P.panel_begin[panel], ee = P.panel_begin[panel + 1];
-            const bool use_grid = P.panel_flags[panel] & 1;
             // ---- is anything drawn into this band?
-            bool any = false;
-            for (uint32_t e = eb + lane; e < ee; e += 32) {
-                ElemHdr h = P.hdrs[e];
-                any |= h.ymin <= B.r1 && h.ymax >= B.r0;
+            bool mine_hits = myh.ymin <= B.r1 && myh.ymax >= B.r0;
+            bool more = false;                                     // panels with more than 32 elements: the rest from memory
+            for (uint32_t e = eb + 32 + lane; e < ee; e += 32) {
+                const ElemHdr h = P.hdrs[e];
+                more |= h.ymin <= B.r1 && h.ymax >= B.r0;
             }
-            if (use_grid) {
-                for (int g = 1; g < P.grid_size; g++) {
-                    int y = dround(ddiv((double)(g * P.H), (double)P.grid_size));
-                    any |= y >= B.r0 && y <= B.r1;
-                }
-            }
-            any = __any_sync(0xffffffffu, any);
+            bool gline = false;
+            if (use_grid && lane < P.n_grid) gline = P.grid_y[lane] >= B.r0 && P.grid_y[lane] <= B.r1;
+            const uint32_t emask = __ballot_sync(0xffffffffu, mine_hits);
+            const bool any = emask != 0u || __any_sync(0xffffffffu, more || gline);
             if (!any) {
                 if (lane == 0) bulk_store(gdst, use_grid ? tmpl1 : tmpl0, band_bytes);
                 continue;
@@ -242,8 +260,18 @@ __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const Raste
             }
             __syncwarp();
             for (uint32_t e = eb; e < ee; e++) {
-                const ElemHdr h = P.hdrs[e];
-                if (h.ymin > B.r1 || h.ymax < B.r0) continue;
+                ElemHdr h;
+                if (e - eb < 32u) {
+                    if (!((emask >> (e - eb)) & 1u)) continue;
+                    const int src = (int)(e - eb);
+                    h.rec_begin = __shfl_sync(0xffffffffu, myh.rec_begin, src);
+                    h.nrec = __shfl_sync(0xffffffffu, myh.nrec, src);
+                    h.nsum = __shfl_sync(0xffffffffu, myh.nsum, src);
+                    h.ymin = 0; h.ymax = 0;
+                } else {
+                    h = P.hdrs[e];
+                    if (h.ymin > B.r1 || h.ymax < B.r0) continue;
+                }
                 const uint32_t *sums = (const uint32_t *)(P.recs + h.rec_begin);
                 const Rec *payload = P.recs + h.rec_begin + h.nsum;
                 const uint32_t nwin = (h.nrec + 31u) / 32u;
@@ -282,7 +310,7 @@ __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const Raste
                     }
                 }
             }
-            if (use_grid) draw_grid<32>(B, P.grid_size, lane);
+            if (use_grid) draw_grid<32>(B, P.n_grid, P.grid_x, P.grid_y, lane);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) bulk_store(gdst, mine, band_bytes);

@@ -224,13 +224,13 @@ RIG_HD void exec_record(const Rec &r, const Q16 *aux, const uint8_t *filter, con
     }
 }
 
-// grid lines of a use_grid panel (generator.py:112-122): 1-px LINE_8 black lines, drawn last
+// grid lines of a use_grid panel (generator.py:112-122): 1-px LINE_8 black lines, drawn last.
+// gx / gy: the n line positions int(round(i * W / grid_size)), int(round(i * H / grid_size)).
 template <int LANES>
-RIG_HD void draw_grid(const Band &b, int grid_size, int lane)
+RIG_HD void draw_grid(const Band &b, int n, const int16_t *gx, const int16_t *gy, int lane)
 {
-    for (int i = 1; i < grid_size; i++) {
-        int x = dround(ddiv((double)(i * b.W), (double)grid_size));
-        int y = dround(ddiv((double)(i * b.H), (double)grid_size));
+    for (int i = 0; i < n; i++) {
+        const int x = gx[i], y = gy[i];
         if ((unsigned)x < (unsigned)b.W)
             for (int yy = b.r0 + lane; yy <= b.r1; yy += LANES) put3(band_px(b, x, yy), 0u);
         if (y >= b.r0 && y <= b.r1) fill_span<LANES>(b, y, 0, b.W - 1, 0u, lane);

@@ -96,7 +96,15 @@ extern "C" int emul_render(const rig_scene *scene, int W, int H, int band_rows, 
                     exec_record<1>(recs[pb + k], aux.data(), T.filter, b, 0, RS, ops);
                 }
             }
-            if (use_grid) draw_grid<1>(b, gs, 0);
+            if (use_grid) {
+                int16_t gx[16], gy[16];
+                for (int g = 1; g < gs && g <= 16; g++) {
+                    volatile double qx = (double)(g * W) / (double)gs, qy = (double)(g * H) / (double)gs;
+                    gx[g - 1] = (int16_t)nearbyint(qx);
+                    gy[g - 1] = (int16_t)nearbyint(qy);
+                }
+                draw_grid<1>(b, gs - 1, gx, gy, 0);
+            }
         }
     }
     if (nrec_out) *nrec_out = total;
