@@ -66,7 +66,7 @@ typedef struct rig_scene {
 typedef struct rig_ctx rig_ctx;
 
 /* Creates a context on CUDA device `device` for W x H panels, at most `max_panels` panels and
- * `max_elements` elements per call.  W must be a multiple of 4 and H a multiple of 8.               */
+ * `max_elements` elements per call.  W must be a multiple of 16 (16-byte aligned rows).             */
 int rig_create(int device, int W, int H, int max_panels, int max_elements, rig_ctx **out);
 void rig_destroy(rig_ctx *ctx);
 /* Message of the last failing call on this context (ctx == NULL: of the last failing rig_create). */

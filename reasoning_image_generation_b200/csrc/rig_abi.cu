@@ -232,9 +232,9 @@ int launch_chunk(rig_ctx *c, const Chunk &ch, uint8_t *out_dev, cudaStream_t st)
         while (heavy < ch.p1 - ch.p0 && heavy < (ch.p1 - ch.p0) / std::max(1u, c->heavy_div) &&
                c->panel_cost[c->h_order[ch.p0 + heavy]] >= 2.0 * mean && c->panel_cost[c->h_order[ch.p0 + heavy]] > 0)
             heavy++;
-        P.heavy_bands = c->heavy_div ? heavy * (uint32_t)(c->H / BAND_ROWS) : 0u;
+        P.heavy_bands = c->heavy_div ? heavy * (uint32_t)((c->H + BAND_ROWS - 1) / BAND_ROWS) : 0u;
     }
-    const uint32_t bands = P.n_panels * (uint32_t)(c->H / BAND_ROWS);
+    const uint32_t bands = P.n_panels * (uint32_t)((c->H + BAND_ROWS - 1) / BAND_ROWS);
     const uint32_t want = (bands + c->raster_warps - 1) / c->raster_warps;
     const uint32_t grid = std::max(1u, std::min((uint32_t)c->sm_count, want));
     k_raster<<<grid, c->raster_warps * 32, c->raster_smem, st>>>(P);
@@ -310,8 +310,8 @@ int rig_create(int device, int W, int H, int max_panels, int max_elements, rig_c
 {
     if (!out) return fail(nullptr, RIG_E_INVALID, "out is NULL");
     *out = nullptr;
-    if (W <= 0 || H <= 0 || W % 4 || (3 * W * BAND_ROWS) % 16 || H % BAND_ROWS || W > 4096 || H > 4096)
-        return fail(nullptr, RIG_E_INVALID, "unsupported canvas %dx%d (W %% 4 == 0, H %% %d == 0, <= 4096)", W, H, BAND_ROWS);
+    if (W <= 0 || H <= 0 || W % 16 || W > 4096 || H > 4096)
+        return fail(nullptr, RIG_E_INVALID, "unsupported canvas %dx%d (W %% 16 == 0 so that rows are 16-byte aligned; <= 4096)", W, H);
     if (max_panels <= 0 || max_elements <= 0) return fail(nullptr, RIG_E_INVALID, "max_panels/max_elements must be positive");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);

@@ -21,10 +21,11 @@
 namespace rig {
 
 #ifndef RIG_BAND_ROWS
-#define RIG_BAND_ROWS 8
+#define RIG_BAND_ROWS 5
 #endif
 constexpr int BAND_ROWS = RIG_BAND_ROWS;
-constexpr int RASTER_MAX_WARPS = BAND_ROWS >= 8 ? 16 : 32;
+// warps per CTA: as many band buffers (+2 templates) as fit 227 KB at W = 512, and registers to match
+constexpr int RASTER_MAX_WARPS = BAND_ROWS >= 8 ? 16 : BAND_ROWS == 7 ? 19 : BAND_ROWS == 6 ? 22 : BAND_ROWS == 5 ? 27 : 32;
 #ifndef RIG_EXPAND_WARPS
 #define RIG_EXPAND_WARPS 1
 #endif
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const Raste
         __syncthreads();
     }
     // rows of the horizontal grid lines
-    const int bands_per_panel = P.H / BAND_ROWS;
+    const int bands_per_panel = (P.H + BAND_ROWS - 1) / BAND_ROWS;   // the last band of a panel may be shorter
     const uint32_t total_bands = P.n_panels * (uint32_t)bands_per_panel;
     bool dirty = false;   // my band buffer has an outstanding bulk read
     uint32_t cur_slot = 0xffffffffu, panel = 0, eb = 0, ee = 0;
@@ -232,6 +233,8 @@ __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const Raste
             const int band = (int)(bi - slot * bands_per_panel);
             Band B;
             B.r0 = band * BAND_ROWS; B.r1 = B.r0 + BAND_ROWS - 1; B.W = P.W; B.H = P.H; B.buf = mine;
+            if (B.r1 > P.H - 1) B.r1 = P.H - 1;
+            const uint32_t out_bytes = (uint32_t)(3 * P.W * (B.r1 - B.r0 + 1));
             uint8_t *gdst = P.out + ((size_t)pl * P.H + B.r0) * (size_t)P.W * 3;
             // ---- is anything drawn into this band?
             bool mine_hits = myh.ymin <= B.r1 && myh.ymax >= B.r0;
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const Raste
             const uint32_t emask = __ballot_sync(0xffffffffu, mine_hits);
             const bool any = emask != 0u || __any_sync(0xffffffffu, more || gline);
             if (!any) {
-                if (lane == 0) bulk_store(gdst, use_grid ? tmpl1 : tmpl0, band_bytes);
+                if (lane == 0) bulk_store(gdst, use_grid ? tmpl1 : tmpl0, out_bytes);
                 continue;
             }
             // ---- build the band in shared memory
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const Raste
             if (use_grid) draw_grid<32>(B, P.n_grid, P.grid_x, P.grid_y, lane);
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) bulk_store(gdst, mine, band_bytes);
+            if (lane == 0) bulk_store(gdst, mine, out_bytes);
             dirty = true;
         }
     }

@@ -41,7 +41,7 @@ def test_bad_canvas_is_rejected_before_touching_cuda(built):
     lib = _abi.load()
     h = ctypes.c_void_p()
     assert lib.rig_create(0, 510, 512, 16, 64, ctypes.byref(h)) == _abi.RIG_E_INVALID
-    assert lib.rig_create(0, 512, 508, 16, 64, ctypes.byref(h)) == _abi.RIG_E_INVALID
+    assert lib.rig_create(0, 512, 0, 16, 64, ctypes.byref(h)) == _abi.RIG_E_INVALID
 
 
 def test_shape_tables_equal_the_python_expressions_of_the_reference(built):
