@@ -22,18 +22,17 @@ constexpr int HASH_WORDS = HASH_GRID * HASH_GRID / 64;   // uint64 words per has
 __global__ void __launch_bounds__(256)
 k_block_sums(const uint8_t *__restrict__ imgs, int W, int H, uint32_t coef, uint32_t *__restrict__ sums)
 {
-    __shared__ uint32_t acc[8][HASH_GRID];
+    __shared__ uint32_t acc[HASH_GRID];
     const int img = blockIdx.x / HASH_GRID, by = blockIdx.x % HASH_GRID;
     const int bh = H / HASH_GRID, bw = W / HASH_GRID;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < HASH_GRID) acc[threadIdx.x] = 0;
+    __syncthreads();
     const uint32_t *base = (const uint32_t *)(imgs + ((size_t)img * H + (size_t)by * bh) * (size_t)W * 3);
     const int words_per_row = W * 3 / 4, quads_per_row = W / 4;     // a quad = 4 pixels = 3 words
-    uint32_t mine[HASH_GRID];
-#pragma unroll
-    for (int k = 0; k < HASH_GRID; k++) mine[k] = 0;
+    const int lanes_per_block = bw / 4;                             // a power of two (checked on the host)
     for (int row = warp; row < bh; row += 8) {
         const uint32_t *rp = base + (size_t)row * words_per_row;
-        // 32 lanes x 4 pixels = 128 pixels per sweep; bw >= 16 and 128 / bw blocks per sweep
         for (int q0 = 0; q0 < quads_per_row; q0 += 32) {
             const int q = q0 + lane;
             uint32_t s = 0;
@@ -42,32 +41,14 @@ k_block_sums(const uint8_t *__restrict__ imgs, int W, int H, uint32_t coef, uint
                 s = (__dp4a(w0 & 0x00ffffffu, coef, 0u) >> 8) + (__dp4a(__byte_perm(w0, w1, 0x4543) & 0x00ffffffu, coef, 0u) >> 8) +
                     (__dp4a(__byte_perm(w1, w2, 0x4432) & 0x00ffffffu, coef, 0u) >> 8) + (__dp4a(w2 >> 8, coef, 0u) >> 8);
             }
-            // lanes of one block are contiguous: segmented sum over groups of bw/4 lanes (a power of two for W = 512)
-            const int lanes_per_block = bw / 4;
+            // lanes of one block are contiguous: segmented sum over groups of lanes_per_block lanes
             for (int o = 1; o < lanes_per_block && o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lanes_per_block >= 32) {
-                if (lane == 0) mine[(q0 * 4) / bw] += s;
-            } else if ((lane & (lanes_per_block - 1)) == 0 && q < quads_per_row) {
-                const int bx = (q * 4) / bw;
-#pragma unroll
-                for (int k = 0; k < HASH_GRID; k++) if (k == bx) mine[k] += s;
-            }
+            const int group = lanes_per_block < 32 ? lanes_per_block : 32;
+            if ((lane & (group - 1)) == 0 && q < quads_per_row) atomicAdd(&acc[(q * 4) / bw], s);
         }
     }
-    // fold the per-lane partial sums of each block: lane l kept block (sweep, l / lanes_per_block)
-#pragma unroll
-    for (int k = 0; k < HASH_GRID; k++) {
-        uint32_t v = mine[k];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) acc[warp][k] = v;
-    }
     __syncthreads();
-    if (threadIdx.x < HASH_GRID) {
-        uint32_t v = 0;
-        for (int w = 0; w < 8; w++) v += acc[w][threadIdx.x];
-        sums[(size_t)img * HASH_GRID * HASH_GRID + by * HASH_GRID + threadIdx.x] = v;
-    }
+    if (threadIdx.x < HASH_GRID) sums[(size_t)img * HASH_GRID * HASH_GRID + by * HASH_GRID + threadIdx.x] = acc[threadIdx.x];
 }
 
 // One warp per image: sums -> 256-bit hash
