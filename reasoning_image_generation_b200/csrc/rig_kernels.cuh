@@ -37,7 +37,10 @@ struct WarpSync {
     __device__ __forceinline__ void operator()() const { __syncwarp(); }
 };
 
-__global__ void __launch_bounds__(EXPAND_WARPS * 32)
+#ifndef RIG_EXPAND_MIN_CTAS
+#define RIG_EXPAND_MIN_CTAS 20
+#endif
+__global__ void __launch_bounds__(EXPAND_WARPS * 32, RIG_EXPAND_MIN_CTAS)
 k_expand(const DElem *__restrict__ elems, const uint32_t *__restrict__ eorder, uint32_t e0, uint32_t e1,
          const ShapeTables *__restrict__ T, int W, int H,
          ElemHdr *__restrict__ hdrs, Rec *__restrict__ recs, uint32_t rec_cap, Q16 *__restrict__ aux, uint32_t aux_cap,

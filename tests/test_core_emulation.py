@@ -67,3 +67,28 @@ def test_unsupported_inputs_are_rejected(emul_lib):
     sb.add_panel([dict(kind='square', size=100, fill=True, stroke_width=9, center=(1, 1), angle=0, color=(1, 2, 3))])
     rc, _, _, err = emul_render_scene(emul_lib, sb.finish(), 8)
     assert rc == -4 and 'stroke_width' in err
+
+
+def test_fuzzed_elements_match_oracle(emul_lib):
+    """Elements far outside the sampler's range (sizes 1..300, stroke 0..4, any angle, centres off-canvas)."""
+    import random
+    rng = random.Random(77)
+    sb = SceneBuilder(512, 512, bg_color=(250, 240, 230))
+    panels = []
+    for p in range(60):
+        els = []
+        for _ in range(rng.randint(0, 6)):
+            els.append(dict(kind=rng.choice(ref_render.KINDS), size=rng.choice([1, 2, 7, 30, 31, 60, 99, 128, 170, 255, 300]),
+                            fill=rng.random() < 0.5, stroke_width=rng.randint(0, 4),
+                            center=(rng.uniform(-300, 800), rng.uniform(-300, 800)) if rng.random() < 0.5
+                            else (rng.randint(-40, 552), rng.randint(-40, 552)),
+                            angle=rng.choice([rng.randint(-720, 720), rng.uniform(0, 360), 0, 45, 90]),
+                            color=(rng.randint(0, 255), rng.randint(0, 255), rng.randint(0, 255))))
+        panels.append((els, rng.random() < 0.5))
+        sb.add_panel(els, panels[-1][1])
+    rc, out, nrec, err = emul_render_scene(emul_lib, sb.finish(), 5)
+    assert rc == 0, err
+    be = ref_render.CBackend()
+    for p, (els, ug) in enumerate(panels):
+        ref = ref_render.render_panel(512, 512, (250, 240, 230), els, ug, 3, backend=be)
+        assert (ref == out[p]).all(), (p, els)

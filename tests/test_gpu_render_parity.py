@@ -141,3 +141,47 @@ def test_errors_are_reported_not_swallowed(renderer, built):
     small.close()
     with pytest.raises(RigError):
         Renderer(512, 512, device=99)
+
+
+def test_fuzzed_elements_match_oracle(renderer):
+    """Random element dicts far outside what the sampler emits (any angle, odd sizes, float centres well outside the
+    canvas, stroke 0..4, up to 10 elements) -- one batch through the C ABI, every panel against the oracle."""
+    import random
+    rng = random.Random(20251018)
+    kinds = ref_render.KINDS
+    panels = []
+    for p in range(160):
+        els = []
+        for _ in range(rng.randint(0, 10)):
+            els.append(dict(kind=rng.choice(kinds), size=rng.choice([1, 2, 7, 30, 31, 60, 99, 128, 170, 255, 300]),
+                            fill=rng.random() < 0.5, stroke_width=rng.randint(0, 4),
+                            center=(rng.uniform(-300, 800), rng.uniform(-300, 800)) if rng.random() < 0.5
+                            else (rng.randint(-40, 552), rng.randint(-40, 552)),
+                            angle=rng.choice([rng.randint(-720, 720), rng.uniform(0, 360), 0, 45, 90]),
+                            color=(rng.randint(0, 255), rng.randint(0, 255), rng.randint(0, 255))))
+        panels.append((els, rng.random() < 0.5))
+    sb = SceneBuilder(512, 512, bg_color=(250, 240, 230))
+    for els, ug in panels:
+        sb.add_panel(els, ug)
+    out = renderer.render(sb.finish(), 'bgr')
+    be = ref_render.CBackend()
+    for p, (els, ug) in enumerate(panels):
+        ref = ref_render.render_panel(512, 512, (250, 240, 230), els, ug, 3, backend=be)
+        assert (ref == out[p]).all(), (p, els)
+
+
+def test_record_arena_overflow_is_retried_not_silently_wrong(built):
+    """Wrap-around copies make an element up to 4x larger than the host's sizing estimate: the library must notice the
+    arena overflow and re-render in smaller chunks (host destination) or report it (resident scene)."""
+    els = [dict(kind='crescent', size=300, fill=True, stroke_width=3, center=(2, 2), angle=30, color=(9, 99, 199)),
+           dict(kind='heart', size=300, fill=True, stroke_width=3, center=(510, 509), angle=45, color=(9, 99, 199))]
+    sb = SceneBuilder(512, 512)
+    for _ in range(24):
+        sb.add_panel(els, False)
+    sc = sb.finish()
+    small = Renderer(512, 512, device=0, max_panels=24, max_elements=48)     # arena = the 65 536-slot minimum
+    out = small.render(sc, 'bgr')
+    be = ref_render.CBackend()
+    ref = ref_render.render_panel(512, 512, (255, 255, 255), els, False, 3, backend=be)
+    assert (out == ref[None]).all()
+    small.close()

@@ -18,7 +18,7 @@ for _ in range(5): r.render_resident(out.data_ptr(), stream=st)
 torch.cuda.synchronize(); r.sync(); s = r.stats()
 print("expand %%.3f raster %%.3f ms" %% (s['expand_ms']/5, s['raster_ms']/5))
 ''' % root
-for lib, mc, hd, w in [('b8', 16, 4, 16), ('b7', 16, 4, 19), ('b6', 16, 4, 22), ('b5', 16, 4, 27)]:
+for lib, mc, hd, w in [('e1', 16, 4, 27), ('e20', 16, 4, 27), ('e24', 16, 4, 27), ('e28', 16, 4, 27)]:
     env = dict(os.environ, RIG_LIB=os.path.join(root, 'reasoning_image_generation_b200', 'librig_%s.so' % lib),
                RIG_MAX_CLAIM=str(mc), RIG_HEAVY_DIV=str(hd), RIG_WARPS=str(w))
     o = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True)
