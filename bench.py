@@ -251,7 +251,7 @@ def run_ours(args):
     # ---- near-duplicate stage (reported beside `value`, not part of it)
     # (1) perceptual hash of the rendered step (HBM-read-bound: 786,432 B per image)
     f = DedupFilter(r)
-    hashes = f.hash_images(out[:256], 'rgb')                      # warm-up (lazy module load)
+    hashes = f.hash_images(out, 'rgb')                            # warm-up (lazy module load, scratch allocation)
     torch.cuda.synchronize(); r.sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

@@ -526,9 +526,9 @@ int rig_hash_batch(rig_ctx *c, const uint8_t *imgs_dev, int n, int layout, uint6
     if (n < 0 || (n && (!imgs_dev || !hashes_dev))) return fail(c, RIG_E_INVALID, "bad arguments to rig_hash_batch");
     if (layout != RIG_LAYOUT_RGB && layout != RIG_LAYOUT_BGR) return fail(c, RIG_E_INVALID, "bad layout %d", layout);
     {
-        const int lpb = c->W / HASH_GRID / 4;     // lanes per hash block in k_block_sums
+        const int lpb = c->W / HASH_GRID / 16;    // lanes per hash block in k_block_sums
         if (c->W % (16 * HASH_GRID) || c->H % HASH_GRID || (lpb & (lpb - 1)))
-            return fail(c, RIG_E_UNSUPPORTED, "hashing needs W %% %d == 0, W / 64 a power of two and H %% %d == 0", 16 * HASH_GRID, HASH_GRID);
+            return fail(c, RIG_E_UNSUPPORTED, "hashing needs W %% %d == 0, W / 256 a power of two and H %% %d == 0", 16 * HASH_GRID, HASH_GRID);
     }
     if (((uintptr_t)imgs_dev) % 16) return fail(c, RIG_E_INVALID, "imgs_dev must be 16-byte aligned");
     if (n == 0) return RIG_OK;

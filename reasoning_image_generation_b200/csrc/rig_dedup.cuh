@@ -15,10 +15,17 @@ namespace rig {
 constexpr int HASH_GRID = 16;                       // 16 x 16 blocks
 constexpr int HASH_WORDS = HASH_GRID * HASH_GRID / 64;   // uint64 words per hash
 
-// One CTA per (image, block-row), 8 warps; a warp sweeps rows of the block-row.  A lane reads 4 pixels
-// (3 aligned 32-bit words), luma per pixel is one byte-permute + one dp4a, and a 16-pixel group (4 lanes)
-// always lies inside one block (W / 16 is a multiple of 16), so block sums are shuffles, not atomics.
+// One CTA per (image, block-row), 8 warps; a warp sweeps rows of the block-row.  A lane reads 16 pixels
+// (3 aligned 128-bit words = 4 quads of 3 words), luma per pixel is one byte-permute + one dp4a, and a
+// 16-pixel group always lies inside one block (W / 16 is a multiple of 16), so block sums are shuffles
+// plus one shared atomic per block and sweep.
 // coef = 77 | 150 << 8 | 29 << 16 for RGB byte order, 29 | 150 << 8 | 77 << 16 for BGR.
+__device__ __forceinline__ uint32_t luma4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t coef)
+{
+    return (__dp4a(w0 & 0x00ffffffu, coef, 0u) >> 8) + (__dp4a(__byte_perm(w0, w1, 0x4543) & 0x00ffffffu, coef, 0u) >> 8) +
+           (__dp4a(__byte_perm(w1, w2, 0x4432) & 0x00ffffffu, coef, 0u) >> 8) + (__dp4a(w2 >> 8, coef, 0u) >> 8);
+}
+
 __global__ void __launch_bounds__(256)
 k_block_sums(const uint8_t *__restrict__ imgs, int W, int H, uint32_t coef, uint32_t *__restrict__ sums)
 {
@@ -28,23 +35,22 @@ k_block_sums(const uint8_t *__restrict__ imgs, int W, int H, uint32_t coef, uint
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < HASH_GRID) acc[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t *base = (const uint32_t *)(imgs + ((size_t)img * H + (size_t)by * bh) * (size_t)W * 3);
-    const int words_per_row = W * 3 / 4, quads_per_row = W / 4;     // a quad = 4 pixels = 3 words
-    const int lanes_per_block = bw / 4;                             // a power of two (checked on the host)
+    const uint4 *base = (const uint4 *)(imgs + ((size_t)img * H + (size_t)by * bh) * (size_t)W * 3);
+    const int vec_per_row = W * 3 / 16, groups_per_row = W / 16;    // a group = 16 pixels = 3 uint4
+    const int lanes_per_block = bw / 16;                            // a power of two (checked on the host)
     for (int row = warp; row < bh; row += 8) {
-        const uint32_t *rp = base + (size_t)row * words_per_row;
-        for (int q0 = 0; q0 < quads_per_row; q0 += 32) {
-            const int q = q0 + lane;
+        const uint4 *rp = base + (size_t)row * vec_per_row;
+        for (int g0 = 0; g0 < groups_per_row; g0 += 32) {
+            const int g = g0 + lane;
             uint32_t s = 0;
-            if (q < quads_per_row) {
-                const uint32_t w0 = __ldg(rp + 3 * q), w1 = __ldg(rp + 3 * q + 1), w2 = __ldg(rp + 3 * q + 2);
-                s = (__dp4a(w0 & 0x00ffffffu, coef, 0u) >> 8) + (__dp4a(__byte_perm(w0, w1, 0x4543) & 0x00ffffffu, coef, 0u) >> 8) +
-                    (__dp4a(__byte_perm(w1, w2, 0x4432) & 0x00ffffffu, coef, 0u) >> 8) + (__dp4a(w2 >> 8, coef, 0u) >> 8);
+            if (g < groups_per_row) {
+                const uint4 a = __ldg(rp + 3 * g), b = __ldg(rp + 3 * g + 1), c = __ldg(rp + 3 * g + 2);
+                s = luma4(a.x, a.y, a.z, coef) + luma4(a.w, b.x, b.y, coef) + luma4(b.z, b.w, c.x, coef) + luma4(c.y, c.z, c.w, coef);
             }
             // lanes of one block are contiguous: segmented sum over groups of lanes_per_block lanes
             for (int o = 1; o < lanes_per_block && o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             const int group = lanes_per_block < 32 ? lanes_per_block : 32;
-            if ((lane & (group - 1)) == 0 && q < quads_per_row) atomicAdd(&acc[(q * 4) / bw], s);
+            if ((lane & (group - 1)) == 0 && g < groups_per_row) atomicAdd(&acc[(g * 16) / bw], s);
         }
     }
     __syncthreads();
