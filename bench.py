@@ -260,6 +260,16 @@ def run_ours(args):
     e1.record(stream)
     barrier(); r.sync()
     hash_ms = e0.elapsed_time(e1)
+    # (1b) the same hashes from the fused variant (block sums taken from the band while it is in shared memory)
+    fused = torch.empty_like(hashes)
+    r.render_resident_hashed(out.data_ptr(), fused.data_ptr(), stream=st)
+    barrier(); r.sync()
+    e0.record(stream)
+    r.render_resident_hashed(out.data_ptr(), fused.data_ptr(), stream=st)
+    e1.record(stream)
+    barrier(); r.sync()
+    fused_ms = e0.elapsed_time(e1)
+    fused_equal = bool(torch.equal(fused, hashes))
     drop_r, hits_r = f.scan(hashes, 10)                           # also the warm-up of the scan kernel
     torch.cuda.synchronize(); r.sync()
     # (2) all-pairs scan on the SURVEY 8(d) timing input: uniform random 256-bit hashes (seed 0) with 1 % planted
@@ -326,6 +336,7 @@ def run_ours(args):
                       'input': 'uniform random 256-bit hashes, seed 0, 1 % planted near-duplicates (SURVEY 8d)',
                       'exchange': 'nccl all_gather + max all_reduce' if dist is not None else 'none (1 rank)',
                       'hash_images_per_s': world * n / (hash_ms / 1e3), 'hash_read_gbs_per_gpu': n * IMG_BYTES / (hash_ms / 1e3) / 1e9,
+                      'render_plus_fused_hash_ms_per_step': fused_ms, 'fused_hash_equals_standalone': fused_equal,
                       'rendered_step_dropped': int(drop_r.sum().item())},
             'clocks': clocks,
         }

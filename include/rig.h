@@ -88,6 +88,11 @@ int rig_render_batch(rig_ctx *ctx, const rig_scene *scene, uint8_t *out, int out
 int rig_scene_upload(rig_ctx *ctx, const rig_scene *scene, int out_layout, void *stream);
 int rig_render_resident(rig_ctx *ctx, uint8_t *out_device, void *stream);
 
+/* The same, with the perceptual hash of every panel (see rig_hash_batch) accumulated inside the rasteriser while each
+ * band of rows is still in shared memory: hashes_device receives n_panels * 4 uint64, bit-identical to
+ * rig_hash_batch(out_device), without re-reading the pixels from HBM.                                                  */
+int rig_render_resident_hashed(rig_ctx *ctx, uint8_t *out_device, uint64_t *hashes_device, void *stream);
+
 int rig_sync(rig_ctx *ctx);
 
 /* Counters of the last render on this context (for bench.py's gpu_launches / diagnostics). */

@@ -56,7 +56,7 @@ class RigStats(ctypes.Structure):
 # every symbol include/rig.h declares; tests check that the built library exports all of them
 EXPORTS = (
     'rig_create', 'rig_destroy', 'rig_last_error', 'rig_render_batch', 'rig_scene_upload',
-    'rig_render_resident', 'rig_sync', 'rig_get_stats', 'rig_set_profiling', 'rig_debug_shape_tables',
+    'rig_render_resident', 'rig_render_resident_hashed', 'rig_sync', 'rig_get_stats', 'rig_set_profiling', 'rig_debug_shape_tables',
     'rig_hash_batch', 'rig_dedup', 'rig_hash_words', 'rig_pinned_alloc', 'rig_pinned_free',
 )
 
@@ -87,6 +87,8 @@ def load() -> ctypes.CDLL:
     lib.rig_scene_upload.restype = ctypes.c_int
     lib.rig_render_resident.argtypes = [vp, vp, vp]
     lib.rig_render_resident.restype = ctypes.c_int
+    lib.rig_render_resident_hashed.argtypes = [vp, vp, vp, vp]
+    lib.rig_render_resident_hashed.restype = ctypes.c_int
     lib.rig_sync.argtypes = [vp]
     lib.rig_sync.restype = ctypes.c_int
     lib.rig_get_stats.argtypes = [vp, ctypes.POINTER(RigStats)]

@@ -53,6 +53,7 @@ struct rig_ctx {
     uint8_t *d_stage[2] = {nullptr, nullptr};
     size_t stage_panels = 0;
     uint32_t *d_sums = nullptr;       // per-image block sums of the hash stage
+    int16_t *d_gridx = nullptr;       // vertical grid line positions for the fused hash
     size_t sums_cap = 0;
     // resident scene
     int n_panels = 0, n_elements = 0, grid_size = 3, layout = RIG_LAYOUT_RGB;
@@ -199,7 +200,7 @@ void resolve_profiling(rig_ctx *c)
     c->ev_panels.clear();
 }
 
-int launch_chunk(rig_ctx *c, const Chunk &ch, uint8_t *out_dev, cudaStream_t st)
+int launch_chunk(rig_ctx *c, const Chunk &ch, uint8_t *out_dev, cudaStream_t st, bool hash = false)
 {
     CK(c, cudaMemsetAsync(c->d_counters, 0, CTR_COUNT * sizeof(uint32_t), st));
     const uint32_t ne = ch.e1 - ch.e0;
@@ -237,7 +238,10 @@ int launch_chunk(rig_ctx *c, const Chunk &ch, uint8_t *out_dev, cudaStream_t st)
     const uint32_t bands = P.n_panels * (uint32_t)((c->H + BAND_ROWS - 1) / BAND_ROWS);
     const uint32_t want = (bands + c->raster_warps - 1) / c->raster_warps;
     const uint32_t grid = std::max(1u, std::min((uint32_t)c->sm_count, want));
-    k_raster<<<grid, c->raster_warps * 32, c->raster_smem, st>>>(P);
+    P.sums = c->d_sums;
+    P.coef = c->layout == RIG_LAYOUT_RGB ? (77u | (150u << 8) | (29u << 16)) : (29u | (150u << 8) | (77u << 16));
+    if (hash) k_raster<true><<<grid, c->raster_warps * 32, c->raster_smem, st>>>(P);
+    else k_raster<false><<<grid, c->raster_warps * 32, c->raster_smem, st>>>(P);
     c->stats.kernel_launches++;
     if (c->profiling) { prof_event(c, st); c->ev_panels.push_back(ch.p1 - ch.p0); }
     k_collect_overflow<<<1, 32, 0, st>>>(c->d_counters, c->d_overflow);
@@ -288,13 +292,45 @@ int upload_scene(rig_ctx *c, const rig_scene *s, int layout, cudaStream_t st)
     return upload_order(c, st);
 }
 
-int render_device(rig_ctx *c, uint8_t *out_dev, cudaStream_t st)
+int ensure_sums(rig_ctx *c, size_t n, cudaStream_t st)
+{
+    if (c->sums_cap < n) {
+        CK(c, cudaStreamSynchronize(st));
+        if (c->d_sums) CK(c, cudaFree(c->d_sums));
+        c->d_sums = nullptr;
+        CK(c, cudaMalloc(&c->d_sums, sizeof(uint32_t) * 256 * n));
+        c->sums_cap = n;
+    }
+    return RIG_OK;
+}
+
+int render_device(rig_ctx *c, uint8_t *out_dev, cudaStream_t st, uint64_t *hashes_dev = nullptr)
 {
     CK(c, cudaMemsetAsync(c->d_overflow, 0, 4 * sizeof(uint32_t), st));
     const size_t img = (size_t)c->W * c->H * 3;
-    for (const Chunk &ch : c->chunks) {
-        int rc = launch_chunk(c, ch, out_dev + (size_t)ch.p0 * img, st);
+    if (hashes_dev && c->n_panels) {
+        int rc = ensure_sums(c, (size_t)c->n_panels, st);
         if (rc) return rc;
+        CK(c, cudaMemsetAsync(c->d_sums, 0, sizeof(uint32_t) * 256 * (size_t)c->n_panels, st));
+    }
+    for (const Chunk &ch : c->chunks) {
+        int rc = launch_chunk(c, ch, out_dev + (size_t)ch.p0 * img, st, hashes_dev != nullptr);
+        if (rc) return rc;
+    }
+    if (hashes_dev && c->n_panels) {
+        int16_t gx[16];
+        for (int g = 1; g < c->grid_size && g <= 16; g++) {
+            volatile double qx = (double)(g * c->W) / (double)c->grid_size;
+            gx[g - 1] = (int16_t)nearbyint(qx);
+        }
+        CK(c, cudaMemcpyAsync(c->d_gridx, gx, sizeof gx, cudaMemcpyHostToDevice, st));
+        const uint32_t r = c->layout == RIG_LAYOUT_RGB ? (c->bg & 0xff) : ((c->bg >> 16) & 0xff), g = (c->bg >> 8) & 0xff,
+                       b = c->layout == RIG_LAYOUT_RGB ? ((c->bg >> 16) & 0xff) : (c->bg & 0xff);
+        const uint32_t luma_bg = (77u * r + 150u * g + 29u * b) >> 8;
+        k_hash_bits_fused<<<((unsigned)c->n_panels * 32 + 255) / 256, 256, 0, st>>>(c->d_sums, c->d_flags, c->n_panels, c->W, c->H, luma_bg,
+                                                                               c->grid_size - 1, c->d_gridx, hashes_dev);
+        c->stats.kernel_launches++;
+        CK(c, cudaGetLastError());
     }
     c->pending_overflow_check = true;
     return RIG_OK;
@@ -354,7 +390,8 @@ int rig_create(int device, int W, int H, int max_panels, int max_elements, rig_c
     if (const char *e = getenv("RIG_HEAVY_DIV")) c->heavy_div = (uint32_t)std::max(0, atoi(e));
     if (const char *e = getenv("RIG_WARPS")) { int w = atoi(e); if (w >= 1 && w <= warps) c->raster_warps = w; }
     c->raster_smem = raster_smem_bytes(W, c->raster_warps);
-    CKC(cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->raster_smem));
+    CKC(cudaFuncSetAttribute(k_raster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->raster_smem));
+    CKC(cudaFuncSetAttribute(k_raster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->raster_smem));
     CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
@@ -379,6 +416,7 @@ int rig_create(int device, int W, int H, int max_panels, int max_elements, rig_c
     CKC(cudaMalloc(&c->d_recs, sizeof(Rec) * (size_t)c->rec_cap));
     CKC(cudaMalloc(&c->d_aux, sizeof(Q16) * (size_t)c->aux_cap));
     CKC(cudaMalloc(&c->d_counters, CTR_COUNT * sizeof(uint32_t)));
+    CKC(cudaMalloc(&c->d_gridx, 16 * sizeof(int16_t)));
     CKC(cudaMalloc(&c->d_overflow, 4 * sizeof(uint32_t)));
     CKC(cudaMemset(c->d_overflow, 0, 4 * sizeof(uint32_t)));
 #undef CKC
@@ -394,7 +432,7 @@ void rig_destroy(rig_ctx *c)
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     cudaFree(c->d_tables); cudaFree(c->d_elems); cudaFreeHost(c->h_elems); cudaFree(c->d_begin); cudaFree(c->d_order); cudaFree(c->d_eorder); cudaFree(c->d_flags);
     cudaFree(c->d_hdrs); cudaFree(c->d_recs); cudaFree(c->d_aux); cudaFree(c->d_counters); cudaFree(c->d_overflow);
-    cudaFree(c->d_stage[0]); cudaFree(c->d_stage[1]); cudaFree(c->d_sums);
+    cudaFree(c->d_stage[0]); cudaFree(c->d_stage[1]); cudaFree(c->d_sums); cudaFree(c->d_gridx);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_used) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
@@ -420,6 +458,20 @@ int rig_render_resident(rig_ctx *c, uint8_t *out_device, void *stream)
     if (((uintptr_t)out_device) % 16) return fail(c, RIG_E_INVALID, "out_device must be 16-byte aligned");
     CK(c, cudaSetDevice(c->device));
     return render_device(c, out_device, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int rig_render_resident_hashed(rig_ctx *c, uint8_t *out_device, uint64_t *hashes_device, void *stream)
+{
+    if (!c) return RIG_E_INVALID;
+    if ((!out_device || !hashes_device) && c->n_panels) return fail(c, RIG_E_INVALID, "out_device / hashes_device is NULL");
+    if (((uintptr_t)out_device) % 16) return fail(c, RIG_E_INVALID, "out_device must be 16-byte aligned");
+    {
+        const int lpb = c->W / 256;
+        if (c->W % 256 || c->H % 16 || (lpb & (lpb - 1)) || c->W / 16 > 64)
+            return fail(c, RIG_E_UNSUPPORTED, "fused hashing needs W %% 256 == 0 (W / 256 a power of two, W <= 1024) and H %% 16 == 0");
+    }
+    CK(c, cudaSetDevice(c->device));
+    return render_device(c, out_device, stream ? (cudaStream_t)stream : c->stream, hashes_device);
 }
 
 int rig_sync(rig_ctx *c)

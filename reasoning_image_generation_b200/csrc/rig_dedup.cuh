@@ -80,6 +80,36 @@ __global__ void k_hash_bits(const uint32_t *__restrict__ sums, int n, uint64_t *
     }
 }
 
+// Same, for sums produced by k_raster<true>: those are deltas against the all-template panel, whose block sums are
+// constants: bh rows x (bw background pixels minus the panel's vertical grid lines crossing the block) x luma(bg).
+__global__ void k_hash_bits_fused(const uint32_t *__restrict__ sums, const uint8_t *__restrict__ panel_flags, int n, int W, int H,
+                                  uint32_t luma_bg, int n_grid, const int16_t *__restrict__ grid_x, uint64_t *__restrict__ hashes)
+{
+    const int img = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (img >= n) return;
+    const uint32_t *s = sums + (size_t)img * 256;
+    const bool grid = panel_flags[img] & 1;
+    const int bw = W / 16, bh = H / 16;
+    uint32_t v[8];
+    uint64_t t = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int b = k * 32 + lane, bx = b & 15;
+        int lines = 0;
+        if (grid)
+            for (int g = 0; g < n_grid; g++) lines += grid_x[g] >= bx * bw && grid_x[g] < (bx + 1) * bw && grid_x[g] < W;
+        v[k] = s[b] + (uint32_t)(bh * (bw - lines)) * luma_bg;
+        t += v[k];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint32_t bits = __ballot_sync(0xffffffffu, 256ull * v[k] > t);
+        if (lane == 0) ((uint32_t *)(hashes + (size_t)img * HASH_WORDS))[k] = bits;
+    }
+}
+
 // All-pairs scan.  CTA = 256 rows x one column tile of TJ hashes staged in shared memory; a thread
 // keeps its row hash in registers and walks the tile (every lane reads the same shared address:
 // broadcast).  The first 64 bits reject almost every pair with 2 POPCs; the remaining 192 bits are

@@ -158,10 +158,27 @@ struct RasterParams {
     int n_grid;                    // grid lines per direction (grid_size - 1, at most 15)
     int16_t grid_x[16], grid_y[16]; // int(round(i * W / grid_size)) etc. (generator.py:117,121), computed on the host
     uint32_t bg;                   // c0 | c1<<8 | c2<<16
+    uint32_t *sums;                // HASH variant: [n_panels_total][256] block-sum deltas vs the all-template panel (else unused)
+    uint32_t coef;                 // HASH variant: luma weights in output channel order (dp4a operand)
     uint32_t max_claim, heavy_bands; // scheduling: largest claim; the first heavy_bands bands (costliest panels) are claimed singly
 };
 
-// dynamic shared memory layout: [template plain][template grid][warp bands ...][RasterScratch per warp][filter 64]
+// luma sum of 4 consecutive packed pixels (3 words): Y = (77 R + 150 G + 29 B) >> 8 per pixel
+__device__ __forceinline__ uint32_t luma_quad(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t coef)
+{
+    return (__dp4a(w0 & 0x00ffffffu, coef, 0u) >> 8) + (__dp4a(__byte_perm(w0, w1, 0x4543) & 0x00ffffffu, coef, 0u) >> 8) +
+           (__dp4a(__byte_perm(w1, w2, 0x4432) & 0x00ffffffu, coef, 0u) >> 8) + (__dp4a(w2 >> 8, coef, 0u) >> 8);
+}
+__device__ __forceinline__ uint32_t luma_group16(const uint8_t *p, uint32_t coef)   // 16 pixels = 48 bytes, 16-byte aligned
+{
+    const uint4 a = ((const uint4 *)p)[0], b = ((const uint4 *)p)[1], c = ((const uint4 *)p)[2];
+    return luma_quad(a.x, a.y, a.z, coef) + luma_quad(a.w, b.x, b.y, coef) + luma_quad(b.z, b.w, c.x, coef) + luma_quad(c.y, c.z, c.w, coef);
+}
+
+// dynamic shared memory layout: [template plain][template grid][warp bands ...][RasterScratch per warp][filter 64][template lumas]
+// HASH: the perceptual-hash block sums are accumulated from the finished band while it is still in shared memory
+// (as deltas against the all-template panel), so hashing never re-reads the 786 KB image from HBM.
+template <bool HASH>
 __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const RasterParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -171,6 +188,7 @@ __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const Raste
     uint8_t *mine = smem + (size_t)(2 + warp) * band_bytes;
     RasterScratch *scratch = (RasterScratch *)(smem + (size_t)(2 + nwarps) * band_bytes);
     uint8_t *filter = (uint8_t *)(scratch + nwarps);
+    uint32_t *tluma = (uint32_t *)(filter + 64);      // HASH: luma of each 16-pixel group of one template row, [2][W/16]
     RasterScratch &S = scratch[warp];
 
     // ---- CTA prologue: constant templates + filter table
@@ -194,6 +212,12 @@ __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const Raste
         }
         fence_async_smem();
         __syncthreads();
+        if (HASH) {
+            const int groups = P.W / 16;
+            for (int g = threadIdx.x; g < 2 * groups; g += blockDim.x)
+                tluma[g] = luma_group16((g < groups ? tmpl0 : tmpl1) + (g % groups) * 48, P.coef);
+            __syncthreads();
+        }
     }
     // rows of the horizontal grid lines
     const int bands_per_panel = (P.H + BAND_ROWS - 1) / BAND_ROWS;   // the last band of a panel may be shorter
@@ -317,6 +341,28 @@ __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const Raste
                 }
             }
             if (use_grid) draw_grid<32>(B, P.n_grid, P.grid_x, P.grid_y, lane);
+            if (HASH) {
+                __syncwarp();
+                const int groups = P.W / 16, bh = P.H / 16, lpb = P.W / 256;      // lanes (16-px groups) per hash block
+                const uint32_t *tl = tluma + (use_grid ? groups : 0);
+                uint32_t *psum = P.sums + (size_t)panel * 256u;
+                for (int g0 = 0; g0 < groups; g0 += 32) {
+                    const int g = g0 + lane;
+                    int cur_by = B.r0 / bh;
+                    uint32_t acc = 0;
+                    for (int y = B.r0; y <= B.r1 + 1; y++) {
+                        const int by = y <= B.r1 ? y / bh : -1;
+                        if (by != cur_by) {                                      // flush the block row: segmented sum, one RED per block
+                            uint32_t s = acc;
+                            for (int o = 1; o < lpb && o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                            const int grp = lpb < 32 ? lpb : 32;
+                            if ((lane & (grp - 1)) == 0 && g < groups && s != 0u) atomicAdd(psum + cur_by * 16 + (g * 16) / (P.W / 16), s);
+                            acc = 0; cur_by = by;
+                        }
+                        if (y <= B.r1 && g < groups) acc += luma_group16(mine + ((y - B.r0) * P.W + g * 16) * 3, P.coef) - tl[g];
+                    }
+                }
+            }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) bulk_store(gdst, mine, out_bytes);
@@ -328,7 +374,7 @@ __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const Raste
 
 inline size_t raster_smem_bytes(int W, int nwarps)
 {
-    return (size_t)(2 + nwarps) * 3 * W * BAND_ROWS + (size_t)nwarps * sizeof(RasterScratch) + 64;
+    return (size_t)(2 + nwarps) * 3 * W * BAND_ROWS + (size_t)nwarps * sizeof(RasterScratch) + 64 + 2 * (size_t)(W / 16) * 4;
 }
 
 }  // namespace rig

@@ -133,6 +133,11 @@ class Renderer:
         with self._lock:
             self._check(self._lib.rig_render_resident(self._h, out_ptr, stream or None))
 
+    def render_resident_hashed(self, out_ptr: int, hashes_ptr: int, stream: int = 0):
+        """Resident scene -> pixels at out_ptr and uint64[n, 4] perceptual hashes at hashes_ptr (hash fused into the rasteriser)."""
+        with self._lock:
+            self._check(self._lib.rig_render_resident_hashed(self._h, out_ptr, hashes_ptr, stream or None))
+
     def sync(self):
         with self._lock:
             self._check(self._lib.rig_sync(self._h))

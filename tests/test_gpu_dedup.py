@@ -90,3 +90,35 @@ def test_render_hash_dedup_pipeline_drops_planted_duplicates(ctx):
     assert d[400:].all()
     want = dedup_oracle.drop_flags(h.cpu().numpy().view(np.uint64), 0)
     assert (d == want).all()
+
+
+def test_fused_hash_equals_standalone_hash_and_oracle(ctx):
+    """rig_render_resident_hashed: block sums accumulated inside the rasteriser == hashing the written pixels."""
+    r, f, torch = ctx
+    from reasoning_image_generation_b200.scene import SceneBuilder
+    sc = synthetic_scene(700, seed=44)
+    for layout in ('rgb', 'bgr'):
+        imgs = torch.empty((700, 512, 512, 3), dtype=torch.uint8, device='cuda')
+        fused = torch.empty((700, 4), dtype=torch.int64, device='cuda')
+        r.upload(sc, layout)
+        r.render_resident_hashed(imgs.data_ptr(), fused.data_ptr()); r.sync()
+        plain = torch.empty_like(imgs)
+        r.render_resident(plain.data_ptr()); r.sync()
+        assert torch.equal(imgs, plain)                      # the hashed variant writes the same pixels
+        sep = f.hash_images(imgs, layout); torch.cuda.synchronize(); r.sync()
+        assert torch.equal(fused, sep)
+        host = imgs[:40].cpu().numpy()
+        want = np.stack([dedup_oracle.phash(host[i], layout) for i in range(40)])
+        assert (fused[:40].cpu().numpy().view(np.uint64) == want).all()
+    # a non-white background and an all-empty batch
+    sb = SceneBuilder(512, 512, bg_color=(12, 200, 77))
+    for p in range(6):
+        sb.add_panel([], p % 2 == 0)
+    sb.add_panel([dict(kind='heart', size=150, fill=True, stroke_width=3, center=(256, 256), angle=30, color=(250, 250, 250))], True)
+    s2 = sb.finish()
+    imgs = torch.empty((7, 512, 512, 3), dtype=torch.uint8, device='cuda')
+    fused = torch.empty((7, 4), dtype=torch.int64, device='cuda')
+    r.upload(s2, 'rgb'); r.render_resident_hashed(imgs.data_ptr(), fused.data_ptr()); r.sync()
+    host = imgs.cpu().numpy()
+    want = np.stack([dedup_oracle.phash(host[i], 'rgb') for i in range(7)])
+    assert (fused.cpu().numpy().view(np.uint64) == want).all()

@@ -63,3 +63,19 @@ pin = r.pinned_output(sub.n_panels)
 t = time.time(); r.render(sub, 'bgr', out=pin); dt = time.time() - t
 t = time.time(); r.render(sub, 'bgr', out=pin); dt = time.time() - t
 print(f'e2e host (pinned out) {sub.n_panels} panels: {dt*1e3:.1f} ms -> {sub.n_panels/dt:.0f} img/s')
+# fused hash variant
+r.upload(sc, 'bgr')
+hs = torch.empty((n, 4), dtype=torch.int64, device='cuda')
+for rep in range(3): r.render_resident_hashed(out.data_ptr(), hs.data_ptr(), stream=st)
+torch.cuda.synchronize(); ev0.record()
+for rep in range(K): r.render_resident_hashed(out.data_ptr(), hs.data_ptr(), stream=st)
+ev1.record(); torch.cuda.synchronize(); r.sync()
+ms = ev0.elapsed_time(ev1) / K
+print(f'render + fused hash: {ms:.3f} ms per {n} panels -> {n/ms*1e3:.0f} img/s')
+from reasoning_image_generation_b200.dedup import DedupFilter
+f = DedupFilter(r)
+h2 = f.hash_images(out, 'bgr'); torch.cuda.synchronize(); r.sync()
+ev0.record(); 
+for rep in range(K): h2 = f.hash_images(out, 'bgr')
+ev1.record(); torch.cuda.synchronize(); r.sync()
+print(f'standalone hash: {ev0.elapsed_time(ev1)/K:.3f} ms per {n} panels; equal to fused: {bool(torch.equal(h2, hs))}')
