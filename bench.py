@@ -173,6 +173,10 @@ def run_ours(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    # stdout carries exactly one JSON line: anything libraries print there (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; this repository has no CPU rendering path (use --impl reference '
                          'for the CPU baseline)')
@@ -340,7 +344,7 @@ def run_ours(args):
                       'rendered_step_dropped': int(drop_r.sum().item())},
             'clocks': clocks,
         }
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + '\n').encode())
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
