@@ -8,8 +8,8 @@
 // cv2.circle / cv2.line on integer vertices (/root/reference/src/shapes.py:282-302,564-594,
 // /root/reference/src/generator.py:112-122).  Those calls are sequential scan conversions inside
 // OpenCV.  Here every such call is split into
-//   * a SETUP step (make_*): one lane turns one segment / polygon into a fixed 32-byte record whose
-//     fields are the loop-invariant integers of OpenCV's scan loop, and
+//   * a SETUP step (setup_* / make_* / pack_*): one lane turns one segment / polygon into 32-byte record
+//     slots whose fields are the loop-invariant integers of OpenCV's scan loop, and
 //   * an EVAL step (*_eval): a closed form of iteration k of that loop, so that the 32 lanes of a
 //     warp can run 32 iterations at once and a warp that owns a band of rows can jump straight to
 //     the iterations that land in its band.
@@ -251,6 +251,8 @@ RIG_HD void line8_krange(const Line8 &l, int r0, int r1, int &k0, int &k1)
     if (l.vert) {
         k0 = mlo < 0 ? 0 : mlo;
         k1 = mhi > l.dx ? l.dx : mhi;
+    } else if (l.dx < 32) {
+        k0 = 0; k1 = l.dx;           // one pass anyway: the caller row-tests each pixel
     } else {
         if (mhi < 0 || mlo > l.dy) { k0 = 1; k1 = 0; return; }
         k0 = mlo <= 0 ? 0 : line8_first_k(l.dx, l.dy, mlo);
@@ -259,10 +261,6 @@ RIG_HD void line8_krange(const Line8 &l, int r0, int r1, int &k0, int &k1)
 }
 
 // ---- LINEAA -------------------------------------------------------------------------------------
-struct AATables {
-    uint8_t slope_corr[32];
-    uint8_t filter[64];
-};
 // loop-invariant state of one LineAA() call (after clipping, end-point swap and slope set-up)
 struct LineAA {
     int valid;          // 0: clipped away
@@ -572,7 +570,7 @@ constexpr int CONVEX_SLOTS = 4;
 RIG_HD Rec rec_cont()
 {
     Rec r = rec_nop();
-    r.w[0] = 7u /* REC_CONT */ | (1u << 16);
+    r.w[0] = (uint32_t)REC_CONT | (1u << 16);   // ymin = 1 > ymax = 0: never selected
     return r;
 }
 RIG_FN void pack_convex(const ConvexChains &C, uint32_t color, int H, Rec *out)
@@ -611,7 +609,7 @@ RIG_HD ConvexChains unpack_convex(const Rec &h, const Rec &c1, const Rec &c2, co
 // For polygons whose footprint fits a 12 x 12 pixel box (stroke end caps, short stroke quads) the
 // warp does not replay the edges one after another; each lane takes one pixel of the box and applies,
 // in OpenCV's order, every edge's blend that lands on it and finally the interior fill.
-//   header : flags = number of edges; hi1 = x0; w2 = u16(y0) | w << 16 | h << 24
+//   header : flags = number of edges; hi1 = x0; w2 = u16(y0) | w << 16 | h << 24; w3 = ceil(65536 / w)
 //   edge e : cont slot 1+e: w2 = F0, w3 = step, w4,w5 = ep, w6 = u16(c0) | (ecount & 0xff) << 16 | ymajor << 24 | valid << 25
 //   spans  : cont slot 1+nedges: 12 rows x (x1, x2) as uint8 offsets from x0 (x1 > x2: empty), bytes of w2..w7
 constexpr int MINI_MAX = 12;
@@ -691,6 +689,7 @@ RIG_FN bool pack_minipoly(int W, int H, const LineAA *E, int n, const ConvexChai
     out[0] = rec_nop();
     rec_head(out[0], REC_MINIPOLY, (uint32_t)n, ymin, ymax, xmin, color, H);
     out[0].w[2] = (uint32_t)(uint16_t)(int16_t)ymin | ((uint32_t)w << 16) | ((uint32_t)h << 24);
+    out[0].w[3] = (65536u + (uint32_t)w - 1u) / (uint32_t)w;   // i / w == (i * w3) >> 16 for i < 144: the rasteriser never divides
     for (int e = 0; e < n; e++) pack_edge_slot(E[e], out[1 + e]);
     Rec &sp = out[1 + n];
     sp = rec_cont();

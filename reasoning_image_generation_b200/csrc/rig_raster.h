@@ -77,7 +77,7 @@ RIG_HD void exec_record(const Rec &r, const Q16 *aux, const uint8_t *filter, con
         for (int k = k0 + lane; k <= k1; k += LANES) {
             int x, y;
             line8_eval(l, k, x, y);
-            put3(band_px(b, x, y), color);
+            if (y >= y0 && y <= y1) put3(band_px(b, x, y), color);
         }
         break;
     }
@@ -115,7 +115,7 @@ RIG_HD void exec_record(const Rec &r, const Q16 *aux, const uint8_t *filter, con
         const int n = (int)rec_flags(r);
         const int x0 = rec_hi1(r), by0 = (int16_t)(r.w[2] & 0xffff), w = (int)((r.w[2] >> 16) & 0xff);
         const int rows = y1 - y0 + 1, npx = rows * w;
-        const uint32_t inv = (65536u + (uint32_t)w - 1u) / (uint32_t)w;   // i / w == (i * inv) >> 16 for i < 144, w <= 12
+        const uint32_t inv = r.w[3];                              // ceil(65536 / w): i / w == (i * inv) >> 16 for i < 144, w <= 12
         const Rec sp = ops.slot_part(1 + n, 2, 7);
         // LANES pixels of the box at a time: each lane keeps its pixel in a register while the edges are
         // applied in OpenCV's order, then the interior fill overrides, then one store

@@ -14,7 +14,6 @@ enum Kind : int {
     K_CRESCENT, K_ROUNDED_SQUARE, K_COUNT
 };
 
-constexpr int MAX_LOOP_VERTS = 60;   // heart
 constexpr int MAX_RING_VERTS = 74;   // 5-degree circle polygon: 73 points
 constexpr int MAX_STROKE = 4;        // caps stay 90-degree diamonds up to thickness 4
 

@@ -96,8 +96,6 @@ static double py_floordiv(double vx, double wx)
     return floordiv;
 }
 
-static inline uint8_t sat8(int v) { return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v); }
-
 int pack_elements(const rig_scene &s, int W, int H, int layout_bgr, DElem *out, char *err, size_t errlen)
 {
     const int gs = s.grid_size > 0 ? s.grid_size : 3;
@@ -147,7 +145,6 @@ int pack_elements(const rig_scene &s, int W, int H, int layout_bgr, DElem *out, 
             e.pad = 0; e.pad2 = 0;
         }
     }
-    (void)sat8;
     return RIG_OK;
 }
 
