@@ -278,7 +278,14 @@ RIG_FN LineAA setup_lineaa(int W, int H, P2L pt1, P2L pt2, const uint8_t *slope_
     L.xmin = L.ymin = 1; L.xmax = L.ymax = 0;
     long long dx, dy, ax, ay, i, j, step;
     int ecount, slope;
-    if (!clip_line((long long)W << XY_SHIFT, (long long)H << XY_SHIFT, pt1, pt2)) return L;
+    {
+        // clipLine only does something when an end point is outside the canvas: test that inline, call it rarely
+        const unsigned long long wf = (unsigned long long)W << XY_SHIFT, hf = (unsigned long long)H << XY_SHIFT;
+        if (((unsigned long long)pt1.x >= wf || (unsigned long long)pt2.x >= wf || (unsigned long long)pt1.y >= hf ||
+             (unsigned long long)pt2.y >= hf) &&
+            !clip_line((long long)W << XY_SHIFT, (long long)H << XY_SHIFT, pt1, pt2))
+            return L;
+    }
     dx = pt2.x - pt1.x;
     dy = pt2.y - pt1.y;
     j = dx < 0 ? -1 : 0;

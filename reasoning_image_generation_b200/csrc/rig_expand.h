@@ -52,8 +52,15 @@ RIG_HD int ring_fill(const float *sin_tab, long long cx_fx, long long cy_fx, int
         S.py[base + i] = p.y;
     }
     sync();
-    bool dup = false;
-    for (int i = 1; i < nraw; i++) dup |= S.px[base + i] == S.px[base + i - 1] && S.py[base + i] == S.py[base + i - 1];
+    // consecutive duplicates only occur for tiny radii: each lane checks its own vertices, the verdict is shared
+    // through the last scratch entry (never a vertex: nraw <= 73 < 127)
+    if (lane == 0) S.px[127] = 0;
+    sync();
+    for (int i = 1 + lane; i < nraw; i += LANES)
+        if (S.px[base + i] == S.px[base + i - 1] && S.py[base + i] == S.py[base + i - 1]) S.px[127] = 1;
+    sync();
+    const bool dup = S.px[127] != 0;
+    sync();
     if (!dup) return nraw;
     sync();
     int nv = 1;                                            // all lanes run the same serial compaction
