@@ -135,9 +135,37 @@ void plan_chunks(rig_ctx *c, size_t panel_limit)
     }
     c->h_eorder.resize(c->n_elements);
     for (uint32_t e = 0; e < (uint32_t)c->n_elements; e++) c->h_eorder[e] = e;
+    // Panel order inside a chunk (RIG_ORDER: 0 natural, 1 costliest first, 2 default = costliest 1/32 first, the rest in
+    // their natural order): draw-heavy bands are issue bound and empty bands are store bound, so the two kinds must
+    // stay interleaved for the TMA stores to overlap the drawing; only the few extreme panels go first (launch tail).
+    int order_mode = 2;
+    if (const char *e = getenv("RIG_ORDER")) order_mode = atoi(e);
     for (const Chunk &ch : c->chunks) {
-        std::stable_sort(c->h_order.begin() + ch.p0, c->h_order.begin() + ch.p1,
-                         [&](uint32_t a, uint32_t b) { return c->panel_cost[a] > c->panel_cost[b]; });
+        if (order_mode == 1)
+            std::stable_sort(c->h_order.begin() + ch.p0, c->h_order.begin() + ch.p1,
+                             [&](uint32_t a, uint32_t b) { return c->panel_cost[a] > c->panel_cost[b]; });
+        else if (order_mode == 3) {
+            // costliest paired with cheapest, second costliest with second cheapest, ...: every stretch of the order
+            // mixes issue-bound and store-bound bands, and the launch ends on median panels
+            std::vector<uint32_t> byc(c->h_order.begin() + ch.p0, c->h_order.begin() + ch.p1);
+            std::stable_sort(byc.begin(), byc.end(), [&](uint32_t a, uint32_t b) { return c->panel_cost[a] > c->panel_cost[b]; });
+            size_t lo = 0, hi = byc.size(), o = ch.p0;
+            while (lo < hi) {
+                c->h_order[o++] = byc[lo++];
+                if (lo < hi) c->h_order[o++] = byc[--hi];
+            }
+        }
+        else if (order_mode == 2) {
+            const size_t nlead = (ch.p1 - ch.p0) / 32;
+            std::vector<uint32_t> idx(c->h_order.begin() + ch.p0, c->h_order.begin() + ch.p1);
+            std::vector<uint32_t> byc(idx);
+            std::stable_sort(byc.begin(), byc.end(), [&](uint32_t a, uint32_t b) { return c->panel_cost[a] > c->panel_cost[b]; });
+            std::vector<uint8_t> lead(c->n_panels, 0);
+            for (size_t i = 0; i < nlead; i++) lead[byc[i]] = 1;
+            size_t o = ch.p0;
+            for (size_t i = 0; i < nlead; i++) c->h_order[o++] = byc[i];
+            for (uint32_t p : idx) if (!lead[p]) c->h_order[o++] = p;
+        }
         std::stable_sort(c->h_eorder.begin() + ch.e0, c->h_eorder.begin() + ch.e1,
                          [&](uint32_t a, uint32_t b) { return c->nominal_recs[a] > c->nominal_recs[b]; });
     }
@@ -217,6 +245,8 @@ int launch_chunk(rig_ctx *c, const Chunk &ch, uint8_t *out_dev, cudaStream_t st,
     P.tables = c->d_tables; P.out = out_dev; P.counters = c->d_counters; P.p0 = ch.p0; P.n_panels = ch.p1 - ch.p0;
     P.W = c->W; P.H = c->H; P.grid_size = c->grid_size; P.bg = c->bg;
     P.max_claim = c->max_claim;
+    P.skip_mask = 0;
+    if (const char *e = getenv("RIG_SKIP_MASK")) P.skip_mask = (uint32_t)strtoul(e, nullptr, 0);
     P.n_grid = c->grid_size - 1;
     for (int g = 1; g < c->grid_size && g <= 16; g++) {
         // int(round(i * W / grid_size)): Python rounds the float quotient half-to-even (generator.py:117,121)

@@ -160,6 +160,7 @@ struct RasterParams {
     uint32_t bg;                   // c0 | c1<<8 | c2<<16
     uint32_t *sums;                // HASH variant: [n_panels_total][256] block-sum deltas vs the all-template panel (else unused)
     uint32_t coef;                 // HASH variant: luma weights in output channel order (dp4a operand)
+    uint32_t skip_mask;            // diagnostics (RIG_SKIP_MASK): bit t set = records of type t are not executed
     uint32_t max_claim, heavy_bands; // scheduling: largest claim; the first heavy_bands bands (costliest panels) are claimed singly
 };
 
@@ -334,6 +335,7 @@ __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const Raste
                             ops.j = __ffs(m) - 1;
                             m &= m - 1;
                             const Rec r = ops.slot(0);
+                            if ((P.skip_mask >> rec_type(r)) & 1u) continue;
                             exec_record<32>(r, P.aux, filter, B, lane, S, ops);
                             __syncwarp();
                         }

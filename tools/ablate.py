@@ -1,5 +1,5 @@
-"""Tuning sweep (GPU box): resident render time for scheduling knobs; one process per configuration."""
-import os, subprocess, sys, itertools
+"""Ablation timing (GPU box): raster time with record types skipped (results are wrong on purpose)."""
+import os, subprocess, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 code = r'''
 import sys, os, torch
@@ -18,8 +18,9 @@ for _ in range(5): r.render_resident(out.data_ptr(), stream=st)
 torch.cuda.synchronize(); r.sync(); s = r.stats()
 print("expand %%.3f raster %%.3f ms" %% (s['expand_ms']/5, s['raster_ms']/5))
 ''' % root
-for om, hd in ((1, 4), (3, 4), (3, 0)):
-    lib, mc, hd, w = 'rig', 16, 4, 27
-    env = dict(os.environ, RIG_ORDER=str(om), RIG_HEAVY_DIV=str(hd))
+names = {1: 'LINE8', 2: 'LINEAA', 3: 'DISC', 4: 'CRESCENT', 5: 'CONVEX', 6: 'POLYFILL', 8: 'MINIPOLY', 9: 'STAMP'}
+masks = [('none', 0), ('all records', 0xffffffff)] + [('skip ' + v, 1 << k) for k, v in names.items()] + [('only MINIPOLY+STAMP', 0xffffffff & ~((1 << 8) | (1 << 9))), ('only LINEAA', 0xffffffff & ~(1 << 2))]
+for name, m in masks:
+    env = dict(os.environ, RIG_SKIP_MASK=hex(m))
     o = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True)
-    print('order mode', om, 'heavy_div', hd, '->', o.stdout.strip() or o.stderr[-300:], flush=True)
+    print(f'{name:24s}', o.stdout.strip() or o.stderr[-300:], flush=True)
