@@ -138,7 +138,7 @@ void plan_chunks(rig_ctx *c, size_t panel_limit)
     // Panel order inside a chunk (RIG_ORDER: 0 natural, 1 costliest first, 2 default = costliest 1/32 first, the rest in
     // their natural order): draw-heavy bands are issue bound and empty bands are store bound, so the two kinds must
     // stay interleaved for the TMA stores to overlap the drawing; only the few extreme panels go first (launch tail).
-    int order_mode = 2;
+    int order_mode = 1;
     if (const char *e = getenv("RIG_ORDER")) order_mode = atoi(e);
     for (const Chunk &ch : c->chunks) {
         if (order_mode == 1)
