@@ -135,9 +135,9 @@ void plan_chunks(rig_ctx *c, size_t panel_limit)
     }
     c->h_eorder.resize(c->n_elements);
     for (uint32_t e = 0; e < (uint32_t)c->n_elements; e++) c->h_eorder[e] = e;
-    // Panel order inside a chunk (RIG_ORDER: 0 natural, 1 costliest first, 2 default = costliest 1/32 first, the rest in
-    // their natural order): draw-heavy bands are issue bound and empty bands are store bound, so the two kinds must
-    // stay interleaved for the TMA stores to overlap the drawing; only the few extreme panels go first (launch tail).
+    // Panel order inside a chunk.  RIG_ORDER: 0 natural, 1 (default) costliest first, 2 costliest 1/32 first then natural,
+    // 3 costliest paired with cheapest.  Measured (profiles/r1_notes.md): 5.30 / 4.43 / 4.85 / 4.38 ms -- the launch tail
+    // is what matters, interleaving store-bound and issue-bound bands does not.
     int order_mode = 1;
     if (const char *e = getenv("RIG_ORDER")) order_mode = atoi(e);
     for (const Chunk &ch : c->chunks) {
