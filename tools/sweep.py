@@ -18,8 +18,8 @@ for _ in range(5): r.render_resident(out.data_ptr(), stream=st)
 torch.cuda.synchronize(); r.sync(); s = r.stats()
 print("expand %%.3f raster %%.3f ms" %% (s['expand_ms']/5, s['raster_ms']/5))
 ''' % root
-for om, hd in ((1, 4), (3, 4), (3, 0)):
-    lib, mc, hd, w = 'rig', 16, 4, 27
-    env = dict(os.environ, RIG_ORDER=str(om), RIG_HEAVY_DIV=str(hd))
+for lib, w in (('o6', 22), ('o8', 16)):
+    env = dict(os.environ, RIG_LIB=os.path.join(root, 'reasoning_image_generation_b200', 'librig_%s.so' % lib), RIG_WARPS=str(w))
     o = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True)
+    om = lib; hd = w
     print('order mode', om, 'heavy_div', hd, '->', o.stdout.strip() or o.stderr[-300:], flush=True)
