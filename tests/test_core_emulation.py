@@ -92,3 +92,25 @@ def test_fuzzed_elements_match_oracle(emul_lib):
     for p, (els, ug) in enumerate(panels):
         ref = ref_render.render_panel(512, 512, (250, 240, 230), els, ug, 3, backend=be)
         assert (ref == out[p]).all(), (p, els)
+
+
+@pytest.mark.parametrize('W,H', [(256, 192), (640, 361), (64, 48)])
+def test_other_canvas_sizes(emul_lib, W, H):
+    """GenConfig.canvas_size is configurable (/root/reference/src/config.py:26): nothing may assume 512 x 512."""
+    import random
+    rng = random.Random(W * 1000 + H)
+    sb = SceneBuilder(W, H)
+    panels = []
+    for p in range(24):
+        els = [dict(kind=rng.choice(ref_render.KINDS), size=rng.choice([20, 40, 64, 90]), fill=rng.random() < 0.6,
+                    stroke_width=rng.randint(1, 3), center=(rng.randint(-10, W + 10), rng.randint(-10, H + 10)),
+                    angle=rng.choice([0, 30, 45, 90, 200]), color=(rng.randint(0, 255), rng.randint(0, 255), rng.randint(0, 255)))
+               for _ in range(rng.randint(0, 4))]
+        panels.append((els, p % 2 == 0))
+        sb.add_panel(els, p % 2 == 0)
+    rc, out, nrec, err = emul_render_scene(emul_lib, sb.finish(), 5)
+    assert rc == 0, err
+    be = ref_render.CBackend()
+    for p, (els, ug) in enumerate(panels):
+        ref = ref_render.render_panel(W, H, (255, 255, 255), els, ug, 3, backend=be)
+        assert (ref == out[p]).all(), (p, els)

@@ -185,3 +185,26 @@ def test_record_arena_overflow_is_retried_not_silently_wrong(built):
     ref = ref_render.render_panel(512, 512, (255, 255, 255), els, False, 3, backend=be)
     assert (out == ref[None]).all()
     small.close()
+
+
+@pytest.mark.parametrize('W,H', [(256, 192), (640, 361), (1024, 64)])
+def test_other_canvas_sizes(built, W, H):
+    """Canvas sizes other than 512 x 512 (ragged last band, other band widths, fewer warps per CTA at W = 1024)."""
+    import random
+    rng = random.Random(W * 1000 + H)
+    sb = SceneBuilder(W, H)
+    panels = []
+    for p in range(40):
+        els = [dict(kind=rng.choice(ref_render.KINDS), size=rng.choice([20, 40, 64, 90]), fill=rng.random() < 0.6,
+                    stroke_width=rng.randint(1, 3), center=(rng.randint(-10, W + 10), rng.randint(-10, H + 10)),
+                    angle=rng.choice([0, 30, 45, 90, 200]), color=(rng.randint(0, 255), rng.randint(0, 255), rng.randint(0, 255)))
+               for _ in range(rng.randint(0, 4))]
+        panels.append((els, p % 2 == 0))
+        sb.add_panel(els, p % 2 == 0)
+    r = Renderer(W, H, device=0, max_panels=64, max_elements=512)
+    out = r.render(sb.finish(), 'bgr')
+    r.close()
+    be = ref_render.CBackend()
+    for p, (els, ug) in enumerate(panels):
+        ref = ref_render.render_panel(W, H, (255, 255, 255), els, ug, 3, backend=be)
+        assert (ref == out[p]).all(), (p, els)
