@@ -1,0 +1,115 @@
+/* rig_figure.h -- C ABI of the B200 figure rasteriser (librig.so), the render stage of the reference's multigraph path.
+ *
+ * The reference (MrGu11/reasoning_image_generation) has no FFI.  Its multigraph generator builds matplotlib artists and
+ * rasterises them with
+ *     GeometryGenerator._save_figure(fig, save_path, dpi) -> fig.savefig(...)
+ *                                                /root/reference/multigraph_generation/generator.py:250-259
+ * i.e. matplotlib's Agg backend, which receives one RendererAgg.draw_path(gc, path, transform, rgbFace) call per artist
+ * (patches: multigraph_generation/shapes.py:21-72 styled by style.py:29-66; lines: single_variants.py:285-288,313-333,
+ * 352-374; occlusion masks: single_variants.py:552-633).  A batch of such draw_path argument lists is what these entry
+ * points take instead (see INTEGRATION.md for the matplotlib-side walker).  Plain C types only; every function returns 0
+ * or a negative RIG_E_* code (include/rig.h); no exception, abort or CPU rendering fallback exists behind this boundary.
+ *
+ * Pipeline: the library runs matplotlib's path converters and Agg's stroker on host threads (double precision, the same
+ * libm the CPU renderer uses), uploads the resulting polygon edges (24.8 fixed point), and the CUDA kernel k_figure
+ * accumulates Agg's coverage cells per band of rows in shared memory, blends with matplotlib's non-premultiplied blender
+ * and writes each band with one TMA bulk store.
+ */
+#ifndef RIG_FIGURE_H
+#define RIG_FIGURE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "rig.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* matplotlib Path codes (matplotlib.path.Path) */
+#define RIG_PATH_STOP 0
+#define RIG_PATH_MOVETO 1
+#define RIG_PATH_LINETO 2
+#define RIG_PATH_CURVE3 3
+#define RIG_PATH_CURVE4 4
+#define RIG_PATH_CLOSEPOLY 79
+
+/* GraphicsContext enums in matplotlib's order (CapStyle, JoinStyle, snap) */
+#define RIG_CAP_BUTT 0
+#define RIG_CAP_PROJECTING 1
+#define RIG_CAP_ROUND 2
+#define RIG_JOIN_MITER 0
+#define RIG_JOIN_ROUND 1
+#define RIG_JOIN_BEVEL 2
+#define RIG_SNAP_FALSE 0
+#define RIG_SNAP_TRUE 1
+#define RIG_SNAP_AUTO 2
+
+/* Struct-of-arrays artist list of a batch of figures.  All pointers are BORROWED host arrays that must stay valid until
+ * the call returns.  Artist a of image i has image_artist_begin[i] <= a < image_artist_begin[i+1]; artists are drawn in
+ * index order (matplotlib: sorted by zorder, then insertion).  Each artist is one draw_path call:                      */
+typedef struct rig_figure_scene {
+    int32_t n_images;
+    int32_t n_artists;
+    int32_t n_vertices;
+    int32_t reserved;
+    const uint32_t *image_artist_begin;   /* [n_images + 1] */
+    const uint32_t *artist_vertex_begin;  /* [n_artists + 1] */
+    const double *vertices;               /* [2 * n_vertices] path.vertices, in the artist's own coordinates */
+    const uint8_t *codes;                 /* [n_vertices] path.codes (RIG_PATH_*) */
+    const double *affine;                 /* [6 * n_artists] transform.to_values(): a, b, c, d, e, f with
+                                             x' = a x + c y + e, y' = b x + d y + f -- display pixels, origin bottom-left */
+    const double *linewidth;              /* [n_artists] gc line width in PIXELS (points * dpi / 72); 0: no stroke */
+    const uint8_t *cap;                   /* [n_artists] RIG_CAP_* */
+    const uint8_t *join;                  /* [n_artists] RIG_JOIN_* */
+    const uint8_t *snap;                  /* [n_artists] RIG_SNAP_* */
+    const uint8_t *edge_rgba;             /* [4 * n_artists] gc colour as rgba8 (agg: uround(c * 255)), non-premultiplied */
+    const uint8_t *face_rgba;             /* [4 * n_artists] rgbFace as rgba8 */
+    const uint8_t *has_face;              /* [n_artists] 0: rgbFace is None */
+    const double *clip;                   /* [4 * n_artists] gc clip rectangle x0, y0, x1, y1 (display), or NULL */
+    const uint8_t *has_clip;              /* [n_artists] 0: no clip rectangle (whole canvas); may be NULL */
+} rig_figure_scene;
+
+typedef struct rig_figure_ctx rig_figure_ctx;
+
+/* Context on CUDA device `device` for W x H figures (the canvas savefig paints opaque white first), at most max_images
+ * images and max_artists artists per call.  W must be a multiple of 16 and W, H <= 2048.                              */
+int rig_figure_create(int device, int W, int H, int max_images, int max_artists, rig_figure_ctx **out);
+void rig_figure_destroy(rig_figure_ctx *ctx);
+const char *rig_figure_last_error(const rig_figure_ctx *ctx);
+
+/* Replaces fig.savefig's rasterisation for a whole batch: n_images images of H*W*3 bytes (the RGB of Agg's RGBA buffer;
+ * its alpha is 255 everywhere), image-major, to `out`.  out_is_device / out_layout / stream as in rig_render_batch.     */
+int rig_figure_render_batch(rig_figure_ctx *ctx, const rig_figure_scene *scene, uint8_t *out, int out_is_device, int out_layout,
+                            void *stream);
+
+/* Two-step form for scenes that stay resident in HBM (bench.py `value`): upload runs the host path pipeline and copies
+ * the edges to the device once; render_resident rasterises them into device memory.                                   */
+int rig_figure_upload(rig_figure_ctx *ctx, const rig_figure_scene *scene, int out_layout, void *stream);
+int rig_figure_render_resident(rig_figure_ctx *ctx, uint8_t *out_device, void *stream);
+int rig_figure_sync(rig_figure_ctx *ctx);
+
+typedef struct rig_figure_stats {
+    uint64_t kernel_launches;   /* kernels launched by this context since creation */
+    uint64_t edges;             /* polygon edges of the resident scene */
+    uint64_t layers;            /* rasteriser passes (faces + strokes) of the resident scene */
+    uint32_t timed_launches;    /* k_figure launches covered by cover_ms */
+    uint32_t reserved;
+    double cover_ms;            /* summed CUDA-event time of k_figure since rig_figure_set_profiling(ctx, 1) */
+    uint64_t timed_images;
+    double prepare_ms;          /* host time of the last upload's path pipeline */
+} rig_figure_stats;
+int rig_figure_get_stats(rig_figure_ctx *ctx, rig_figure_stats *out);
+int rig_figure_set_profiling(rig_figure_ctx *ctx, int on);
+
+/* Debug/test hook, needs no GPU: runs the host path pipeline and copies what would be uploaded.  layers_out: 8 uint32 per
+ * layer (image, edge_begin, n_edges, rgba, xmin, xmax, ymin, ymax); edges_out: 4 int32 per edge (x1, y1, x2, y2, 24.8 fixed
+ * point, y down).  Returns the number of edges, or a negative RIG_E_* code (RIG_E_CAPACITY: more than edge_cap edges).  */
+int64_t rig_figure_debug_edges(const rig_figure_scene *scene, int W, int H, uint32_t *layers_out, int32_t *edges_out,
+                               int64_t edge_cap, int64_t *n_layers_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIG_FIGURE_H */

@@ -1,0 +1,456 @@
+// rig_figure_abi.cu -- the extern "C" boundary declared in include/rig_figure.h.
+//
+// Host flow of one render: run the path pipeline (rig_figure_path.cpp) over the borrowed artist arrays on a few host
+// threads, copy layers / edges / slab directories to HBM, launch k_figure (persistent, one CTA per SM).  With a host
+// destination the images go through two device staging buffers so the D2H copy of one chunk overlaps the next chunk.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <thread>
+#include <vector>
+
+#include "rig_figure.cuh"
+#include "rig_figure_host.h"
+
+using namespace rig;
+
+namespace {
+thread_local char g_fig_create_err[512] = "";
+}
+
+struct rig_figure_ctx {
+    int device = 0, W = 0, H = 0, max_images = 0, max_artists = 0;
+    int sm_count = 0, warps = 0;
+    size_t smem = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    // resident scene
+    FigurePrepared prep;
+    std::vector<uint32_t> order;
+    std::vector<double> cost;
+    int n_images = 0, layout = RIG_LAYOUT_RGB;
+    FLayer *d_layers = nullptr;
+    FEdge *d_edges = nullptr;
+    uint32_t *d_dir = nullptr, *d_begin = nullptr, *d_order = nullptr, *d_work = nullptr;
+    size_t cap_layers = 0, cap_edges = 0, cap_dir = 0, cap_images = 0;
+    uint8_t *d_stage[2] = {nullptr, nullptr};
+    size_t stage_images = 0;
+    uint32_t max_claim = 8;
+    rig_figure_stats stats = {};
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool, ev_used;
+    std::vector<uint32_t> ev_images;
+    char err[512] = "";
+};
+
+namespace {
+
+int ffail(rig_figure_ctx *c, int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c ? c->err : g_fig_create_err, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define FCK(ctx, call)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return ffail(ctx, RIG_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int validate(rig_figure_ctx *c, const rig_figure_scene *s, char *err, int errlen)
+{
+    auto bad = [&](int code, const char *m) {
+        snprintf(err, errlen, "%s", m);
+        return code;
+    };
+    if (!s) return bad(RIG_E_INVALID, "scene is NULL");
+    if (s->n_images < 0 || s->n_artists < 0 || s->n_vertices < 0) return bad(RIG_E_INVALID, "negative count");
+    if (c && s->n_images > c->max_images) return bad(RIG_E_CAPACITY, "more images than max_images");
+    if (c && s->n_artists > c->max_artists) return bad(RIG_E_CAPACITY, "more artists than max_artists");
+    if (s->n_images && !s->image_artist_begin) return bad(RIG_E_INVALID, "image_artist_begin is NULL");
+    if (s->n_artists && (!s->artist_vertex_begin || !s->affine || !s->linewidth || !s->cap || !s->join || !s->snap || !s->edge_rgba ||
+                         !s->face_rgba || !s->has_face))
+        return bad(RIG_E_INVALID, "an artist array is NULL");
+    if (s->n_vertices && (!s->vertices || !s->codes)) return bad(RIG_E_INVALID, "vertices / codes is NULL");
+    if (s->n_images) {
+        if (s->image_artist_begin[0] != 0 || s->image_artist_begin[s->n_images] != (uint32_t)s->n_artists)
+            return bad(RIG_E_INVALID, "image_artist_begin must start at 0 and end at n_artists");
+        for (int i = 0; i < s->n_images; i++)
+            if (s->image_artist_begin[i] > s->image_artist_begin[i + 1]) return bad(RIG_E_INVALID, "image_artist_begin is not monotone");
+    }
+    if (s->n_artists) {
+        if (s->artist_vertex_begin[0] != 0 || s->artist_vertex_begin[s->n_artists] != (uint32_t)s->n_vertices)
+            return bad(RIG_E_INVALID, "artist_vertex_begin must start at 0 and end at n_vertices");
+        for (int a = 0; a < s->n_artists; a++) {
+            if (s->artist_vertex_begin[a] > s->artist_vertex_begin[a + 1]) return bad(RIG_E_INVALID, "artist_vertex_begin is not monotone");
+            if (s->cap[a] > RIG_CAP_ROUND || s->join[a] > RIG_JOIN_BEVEL || s->snap[a] > RIG_SNAP_AUTO) return bad(RIG_E_INVALID, "bad cap / join / snap value");
+        }
+    }
+    return RIG_OK;
+}
+
+// host path pipeline over all images, on up to 16 threads; results merged in image order
+int prepare_all(const rig_figure_scene *s, int W, int H, bool bgr, FigurePrepared &out, char *err, int errlen)
+{
+    out.layers.clear(); out.edges.clear(); out.dir.clear(); out.image_layer_begin.clear();
+    const int n = s->n_images;
+    int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    if (const char *e = getenv("RIG_HOST_THREADS")) nt = std::max(1, atoi(e));
+    nt = std::max(1, std::min(nt, (n + 255) / 256));
+    std::vector<FigurePrepared> parts(nt);
+    std::vector<int> rcs(nt, 0);
+    std::vector<std::vector<char>> errs(nt, std::vector<char>(256, 0));
+    auto work = [&](int t) {
+        const int i0 = (int)((long long)n * t / nt), i1 = (int)((long long)n * (t + 1) / nt);
+        rcs[t] = figure_prepare(*s, W, H, bgr, i0, i1, parts[t], errs[t].data(), 256);
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
+    for (int t = 0; t < nt; t++)
+        if (rcs[t]) {
+            snprintf(err, errlen, "%s", errs[t].data());
+            return rcs[t];
+        }
+    for (int t = 0; t < nt; t++) {
+        const FigurePrepared &p = parts[t];
+        const uint32_t lbase = (uint32_t)out.layers.size(), ebase = (uint32_t)out.edges.size(), dbase = (uint32_t)out.dir.size();
+        if ((uint64_t)ebase + p.edges.size() > 0xfffffff0ull) {
+            snprintf(err, errlen, "more than 2^32 edges in one batch");
+            return RIG_E_CAPACITY;
+        }
+        for (size_t i = 0; i + 1 < p.image_layer_begin.size(); i++) out.image_layer_begin.push_back(lbase + p.image_layer_begin[i]);
+        for (FLayer L : p.layers) {
+            L.edge_begin += ebase;
+            L.dir_begin += dbase;
+            out.layers.push_back(L);
+        }
+        out.edges.insert(out.edges.end(), p.edges.begin(), p.edges.end());
+        out.dir.insert(out.dir.end(), p.dir.begin(), p.dir.end());
+    }
+    out.image_layer_begin.push_back((uint32_t)out.layers.size());
+    return RIG_OK;
+}
+
+template <class T>
+int ensure(rig_figure_ctx *c, T *&p, size_t &cap, size_t need)
+{
+    if (cap >= need && p) return RIG_OK;
+    FCK(c, cudaStreamSynchronize(c->stream));
+    FCK(c, cudaStreamSynchronize(c->copy_stream));
+    if (p) FCK(c, cudaFree(p));
+    p = nullptr;
+    const size_t n = std::max<size_t>(need + need / 4, 1024);
+    FCK(c, cudaMalloc(&p, n * sizeof(T)));
+    cap = n;
+    return RIG_OK;
+}
+
+void order_range(rig_figure_ctx *c, uint32_t i0, uint32_t i1)
+{
+    for (uint32_t i = i0; i < i1; i++) c->order[i] = i;
+    std::stable_sort(c->order.begin() + i0, c->order.begin() + i1, [&](uint32_t a, uint32_t b) { return c->cost[a] > c->cost[b]; });
+}
+
+int upload(rig_figure_ctx *c, const rig_figure_scene *s, int layout, cudaStream_t st)
+{
+    char msg[256] = "";
+    int rc = validate(c, s, msg, sizeof msg);
+    if (rc) return ffail(c, rc, "%s", msg);
+    if (layout != RIG_LAYOUT_RGB && layout != RIG_LAYOUT_BGR) return ffail(c, RIG_E_INVALID, "bad out_layout %d", layout);
+    const auto t0 = std::chrono::steady_clock::now();
+    rc = prepare_all(s, c->W, c->H, layout == RIG_LAYOUT_BGR, c->prep, msg, sizeof msg);
+    if (rc) return ffail(c, rc, "%s", msg);
+    c->stats.prepare_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    c->n_images = s->n_images;
+    c->layout = layout;
+    const FigurePrepared &p = c->prep;
+    c->cost.assign(c->n_images, 0.0);
+    for (int i = 0; i < c->n_images; i++)
+        for (uint32_t l = p.image_layer_begin[i]; l < p.image_layer_begin[i + 1]; l++)
+            c->cost[i] += (double)p.layers[l].n_edges + 8.0 * std::max(0, p.layers[l].ymax - p.layers[l].ymin + 1);
+    c->order.resize(c->n_images);
+    order_range(c, 0, (uint32_t)c->n_images);
+    c->stats.edges = p.edges.size();
+    c->stats.layers = p.layers.size();
+    if ((rc = ensure(c, c->d_layers, c->cap_layers, p.layers.size()))) return rc;
+    if ((rc = ensure(c, c->d_edges, c->cap_edges, p.edges.size()))) return rc;
+    if ((rc = ensure(c, c->d_dir, c->cap_dir, p.dir.size()))) return rc;
+    if (!p.layers.empty()) FCK(c, cudaMemcpyAsync(c->d_layers, p.layers.data(), sizeof(FLayer) * p.layers.size(), cudaMemcpyHostToDevice, st));
+    if (!p.edges.empty()) FCK(c, cudaMemcpyAsync(c->d_edges, p.edges.data(), sizeof(FEdge) * p.edges.size(), cudaMemcpyHostToDevice, st));
+    if (!p.dir.empty()) FCK(c, cudaMemcpyAsync(c->d_dir, p.dir.data(), sizeof(uint32_t) * p.dir.size(), cudaMemcpyHostToDevice, st));
+    FCK(c, cudaMemcpyAsync(c->d_begin, p.image_layer_begin.data(), sizeof(uint32_t) * (c->n_images + 1), cudaMemcpyHostToDevice, st));
+    if (c->n_images) FCK(c, cudaMemcpyAsync(c->d_order, c->order.data(), sizeof(uint32_t) * c->n_images, cudaMemcpyHostToDevice, st));
+    FCK(c, cudaStreamSynchronize(st));
+    return RIG_OK;
+}
+
+cudaEvent_t fprof_event(rig_figure_ctx *c, cudaStream_t st)
+{
+    cudaEvent_t e = nullptr;
+    if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    cudaEventRecord(e, st);
+    c->ev_used.push_back(e);
+    return e;
+}
+
+void fresolve_profiling(rig_figure_ctx *c)
+{
+    for (size_t i = 0; i + 1 < c->ev_used.size() && i / 2 < c->ev_images.size(); i += 2) {
+        float a = 0;
+        if (cudaEventElapsedTime(&a, c->ev_used[i], c->ev_used[i + 1]) == cudaSuccess) {
+            c->stats.cover_ms += a;
+            c->stats.timed_launches++;
+            c->stats.timed_images += c->ev_images[i / 2];
+        }
+    }
+    for (cudaEvent_t e : c->ev_used) c->ev_pool.push_back(e);
+    c->ev_used.clear();
+    c->ev_images.clear();
+}
+
+// images order[i0 .. i1) of the resident scene; image id k is written at out_dev + (k - img_base) * H * W * 3
+int launch(rig_figure_ctx *c, uint32_t i0, uint32_t i1, uint8_t *out_dev, uint32_t img_base, cudaStream_t st)
+{
+    if (i1 <= i0) return RIG_OK;
+    FCK(c, cudaMemsetAsync(c->d_work, 0, sizeof(uint32_t), st));
+    FigureParams P;
+    P.image_layer_begin = c->d_begin; P.layers = c->d_layers; P.edges = c->d_edges; P.dir = c->d_dir;
+    P.order = c->d_order + i0;
+    P.out = out_dev - (size_t)img_base * c->H * c->W * 3;
+    P.work = c->d_work;
+    P.n_images = i1 - i0;
+    P.W = c->W; P.H = c->H;
+    P.bg = 0x00ffffffu;
+    P.max_claim = c->max_claim;
+    const uint32_t bands = P.n_images * (uint32_t)((c->H + FIG_ROWS - 1) / FIG_ROWS);
+    const uint32_t want = (bands + c->warps - 1) / c->warps;
+    const uint32_t grid = std::max(1u, std::min((uint32_t)c->sm_count, want));
+    if (c->profiling) fprof_event(c, st);
+    k_figure<<<grid, c->warps * 32, c->smem, st>>>(P);
+    c->stats.kernel_launches++;
+    if (c->profiling) { fprof_event(c, st); c->ev_images.push_back(i1 - i0); }
+    FCK(c, cudaGetLastError());
+    return RIG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *rig_figure_last_error(const rig_figure_ctx *ctx) { return ctx ? ctx->err : g_fig_create_err; }
+
+int rig_figure_create(int device, int W, int H, int max_images, int max_artists, rig_figure_ctx **out)
+{
+    if (!out) return ffail(nullptr, RIG_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (W <= 0 || H <= 0 || W % 16 || W > 2048 || H > 2048)
+        return ffail(nullptr, RIG_E_INVALID, "unsupported canvas %dx%d (W %% 16 == 0 so that rows are 16-byte aligned; <= 2048)", W, H);
+    if (max_images <= 0 || max_artists <= 0) return ffail(nullptr, RIG_E_INVALID, "max_images/max_artists must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return ffail(nullptr, RIG_E_NODEVICE, "no usable CUDA device (%s); this library has no CPU path",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return ffail(nullptr, RIG_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    rig_figure_ctx *c = new rig_figure_ctx();
+    c->device = device; c->W = W; c->H = H; c->max_images = max_images; c->max_artists = max_artists;
+    auto bail = [&](int code) {
+        snprintf(g_fig_create_err, sizeof g_fig_create_err, "%s", c->err);
+        rig_figure_destroy(c);
+        return code;
+    };
+#define FCKC(call)                                                                                 \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ffail(c, RIG_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                  \
+            return bail(RIG_E_CUDA);                                                               \
+        }                                                                                          \
+    } while (0)
+    FCKC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FCKC(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 9) {
+        ffail(c, RIG_E_UNSUPPORTED, "device %d is sm_%d%d; the kernel needs bulk async copies (sm_90+; built for sm_100a)", device, prop.major, prop.minor);
+        return bail(RIG_E_UNSUPPORTED);
+    }
+    c->sm_count = prop.multiProcessorCount;
+    const size_t smem_max = prop.sharedMemPerBlockOptin;
+    int warps = FIG_MAX_WARPS;
+    while (warps > 1 && figure_smem_bytes(W, warps) > smem_max) warps--;
+    if (figure_smem_bytes(W, warps) > smem_max) {
+        ffail(c, RIG_E_UNSUPPORTED, "canvas width %d needs %zu B of shared memory per band; the device offers %zu", W, figure_smem_bytes(W, warps), smem_max);
+        return bail(RIG_E_UNSUPPORTED);
+    }
+    if (const char *ev = getenv("RIG_FIG_WARPS")) { int w = atoi(ev); if (w >= 1 && w <= warps) warps = w; }
+    if (const char *ev = getenv("RIG_FIG_MAX_CLAIM")) c->max_claim = (uint32_t)std::max(1, atoi(ev));
+    c->warps = warps;
+    c->smem = figure_smem_bytes(W, warps);
+    FCKC(cudaFuncSetAttribute(k_figure, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+    FCKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    FCKC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        FCKC(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+        FCKC(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+    }
+    FCKC(cudaMalloc(&c->d_begin, sizeof(uint32_t) * ((size_t)max_images + 1)));
+    FCKC(cudaMalloc(&c->d_order, sizeof(uint32_t) * (size_t)max_images));
+    FCKC(cudaMalloc(&c->d_work, sizeof(uint32_t) * 4));
+#undef FCKC
+    *out = c;
+    return RIG_OK;
+}
+
+void rig_figure_destroy(rig_figure_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    cudaFree(c->d_layers); cudaFree(c->d_edges); cudaFree(c->d_dir); cudaFree(c->d_begin); cudaFree(c->d_order); cudaFree(c->d_work);
+    cudaFree(c->d_stage[0]); cudaFree(c->d_stage[1]);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_used) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) {
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+    }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+int rig_figure_upload(rig_figure_ctx *c, const rig_figure_scene *scene, int out_layout, void *stream)
+{
+    if (!c) return RIG_E_INVALID;
+    FCK(c, cudaSetDevice(c->device));
+    return upload(c, scene, out_layout, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int rig_figure_render_resident(rig_figure_ctx *c, uint8_t *out_device, void *stream)
+{
+    if (!c) return RIG_E_INVALID;
+    if (!out_device && c->n_images) return ffail(c, RIG_E_INVALID, "out_device is NULL");
+    if (((uintptr_t)out_device) % 16) return ffail(c, RIG_E_INVALID, "out_device must be 16-byte aligned");
+    FCK(c, cudaSetDevice(c->device));
+    return launch(c, 0, (uint32_t)c->n_images, out_device, 0, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int rig_figure_sync(rig_figure_ctx *c)
+{
+    if (!c) return RIG_E_INVALID;
+    FCK(c, cudaSetDevice(c->device));
+    FCK(c, cudaStreamSynchronize(c->stream));
+    FCK(c, cudaStreamSynchronize(c->copy_stream));
+    if (c->profiling) {
+        FCK(c, cudaDeviceSynchronize());
+        fresolve_profiling(c);
+    }
+    return RIG_OK;
+}
+
+int rig_figure_render_batch(rig_figure_ctx *c, const rig_figure_scene *scene, uint8_t *out, int out_is_device, int out_layout, void *stream)
+{
+    if (!c) return RIG_E_INVALID;
+    if (!out && scene && scene->n_images) return ffail(c, RIG_E_INVALID, "out is NULL");
+    FCK(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    int rc = upload(c, scene, out_layout, st);
+    if (rc) return rc;
+    if (out_is_device) {
+        if (((uintptr_t)out) % 16) return ffail(c, RIG_E_INVALID, "out must be 16-byte aligned");
+        return launch(c, 0, (uint32_t)c->n_images, out, 0, st);
+    }
+    const size_t img = (size_t)c->W * c->H * 3;
+    const size_t stage_limit = std::max<size_t>(1, std::min<size_t>(512, (size_t)c->n_images));
+    if (c->stage_images < stage_limit) {
+        FCK(c, cudaStreamSynchronize(c->copy_stream));
+        for (int i = 0; i < 2; i++) {
+            if (c->d_stage[i]) FCK(c, cudaFree(c->d_stage[i]));
+            c->d_stage[i] = nullptr;
+            FCK(c, cudaMalloc(&c->d_stage[i], stage_limit * img));
+        }
+        c->stage_images = stage_limit;
+    }
+    // chunks of consecutive images, each with its own costliest-first order
+    const uint32_t n = (uint32_t)c->n_images, step = (uint32_t)c->stage_images;
+    for (uint32_t i0 = 0; i0 < n; i0 += step) order_range(c, i0, std::min(n, i0 + step));
+    if (n) FCK(c, cudaMemcpyAsync(c->d_order, c->order.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    int k = 0;
+    for (uint32_t i0 = 0; i0 < n; i0 += step, k++) {
+        const uint32_t i1 = std::min(n, i0 + step);
+        const int b = k & 1;
+        if (k >= 2) FCK(c, cudaStreamWaitEvent(st, c->ev_copied[b], 0));
+        rc = launch(c, i0, i1, c->d_stage[b], i0, st);
+        if (rc) return rc;
+        FCK(c, cudaEventRecord(c->ev_done[b], st));
+        FCK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
+        FCK(c, cudaMemcpyAsync(out + (size_t)i0 * img, c->d_stage[b], (size_t)(i1 - i0) * img, cudaMemcpyDeviceToHost, c->copy_stream));
+        FCK(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
+    }
+    FCK(c, cudaStreamSynchronize(st));
+    FCK(c, cudaStreamSynchronize(c->copy_stream));
+    if (c->profiling) fresolve_profiling(c);
+    // leave the resident order global again
+    order_range(c, 0, n);
+    if (n) FCK(c, cudaMemcpy(c->d_order, c->order.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+    return RIG_OK;
+}
+
+int rig_figure_set_profiling(rig_figure_ctx *c, int on)
+{
+    if (!c) return RIG_E_INVALID;
+    c->profiling = on != 0;
+    if (on) {
+        c->stats.cover_ms = 0;
+        c->stats.timed_launches = 0;
+        c->stats.timed_images = 0;
+    }
+    return RIG_OK;
+}
+
+int rig_figure_get_stats(rig_figure_ctx *c, rig_figure_stats *out)
+{
+    if (!c || !out) return RIG_E_INVALID;
+    *out = c->stats;
+    return RIG_OK;
+}
+
+int64_t rig_figure_debug_edges(const rig_figure_scene *scene, int W, int H, uint32_t *layers_out, int32_t *edges_out, int64_t edge_cap,
+                               int64_t *n_layers_out)
+{
+    char msg[256] = "";
+    int rc = validate(nullptr, scene, msg, sizeof msg);
+    if (rc) return rc;
+    FigurePrepared p;
+    rc = prepare_all(scene, W, H, false, p, msg, sizeof msg);
+    if (rc) return rc;
+    if ((int64_t)p.edges.size() > edge_cap) return RIG_E_CAPACITY;
+    size_t img = 0;
+    for (size_t l = 0; l < p.layers.size(); l++) {
+        while (img + 1 < p.image_layer_begin.size() && p.image_layer_begin[img + 1] <= l) img++;
+        const FLayer &L = p.layers[l];
+        uint32_t *o = layers_out + 8 * l;
+        o[0] = (uint32_t)img; o[1] = L.edge_begin; o[2] = L.n_edges; o[3] = L.rgba;
+        o[4] = (uint32_t)(int32_t)L.xmin; o[5] = (uint32_t)(int32_t)L.xmax; o[6] = (uint32_t)(int32_t)L.ymin; o[7] = (uint32_t)(int32_t)L.ymax;
+    }
+    if (!p.edges.empty()) memcpy(edges_out, p.edges.data(), sizeof(FEdge) * p.edges.size());
+    if (n_layers_out) *n_layers_out = (int64_t)p.layers.size();
+    return (int64_t)p.edges.size();
+}
+
+}  // extern "C"

@@ -17,6 +17,7 @@
 
 #include "rig_expand.h"
 #include "rig_raster.h"
+#include "rig_tma.cuh"
 
 namespace rig {
 
@@ -88,17 +89,6 @@ __global__ void k_collect_overflow(const uint32_t *__restrict__ counters, uint32
         totals[2] += counters[CTR_AUX];
     }
 }
-
-// ---- TMA bulk store helpers (shared::cta -> global) ---------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
-                 "cp.async.bulk.commit_group;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct RasterOps {
     Rec mine;            // the slot this lane loaded in the current 32-slot window

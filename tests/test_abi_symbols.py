@@ -25,6 +25,29 @@ def test_every_declared_symbol_is_exported(built):
     assert sorted(_abi.EXPORTS) == names
 
 
+def test_every_declared_figure_symbol_is_exported(built):
+    """include/rig_figure.h: the figure (matplotlib/Agg) path of the same library."""
+    from reasoning_image_generation_b200 import figure
+    lib = _abi.load()
+    txt = open(os.path.join(ROOT, 'include', 'rig_figure.h')).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    names = sorted(set(re.findall(r'\b(rig_figure_[a-z_]+)\s*\(', txt)))
+    assert len(names) == 10
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(figure.FIGURE_EXPORTS) == names
+
+
+def test_figure_create_without_device_fails_loudly(built):
+    import torch
+    if torch.cuda.is_available():
+        return
+    from reasoning_image_generation_b200 import figure
+    with __import__('pytest').raises(figure.FigureError) as e:
+        figure.FigureRenderer(512, 512)
+    assert e.value.code in (_abi.RIG_E_NODEVICE, _abi.RIG_E_CUDA)
+
+
 def test_create_without_device_fails_loudly_not_silently(built):
     """No CPU fallback: on a box without a usable GPU rig_create returns an error and a message."""
     import torch
