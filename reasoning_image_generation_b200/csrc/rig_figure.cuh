@@ -21,10 +21,16 @@
 namespace rig {
 
 #ifndef FIG_BAND_ROWS
-#define FIG_BAND_ROWS 4
+#define FIG_BAND_ROWS 2
+#endif
+#ifndef FIG_ACC_CELLS
+#define FIG_ACC_CELLS 256
 #endif
 constexpr int FIG_ROWS = FIG_BAND_ROWS;
+constexpr int FIG_ACC = FIG_ACC_CELLS;     // accumulator columns per row; wider layers are resolved in column chunks (multiple of 32, <= 1024)
 constexpr int FIG_MAX_WARPS = 32;
+constexpr uint32_t FIG_NO_ROWS = 0x80007fffu;   // ymin = 32767, ymax = -32768: overlaps no band (a "1 > 0" range would overlap rows 0..1)
+constexpr uint32_t FIG_DIR_MIN_EDGES = 96; // layers with fewer edges are scanned whole (no slab directory look-up)
 
 struct FigureParams {
     const uint32_t *image_layer_begin;   // [n_images + 1]
@@ -40,29 +46,32 @@ struct FigureParams {
     uint32_t max_claim;
 };
 
-// bytes of shared memory one warp needs: band pixels, cover + area accumulators, touched-group masks
+// bytes of shared memory one warp needs: band pixels, cover + area accumulators, per-row touched-group mask and carry-in
 __host__ __device__ inline size_t figure_warp_bytes(int W)
 {
-    return (size_t)FIG_ROWS * ((size_t)3 * W + (size_t)8 * W) + (size_t)FIG_ROWS * 8;
+    return (size_t)FIG_ROWS * ((size_t)3 * W + (size_t)8 * FIG_ACC) + (size_t)FIG_ROWS * 8;
 }
 inline size_t figure_smem_bytes(int W, int nwarps) { return (size_t)3 * W * FIG_ROWS + (size_t)nwarps * figure_warp_bytes(W); }
 
 struct FigAcc {
     int *cover, *area;
-    unsigned *gmask;     // 2 words per band row: bit g = cells [32 g, 32 g + 32) of the row were touched
-    int W, r0, off;
-    unsigned *gm;
+    unsigned *gmask;     // per band row: bit g = cells [x0 + 32 g, x0 + 32 g + 32) were touched
+    int *carry_in;       // per band row: cover of the cells left of x0
+    int x0, r0, off, row_i;
     __device__ __forceinline__ void row(int ey)
     {
-        off = (ey - r0) * W;
-        gm = gmask + (ey - r0) * 2;
+        row_i = ey - r0;
+        off = row_i * FIG_ACC;
     }
     __device__ __forceinline__ void operator()(int ex, int dc, int da)
     {
-        if ((unsigned)ex >= (unsigned)W || (dc | da) == 0) return;
-        atomicAdd(cover + off + ex, dc);
-        atomicAdd(area + off + ex, da);
-        atomicOr(gm + (ex >> 10), 1u << ((ex >> 5) & 31));
+        if ((dc | da) == 0) return;
+        const int cx = ex - x0;
+        if (cx < 0) { atomicAdd(carry_in + row_i, dc); return; }
+        if (cx >= FIG_ACC) return;
+        atomicAdd(cover + off + cx, dc);
+        atomicAdd(area + off + cx, da);
+        atomicOr(gmask + row_i, 1u << (cx >> 5));
     }
 };
 
@@ -71,6 +80,27 @@ __device__ __forceinline__ void fig_put3(uint8_t *p, uint32_t c)
     p[0] = (uint8_t)c; p[1] = (uint8_t)(c >> 8); p[2] = (uint8_t)(c >> 16);
 }
 __device__ __forceinline__ uint32_t fig_get3(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16); }
+
+// the 7 used words of a layer header, kept one layer per lane and handed round by shuffles
+struct FigHdr {
+    uint32_t edge_begin, n_edges, rgba, yy, xx, dir_begin, sd;   // yy = ymin | ymax << 16, xx = xmin | xmax << 16, sd = maxspan | ndir << 16
+};
+__device__ __forceinline__ FigHdr fig_load_hdr(const FLayer *L)
+{
+    const uint4 a = __ldg((const uint4 *)L), b = __ldg((const uint4 *)L + 1);
+    FigHdr h;
+    h.edge_begin = a.x; h.n_edges = a.y; h.rgba = a.z; h.yy = a.w; h.xx = b.x; h.dir_begin = b.y; h.sd = b.z;
+    return h;
+}
+__device__ __forceinline__ FigHdr fig_shfl_hdr(const FigHdr &m, int src)
+{
+    FigHdr h;
+    h.edge_begin = __shfl_sync(0xffffffffu, m.edge_begin, src); h.n_edges = __shfl_sync(0xffffffffu, m.n_edges, src);
+    h.rgba = __shfl_sync(0xffffffffu, m.rgba, src); h.yy = __shfl_sync(0xffffffffu, m.yy, src);
+    h.xx = __shfl_sync(0xffffffffu, m.xx, src); h.dir_begin = __shfl_sync(0xffffffffu, m.dir_begin, src);
+    h.sd = __shfl_sync(0xffffffffu, m.sd, src);
+    return h;
+}
 
 __global__ void __launch_bounds__(FIG_MAX_WARPS * 32, 1) k_figure(const FigureParams P)
 {
@@ -82,8 +112,9 @@ __global__ void __launch_bounds__(FIG_MAX_WARPS * 32, 1) k_figure(const FigurePa
     uint8_t *wbase = smem + band_bytes + (size_t)warp * figure_warp_bytes(W);
     uint8_t *mine = wbase;
     int *cover = (int *)(wbase + band_bytes);
-    int *area = cover + FIG_ROWS * W;
-    unsigned *gmask = (unsigned *)(area + FIG_ROWS * W);
+    int *area = cover + FIG_ROWS * FIG_ACC;
+    unsigned *gmask = (unsigned *)(area + FIG_ROWS * FIG_ACC);
+    int *carry_in = (int *)(gmask + FIG_ROWS);
 
     // ---- CTA prologue: white template; every warp zeroes its accumulators once (resolve leaves them zeroed)
     {
@@ -96,8 +127,8 @@ __global__ void __launch_bounds__(FIG_MAX_WARPS * 32, 1) k_figure(const FigurePa
             const uint32_t m = i % 3;
             t0[i] = m == 0 ? w0 : (m == 1 ? w1 : w2);
         }
-        for (int i = lane; i < 2 * FIG_ROWS * W; i += 32) cover[i] = 0;     // cover and area are contiguous
-        if (lane < 2 * FIG_ROWS) gmask[lane] = 0u;
+        for (int i = lane; i < 2 * FIG_ROWS * FIG_ACC; i += 32) cover[i] = 0;     // cover and area are contiguous
+        if (lane < 2 * FIG_ROWS) gmask[lane] = 0u;                                 // masks and carry-ins
         fence_async_smem();
         __syncthreads();
     }
@@ -105,7 +136,9 @@ __global__ void __launch_bounds__(FIG_MAX_WARPS * 32, 1) k_figure(const FigurePa
     const uint32_t total_bands = P.n_images * (uint32_t)bands_per_image;
     bool dirty = false;
     uint32_t cur_slot = 0xffffffffu, image = 0, lb = 0, le = 0;
-    int my_ymin = 1, my_ymax = 0;      // row range of the image's lane-th layer
+    FigHdr myh;                         // header of the image's lane-th layer
+    myh.edge_begin = myh.n_edges = myh.rgba = myh.xx = myh.dir_begin = myh.sd = 0u;
+    myh.yy = FIG_NO_ROWS;
 
     for (;;) {
         uint32_t first = 0, take = 1;
@@ -126,11 +159,9 @@ __global__ void __launch_bounds__(FIG_MAX_WARPS * 32, 1) k_figure(const FigurePa
                 image = P.order[slot];
                 lb = P.image_layer_begin[image];
                 le = P.image_layer_begin[image + 1];
-                my_ymin = 1; my_ymax = 0;
-                if (lb + lane < le) {
-                    const FLayer *L = P.layers + lb + lane;
-                    my_ymin = L->ymin; my_ymax = L->ymax;
-                }
+                myh.yy = FIG_NO_ROWS;
+                myh.n_edges = 0u;
+                if (lb + lane < le) myh = fig_load_hdr(P.layers + lb + lane);
             }
             const int band = (int)(bi - slot * bands_per_image);
             const int r0 = band * FIG_ROWS;
@@ -140,8 +171,9 @@ __global__ void __launch_bounds__(FIG_MAX_WARPS * 32, 1) k_figure(const FigurePa
             uint8_t *gdst = P.out + ((size_t)image * P.H + r0) * (size_t)W * 3;
             bool more = false;                                    // images with more than 32 layers: the rest from memory
             for (uint32_t l = lb + 32 + lane; l < le; l += 32) more |= P.layers[l].ymin <= r1 && P.layers[l].ymax >= r0;
-            const uint32_t lmask = __ballot_sync(0xffffffffu, my_ymin <= r1 && my_ymax >= r0);
-            if (lmask == 0u && !__any_sync(0xffffffffu, more)) {
+            const uint32_t lmask = __ballot_sync(0xffffffffu, (int)(int16_t)(myh.yy & 0xffffu) <= r1 && (int)(int16_t)(myh.yy >> 16) >= r0);
+            const bool any_more = __any_sync(0xffffffffu, more);
+            if (lmask == 0u && !any_more) {
                 if (lane == 0) bulk_store(gdst, tmpl, out_bytes);
                 continue;
             }
@@ -155,69 +187,89 @@ __global__ void __launch_bounds__(FIG_MAX_WARPS * 32, 1) k_figure(const FigurePa
                 for (uint32_t i = lane; i < band_bytes / 16; i += 32) dst[i] = src[i];
             }
             __syncwarp();
-            for (uint32_t l = lb; l < le; l++) {
-                if (l - lb < 32u) {
-                    if (!((lmask >> (l - lb)) & 1u)) continue;
+            uint32_t todo = lmask;
+            uint32_t lnext = lb + 32;          // next layer beyond the 32 kept in registers
+            for (;;) {
+                FigHdr L;
+                if (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    L = fig_shfl_hdr(myh, src);
+                } else {
+                    if (!any_more || lnext >= le) break;
+                    L = fig_load_hdr(P.layers + lnext);
+                    lnext++;
+                    if ((int)(int16_t)(L.yy & 0xffffu) > r1 || (int)(int16_t)(L.yy >> 16) < r0) continue;
                 }
-                const FLayer L = P.layers[l];
-                if (L.ymin > r1 || L.ymax < r0) continue;
-                // ---- scatter: the edges that can reach rows [r0, r1]
-                {
-                    int lo_row = r0 - (int)L.maxspan;
-                    if (lo_row < L.ymin) lo_row = L.ymin;
-                    const int s_lo = (lo_row - L.ymin) / FIG_SLAB_ROWS, s_hi = (r1 - L.ymin) / FIG_SLAB_ROWS + 1;
-                    const uint32_t e_lo = P.dir[L.dir_begin + s_lo];
-                    const uint32_t e_hi = s_hi >= (int)L.ndir ? L.n_edges : P.dir[L.dir_begin + s_hi];
-                    FigAcc acc;
-                    acc.cover = cover; acc.area = area; acc.gmask = gmask; acc.W = W; acc.r0 = r0; acc.off = 0; acc.gm = gmask;
-                    const FEdge *ep = P.edges + L.edge_begin;
-                    for (uint32_t e = e_lo + lane; e < e_hi; e += 32) {
-                        const int4 v = __ldg((const int4 *)(ep + e));
-                        FEdge ed;
-                        ed.x1 = v.x; ed.y1 = v.y; ed.x2 = v.z; ed.y2 = v.w;
-                        fig_edge_rows(ed, r0, r1, acc);
+                const int Lymin = (int16_t)(L.yy & 0xffffu), Lymax = (int16_t)(L.yy >> 16);
+                const int Lxmin = (int16_t)(L.xx & 0xffffu), Lxmax = (int16_t)(L.xx >> 16);
+                // the edges that can reach rows [r0, r1]
+                uint32_t e_lo = 0, e_hi = L.n_edges;
+                if (L.n_edges >= FIG_DIR_MIN_EDGES) {
+                    int lo_row = r0 - (int)(L.sd & 0xffffu);
+                    if (lo_row < Lymin) lo_row = Lymin;
+                    const int s_lo = (lo_row - Lymin) / FIG_SLAB_ROWS, s_hi = (r1 - Lymin) / FIG_SLAB_ROWS + 1;
+                    e_lo = __ldg(P.dir + L.dir_begin + s_lo);
+                    if (s_hi < (int)(L.sd >> 16)) e_hi = __ldg(P.dir + L.dir_begin + s_hi);
+                }
+                const FEdge *ep = P.edges + L.edge_begin;
+                const int ya = Lymin > r0 ? Lymin : r0, yb = Lymax < r1 ? Lymax : r1;
+                // column chunks of FIG_ACC cells (one chunk unless the layer is wider than the accumulators)
+                for (int x0 = Lxmin & ~31; x0 <= Lxmax; x0 += FIG_ACC) {
+                    // ---- scatter
+                    {
+                        FigAcc acc;
+                        acc.cover = cover; acc.area = area; acc.gmask = gmask; acc.carry_in = carry_in;
+                        acc.x0 = x0; acc.r0 = r0; acc.off = 0; acc.row_i = 0;
+                        for (uint32_t e = e_lo + lane; e < e_hi; e += 32) {
+                            const int4 v = __ldg((const int4 *)(ep + e));
+                            FEdge ed;
+                            ed.x1 = v.x; ed.y1 = v.y; ed.x2 = v.z; ed.y2 = v.w;
+                            fig_edge_rows(ed, r0, r1, acc);
+                        }
                     }
-                }
-                __syncwarp();
-                // ---- resolve
-                const int ya = L.ymin > r0 ? L.ymin : r0, yb = L.ymax < r1 ? L.ymax : r1;
-                for (int y = ya; y <= yb; y++) {
-                    const int ro = (y - r0) * W;
-                    unsigned long long gm = (unsigned long long)gmask[(y - r0) * 2] | ((unsigned long long)gmask[(y - r0) * 2 + 1] << 32);
-                    if (gm == 0ull) continue;
                     __syncwarp();
-                    if (lane < 2) gmask[(y - r0) * 2 + lane] = 0u;
-                    uint8_t *rowpx = mine + (size_t)ro * 3;
-                    int carry = 0, prev_end = 0;
-                    while (gm) {
-                        const int g = __ffsll((long long)gm) - 1;
-                        gm &= gm - 1;
-                        const int xs = g * 32;
-                        if (carry != 0 && xs > prev_end) {          // interior run at constant coverage
-                            const uint32_t al = fig_alpha(carry, 0);
-                            for (int x = prev_end + lane; x < xs; x += 32) fig_put3(rowpx + x * 3, fig_blend_px(fig_get3(rowpx + x * 3), L.rgba, al));
-                        }
-                        const int x = xs + lane;
-                        const bool in = x < W;
-                        const int c = in ? cover[ro + x] : 0, a = in ? area[ro + x] : 0;
-                        if (in && (c | a)) { cover[ro + x] = 0; area[ro + x] = 0; }
-                        int ci = c;
+                    // ---- resolve
+                    const bool last_chunk = x0 + FIG_ACC > Lxmax;
+                    const int fill_end = last_chunk ? W : x0 + FIG_ACC;
+                    for (int y = ya; y <= yb; y++) {
+                        const int ri = y - r0, ro = ri * FIG_ACC;
+                        uint32_t gm = gmask[ri];
+                        int carry = carry_in[ri];
+                        if (gm == 0u && carry == 0) continue;
+                        __syncwarp();
+                        if (lane == 0) { gmask[ri] = 0u; carry_in[ri] = 0; }
+                        uint8_t *rowpx = mine + (size_t)ri * W * 3;
+                        int prev_end = x0;
+                        while (gm) {
+                            const int g = __ffs(gm) - 1;
+                            gm &= gm - 1;
+                            const int xs = x0 + g * 32;
+                            if (carry != 0 && xs > prev_end) {          // interior run at constant coverage
+                                const uint32_t al = fig_alpha(carry, 0);
+                                for (int x = prev_end + lane; x < xs; x += 32) fig_put3(rowpx + x * 3, fig_blend_px(fig_get3(rowpx + x * 3), L.rgba, al));
+                            }
+                            const int x = xs + lane;
+                            const int c = cover[ro + g * 32 + lane], a = area[ro + g * 32 + lane];
+                            if (c | a) { cover[ro + g * 32 + lane] = 0; area[ro + g * 32 + lane] = 0; }
+                            int ci = c;
 #pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const int t = __shfl_up_sync(0xffffffffu, ci, o);
-                            if (lane >= o) ci += t;
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int t = __shfl_up_sync(0xffffffffu, ci, o);
+                                if (lane >= o) ci += t;
+                            }
+                            const uint32_t al = fig_alpha(carry + ci, a);
+                            if (x < W && al) fig_put3(rowpx + x * 3, fig_blend_px(fig_get3(rowpx + x * 3), L.rgba, al));
+                            carry += __shfl_sync(0xffffffffu, ci, 31);
+                            prev_end = xs + 32;
                         }
-                        const uint32_t al = fig_alpha(carry + ci, a);
-                        if (in && al) fig_put3(rowpx + x * 3, fig_blend_px(fig_get3(rowpx + x * 3), L.rgba, al));
-                        carry += __shfl_sync(0xffffffffu, ci, 31);
-                        prev_end = xs + 32;
+                        if (carry != 0 && prev_end < fill_end) {        // interior continues to the next chunk / the right canvas edge
+                            const uint32_t al = fig_alpha(carry, 0);
+                            for (int x = prev_end + lane; x < fill_end; x += 32) fig_put3(rowpx + x * 3, fig_blend_px(fig_get3(rowpx + x * 3), L.rgba, al));
+                        }
                     }
-                    if (carry != 0 && prev_end < W) {               // polygon clipped by the right canvas edge
-                        const uint32_t al = fig_alpha(carry, 0);
-                        for (int x = prev_end + lane; x < W; x += 32) fig_put3(rowpx + x * 3, fig_blend_px(fig_get3(rowpx + x * 3), L.rgba, al));
-                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             fence_async_smem();
             __syncwarp();

@@ -7,8 +7,8 @@
 // into an 8-bit coverage, and matplotlib's fixed_blender_rgba_plain blends the colour with it.  The cell sums are
 // commutative, so the GPU accumulates them with shared-memory atomics in any order; what must be reproduced exactly
 // is each edge's split into rows and cells.  Agg walks an edge row by row with a DDA; here the state of that DDA at
-// the first row of a band is computed in closed form (floor((p + j q) / dy) decomposed so that everything but one
-// quotient stays in 32 bits), and from there the walk is Agg's own.
+// the first row of a band is computed in closed form (floor((p + j q) / dy) decomposed so that everything stays in
+// 32 bits for canvases up to 2048 x 2048), and from there the walk is Agg's own.
 //
 // The same code is compiled for the CPU by tests/cpu_emul/figure_emul.cpp and checked against oracle/aggdraw.c.
 #pragma once
@@ -125,10 +125,11 @@ RIG_HD void fig_edge_rows(const FEdge &e, int r0, int r1, Acc &acc)
     const int lift = fig_floordiv(q, ady), rem = q - lift * ady;
     int xfrom = x1, yfrom = fy1, m = mod0;
     if (ja > 0) {
-        const long long t = (long long)mod0 + (long long)(ja - 1) * rem;
-        const int qd = (int)(t / ady);
-        m = (int)(t - (long long)qd * ady);
-        xfrom = x1 + delta0 + (ja - 1) * lift + qd;
+        // mod0, rem < |dy| < 2^19 and ja <= 2^11 (canvas <= 2048 rows): the sum stays below 2^31
+        const uint32_t t = (uint32_t)mod0 + (uint32_t)(ja - 1) * (uint32_t)rem;
+        const uint32_t qd = t / (uint32_t)ady;
+        m = (int)(t - qd * (uint32_t)ady);
+        xfrom = x1 + delta0 + (ja - 1) * lift + (int)qd;
         yfrom = 256 - first;
     }
     for (int j = ja; j <= jb; j++) {

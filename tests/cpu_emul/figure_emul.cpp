@@ -14,46 +14,65 @@ using namespace rig;
 
 namespace {
 struct HostAcc {
-    std::vector<int> &cover, &area;
-    int W, r0, off = 0;
-    HostAcc(std::vector<int> &c, std::vector<int> &a, int W_, int r0_) : cover(c), area(a), W(W_), r0(r0_) {}
-    void row(int ey) { off = (ey - r0) * W; }
+    std::vector<int> &cover, &area, &carry_in;
+    int acc_cells, x0, r0, off = 0, row_i = 0;
+    HostAcc(std::vector<int> &c, std::vector<int> &a, std::vector<int> &ci, int acc_cells_, int x0_, int r0_)
+        : cover(c), area(a), carry_in(ci), acc_cells(acc_cells_), x0(x0_), r0(r0_) {}
+    void row(int ey) { row_i = ey - r0; off = row_i * acc_cells; }
     void operator()(int ex, int dc, int da)
     {
-        if ((unsigned)ex >= (unsigned)W) return;
-        cover[off + ex] += dc;
-        area[off + ex] += da;
+        if ((dc | da) == 0) return;
+        const int cx = ex - x0;
+        if (cx < 0) { carry_in[row_i] += dc; return; }
+        if (cx >= acc_cells) return;
+        cover[off + cx] += dc;
+        area[off + cx] += da;
     }
 };
+void blend(uint8_t *px, uint32_t rgba, uint32_t al)
+{
+    const uint32_t v = fig_blend_px((uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16), rgba, al);
+    px[0] = (uint8_t)v; px[1] = (uint8_t)(v >> 8); px[2] = (uint8_t)(v >> 16);
+}
 }  // namespace
 
-extern "C" void figure_emul_render(int W, int H, int n_layers, const uint32_t *layers, const int32_t *edges, int band_rows, uint8_t *rgb)
+// acc_cells: accumulator columns per row (multiple of 32); layers wider than that are resolved in column chunks with a
+// carry-in, as k_figure does with FIG_ACC_CELLS
+extern "C" void figure_emul_render(int W, int H, int n_layers, const uint32_t *layers, const int32_t *edges, int band_rows, int acc_cells,
+                                   uint8_t *rgb)
 {
     memset(rgb, 255, (size_t)W * H * 3);
-    std::vector<int> cover((size_t)band_rows * W), area((size_t)band_rows * W);
+    std::vector<int> cover((size_t)band_rows * acc_cells), area((size_t)band_rows * acc_cells), carry_in(band_rows);
     for (int r0 = 0; r0 < H; r0 += band_rows) {
         const int r1 = r0 + band_rows - 1 < H - 1 ? r0 + band_rows - 1 : H - 1;
         for (int l = 0; l < n_layers; l++) {
             const uint32_t *L = layers + 8 * l;
-            const int ymin = (int32_t)L[6], ymax = (int32_t)L[7];
+            const int xmin = (int32_t)L[4], xmax = (int32_t)L[5], ymin = (int32_t)L[6], ymax = (int32_t)L[7];
             if (ymin > r1 || ymax < r0) continue;
-            std::fill(cover.begin(), cover.end(), 0);
-            std::fill(area.begin(), area.end(), 0);
-            HostAcc acc(cover, area, W, r0);
-            for (uint32_t e = 0; e < L[2]; e++) {
-                const int32_t *p = edges + 4 * (size_t)(L[1] + e);
-                FEdge ed{p[0], p[1], p[2], p[3]};
-                fig_edge_rows(ed, r0, r1, acc);
-            }
-            for (int y = r0; y <= r1; y++) {
-                int run = 0;
-                for (int x = 0; x < W; x++) {
-                    run += cover[(size_t)(y - r0) * W + x];
-                    const uint32_t al = fig_alpha(run, area[(size_t)(y - r0) * W + x]);
-                    if (!al) continue;
-                    uint8_t *px = rgb + ((size_t)y * W + x) * 3;
-                    const uint32_t v = fig_blend_px((uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16), L[3], al);
-                    px[0] = (uint8_t)v; px[1] = (uint8_t)(v >> 8); px[2] = (uint8_t)(v >> 16);
+            for (int x0 = xmin & ~31; x0 <= xmax; x0 += acc_cells) {
+                std::fill(cover.begin(), cover.end(), 0);
+                std::fill(area.begin(), area.end(), 0);
+                std::fill(carry_in.begin(), carry_in.end(), 0);
+                HostAcc acc(cover, area, carry_in, acc_cells, x0, r0);
+                for (uint32_t e = 0; e < L[2]; e++) {
+                    const int32_t *p = edges + 4 * (size_t)(L[1] + e);
+                    FEdge ed{p[0], p[1], p[2], p[3]};
+                    fig_edge_rows(ed, r0, r1, acc);
+                }
+                const int fill_end = x0 + acc_cells > xmax ? W : x0 + acc_cells;
+                for (int y = (ymin > r0 ? ymin : r0); y <= (ymax < r1 ? ymax : r1); y++) {
+                    int run = carry_in[y - r0];
+                    int last = x0;          // first pixel not yet decided
+                    for (int cx = 0; cx < acc_cells; cx++) {
+                        const int c = cover[(size_t)(y - r0) * acc_cells + cx], a = area[(size_t)(y - r0) * acc_cells + cx];
+                        run += c;
+                        const uint32_t al = fig_alpha(run, a);
+                        const int x = x0 + cx;
+                        if (al && x < W) blend(rgb + ((size_t)y * W + x) * 3, L[3], al);
+                        last = x + 1;
+                    }
+                    if (run != 0)
+                        for (int x = last; x < fill_end; x++) blend(rgb + ((size_t)y * W + x) * 3, L[3], fig_alpha(run, 0));
                 }
             }
         }

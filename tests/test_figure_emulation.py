@@ -21,17 +21,17 @@ def agg(built):
 @pytest.fixture(scope='module')
 def femul(built):
     lib = ctypes.CDLL(os.path.join(ROOT, 'tests', 'cpu_emul', 'libfigure_emul.so'))
-    lib.figure_emul_render.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    lib.figure_emul_render.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.figure_emul_render.restype = None
     return lib
 
 
-def emul_render(femul, scene, band_rows):
+def emul_render(femul, scene, band_rows, acc_cells=256):
     layers, edges = host_edges(scene)
     out = np.zeros((scene.n_images, scene.H, scene.W, 3), np.uint8)
     for i in range(scene.n_images):
         L = np.ascontiguousarray(layers[layers[:, 0] == i])
-        femul.figure_emul_render(scene.W, scene.H, len(L), L.ctypes.data, edges.ctypes.data, band_rows, out[i].ctypes.data)
+        femul.figure_emul_render(scene.W, scene.H, len(L), L.ctypes.data, edges.ctypes.data, band_rows, acc_cells, out[i].ctypes.data)
     return out
 
 
@@ -101,8 +101,9 @@ def test_random_polylines_and_joins(agg, femul):
         sb.end_image()
     sc = sb.finish()
     ref = agg.render(sc, W, H)
-    got = emul_render(femul, sc, 4)
-    assert int((got != ref).any(axis=3).sum()) == 0
+    for acc_cells in (256, 64, 32):          # layers wider than the accumulators: column chunks with a carry-in
+        got = emul_render(femul, sc, 4, acc_cells)
+        assert int((got != ref).any(axis=3).sum()) == 0, acc_cells
 
 
 def test_empty_and_degenerate_inputs(agg, femul):
