@@ -4,17 +4,20 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repository's CUDA path
     python bench.py --impl reference [--gpus N] [--steps K] ...     # the reference's CPU path (oracle port)
 
-A "step" is one pass of the hot path (k_expand + k_raster through rig_render_resident) over one batch of
-synthetic scene descriptions of the sequence-panel shape, per GPU.
-  value      whole-job images/s, scenes already resident in HBM, CUDA events on the launching stream,
-             barrier + synchronize on both sides, max over ranks
-  e2e        the same metric through the public API (Renderer.render) with HOST buffers: scene packing,
-             H2D of the scene, rendering and the D2H copy of every pixel into pinned host memory are inside
-             the timed region
-  roofline   k_raster (the dominant kernel): algorithmic bytes (786,432 per image) / its CUDA-event time,
-             against the measured HBM figure in MEASURED_PEAKS.json
-  cpu_baseline  the oracle port of the reference renderer (oracle/ref_render.py over the installed cv2 wheel)
-             on this box's host cores, bounded sample of the same workload
+Headline workload (BASELINE.json configs[1]): multigraph single-shape variants (one outlined base patch with internal
+lines or occlusion masks) at 512x512, the figure path: host path pipeline once at upload, then k_figure per step.
+A "step" is one pass of the hot path over one batch of synthetic figure scenes, per GPU.
+  value      whole-job images/s, scenes already resident in HBM (polygon edges in 24.8 fixed point), CUDA events on the
+             launching stream, barrier + synchronize on both sides, max over ranks
+  e2e        the same metric through the public API (FigureRenderer.render) with HOST buffers: the host path pipeline
+             (transform, snap, curve flattening, stroking, clipping), H2D of the edges, rendering and the D2H copy of every
+             pixel into pinned host memory are inside the timed region
+  roofline   k_figure (the dominant kernel): algorithmic bytes (786,432 per image) / its CUDA-event time, against the
+             measured HBM figure in MEASURED_PEAKS.json
+  cpu_baseline  oracle/aggdraw.c (the restated matplotlib/Agg renderer) on this box's host cores, bounded sample
+  sequence_panels  the same quantities for the sequence-panel path (k_expand + k_raster, BASELINE configs[3] shape), with
+             its own roofline, e2e and cpu_baseline, plus the near-duplicate stage (`dedup`)
+`--workload sequence` makes the sequence-panel path the headline instead (and skips the figure leg).
 """
 import argparse
 import json
@@ -31,6 +34,12 @@ IMG_BYTES = 512 * 512 * 3
 PANELS_PER_STEP = 16384        # 12.9 GB of pixels per step per GPU: far larger than the 126 MB L2
 E2E_PANELS = 4096              # 3.2 GB pinned host destination per e2e step
 DEDUP_N = 1 << 20              # hashes in the all-pairs timing input (5.5e11 pairs)
+FIG_PER_STEP = 32768           # 25.8 GB of pixels per step per GPU
+FIG_E2E = 4096
+FIG_METRIC = 'rendered images/sec at 512x512 (multigraph single-shape variants)'
+FIG_WORKLOAD = ('BASELINE configs[1]: multigraph single-shape variants, synthetic (SURVEY 8d: one outlined base patch -- circle / '
+                'ellipse / rectangle / rounded box / regular polygon / wedge, 1.5-2.0 pt, alpha 0.9 -- plus 1-6 internal lines or 1-3 '
+                'occlusion masks), %d images per step per GPU, 512x512x3 uint8' % FIG_PER_STEP)
 METRIC = 'rendered images/sec at 512x512 (sequence-panel scenes)'
 WORKLOAD = ('sequence-panel synthetic scenes (SURVEY 8d: 1.85 elements/panel, 11 kinds, AA strokes 1-3 px, '
             'grid/wrap-around mix), %d panels per step per GPU, 512x512x3 uint8' % PANELS_PER_STEP)
@@ -132,6 +141,66 @@ def cpu_sample(seed, budget_s=14.0, cores=None):
     return done, dt, cores, backend
 
 
+def _fig_cpu_worker(args):
+    seed, i0, i1 = args
+    from oracle.agg_oracle import AggOracle
+    from reasoning_image_generation_b200.synth_figure import synthetic_figure_scene
+    sc = synthetic_figure_scene(i1 - i0, 512, 512, seed=seed, kind='single', first=i0)
+    o = AggOracle()
+    t = time.time()
+    acc = 0
+    for i in range(sc.n_images):
+        acc += int(o.render_rgba(sc, i, 512, 512)[0, 0, 0])
+    return i1 - i0, time.time() - t, 'aggdraw.c'
+
+
+def fig_cpu_sample(seed, budget_s=14.0, cores=None):
+    """Renders consecutive slices of the step's figure scene on all host cores until ~budget_s has passed
+    (scene emission is outside each worker's own timer but inside the wall clock used for the rate)."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    per = 96
+    done, render_s = 0, 0.0
+    t0 = time.time()
+    with mp.get_context('fork').Pool(cores) as pool:
+        while time.time() - t0 < budget_s and done + per * cores <= FIG_PER_STEP:
+            jobs = [(seed, done + i * per, done + (i + 1) * per) for i in range(cores)]
+            res = pool.map(_fig_cpu_worker, jobs)
+            done += sum(r[0] for r in res)
+            render_s += max(r[1] for r in res)
+    return done, render_s, cores, 'aggdraw.c'
+
+
+def run_reference_figure(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle.agg_oracle import build_agg_oracle
+    build_agg_oracle()
+    steps = max(1, args.steps)
+    budget = max(4.0, min(20.0, 90.0 / (steps + args.warmup)))
+    sample, total_s, cores = 0, 0.0, os.cpu_count() or 1
+    for s in range(args.warmup + steps):
+        n, dt, cores, backend = fig_cpu_sample(seed=1000, budget_s=budget)
+        if s >= args.warmup:
+            sample += n
+            total_s += dt
+    v = sample / total_s
+    line = {
+        'impl': 'reference', 'metric': FIG_METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * total_s / steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+        'config': {'workload': FIG_WORKLOAD, 'images_per_step_per_gpu': FIG_PER_STEP},
+        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d images of the step (first slices of the seed-1000 scene) per timed step, oracle/aggdraw.c '
+                                   '(restated matplotlib/Agg pipeline; matplotlib itself is not installable here), one process per '
+                                   'core, render time only' % (sample // steps)},
+        'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -164,72 +233,154 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
+class Env:
+    """Process-wide state of the GPU arm: ranks, the launching stream, barrier and max-over-ranks helpers."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py: no CUDA device; this repository has no CPU rendering path (use --impl reference '
+                             'for the CPU baseline)')
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group('nccl', device_id=torch.device('cuda', self.local))
+            self.dist = dist
+        self.stream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.stream)
+        self.st = self.stream.cuda_stream
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device='cuda')
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+
+def timed_steps(env, render, sync, steps, warmup):
+    """>= max(3, warmup) untimed steps (and >= 0.6 s, so clocks and the sampler settle), then exactly `steps` steps between
+    CUDA events on the launching stream, barrier + synchronize on both sides; returns (ms max over ranks, warm-up steps)."""
+    torch = env.torch
+    n_warm, t_warm = 0, time.perf_counter()
+    while n_warm < max(3, warmup) or time.perf_counter() - t_warm < 0.6:
+        render()
+        torch.cuda.synchronize()
+        n_warm += 1
+    env.barrier()
+    sync()
+    return n_warm
+
+
+def figure_leg(env, args, sampler):
+    torch = env.torch
+    from reasoning_image_generation_b200.figure import FigureRenderer
+    from reasoning_image_generation_b200.synth_figure import synthetic_figure_scene
+    n = FIG_PER_STEP
+    scene = synthetic_figure_scene(n, 512, 512, seed=1000, kind='single', first=env.rank * n)
+    r = FigureRenderer(512, 512, device=env.local, max_images=n, max_artists=max(scene.n_artists, 1))
+    out = torch.empty((n, 512, 512, 3), dtype=torch.uint8, device='cuda')
+    r.upload(scene, 'rgb')
+    render = lambda: r.render_resident(out.data_ptr(), stream=env.st)   # noqa: E731
+    if sampler is not None:
+        sampler.start()
+    n_warm = timed_steps(env, render, r.sync, args.steps, args.warmup)
+    r.set_profiling(True)
+    launches0 = r.stats()['kernel_launches']
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env.barrier()
+    ev0.record(env.stream)
+    for _ in range(args.steps):
+        render()
+    ev1.record(env.stream)
+    env.barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler is not None else None
+    r.sync()
+    stats = r.stats()
+    r.set_profiling(False)
+    (ms_max,) = env.max_over_ranks(ms)
+    value = env.world * n * args.steps / (ms_max / 1e3)
+    checksum_dev = int(out[::509, 200:312, 200:312, 0].to(torch.int64).sum().item())
+    del out
+    torch.cuda.empty_cache()
+
+    # ---- e2e: public API, host artist arrays in, pinned host pixels out
+    from reasoning_image_generation_b200.render import PinnedBuffer
+    sub = scene.slice(0, FIG_E2E)
+    pin = PinnedBuffer(FIG_E2E * IMG_BYTES)
+    pinned = pin.array.reshape(FIG_E2E, 512, 512, 3)
+    for _ in range(2):
+        r.render(sub, 'rgb', out=pinned)
+    env.barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 4))
+    for _ in range(e2e_steps):
+        r.render(sub, 'rgb', out=pinned)
+    torch.cuda.synchronize()
+    (dt,) = env.max_over_ranks(time.perf_counter() - t0)
+    st2 = r.stats()
+    e2e_value = env.world * FIG_E2E * e2e_steps / dt
+    per_img_edges = stats['edges'] / n
+    h2d = int(16 * st2['edges'] + 32 * st2['layers'] + 4 * (FIG_E2E + 1) + 4 * FIG_E2E)
+    checksum = int(pinned[::257, 200:312, 200:312, 0].astype('int64').sum())
+    res = {
+        'value': value, 'ms_per_step': ms_max / args.steps, 'warmup': n_warm, 'clocks': clocks,
+        'launches': stats['kernel_launches'] - launches0, 'stats': stats, 'n': n,
+        'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': FIG_E2E * IMG_BYTES,
+                'images_per_step_per_gpu': FIG_E2E, 'host_prepare_ms_per_step': st2['prepare_ms'],
+                'note': 'FigureRenderer.render: host artist arrays in (path pipeline on host threads, edges uploaded), every pixel '
+                        'copied to pinned host memory (PCIe-bound); checksum %d' % checksum},
+        'config': {'workload': FIG_WORKLOAD, 'images_per_step_per_gpu': n, 'l2': 'outputs (25.8 GB/step) exceed L2; no flush needed',
+                   'artists_per_step_per_gpu': scene.n_artists, 'edges_per_image': per_img_edges,
+                   'layers_per_image': stats['layers'] / n, 'out_layout': 'RGB', 'checksum': checksum_dev},
+    }
+    pin.close()
+    r.close()
+    return res
+
+
+def sequence_leg(env, args, sampler, with_cpu):
+    torch = env.torch
     from reasoning_image_generation_b200 import Renderer
     from reasoning_image_generation_b200.dedup import DedupFilter
     from reasoning_image_generation_b200.synth import synthetic_scene
-
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    # stdout carries exactly one JSON line: anything libraries print there (e.g. NCCL's version banner) goes to stderr
-    sys.stdout.flush()
-    json_fd = os.dup(1)
-    os.dup2(2, 1)
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py: no CUDA device; this repository has no CPU rendering path (use --impl reference '
-                         'for the CPU baseline)')
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    world, rank, dist, stream, st = env.world, env.rank, env.dist, env.stream, env.st
+    barrier = env.barrier
     n = PANELS_PER_STEP
     scene = synthetic_scene(n, seed=1000 + rank)
-    r = Renderer(512, 512, device=local, max_panels=n, max_elements=max(scene.n_elements, 1))
+    r = Renderer(512, 512, device=env.local, max_panels=n, max_elements=max(scene.n_elements, 1))
     out = torch.empty((n, 512, 512, 3), dtype=torch.uint8, device='cuda')
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    st = stream.cuda_stream
     r.upload(scene, 'rgb')
-
-    sampler = ClockSampler(local)
-    if rank == 0:
+    render = lambda: r.render_resident(out.data_ptr(), stream=st)   # noqa: E731
+    if sampler is not None:
         sampler.start()
-    n_warm = 0
-    t_warm = time.perf_counter()
-    while n_warm < max(3, args.warmup) or time.perf_counter() - t_warm < 0.6:   # >= 3 steps and long enough for clocks / sampler
-        r.render_resident(out.data_ptr(), stream=st)
-        torch.cuda.synchronize()
-        n_warm += 1
-    barrier()
-    r.sync()
+    n_warm = timed_steps(env, render, r.sync, args.steps, args.warmup)
     r.set_profiling(True)
     launches0 = r.stats()['kernel_launches']
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
     for _ in range(args.steps):
-        r.render_resident(out.data_ptr(), stream=st)
+        render()
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler is not None else None
     r.sync()
     stats = r.stats()
     r.set_profiling(False)
     launches = stats['kernel_launches'] - launches0
-    t = torch.tensor([ms], dtype=torch.float64, device='cuda')
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    (ms_max,) = env.max_over_ranks(ms)
     value = world * n * args.steps / (ms_max / 1e3)
 
     # ---- e2e: public API, host scene in, pinned host pixels out
@@ -243,11 +394,8 @@ def run_ours(args):
     for _ in range(e2e_steps):
         r.render(sub, 'rgb', out=pinned)
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device='cuda')
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * E2E_PANELS * e2e_steps / float(t.item())
+    (dt,) = env.max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * E2E_PANELS * e2e_steps / dt
     h2d = 40 * sub.n_elements + 4 * (sub.n_panels + 1) + sub.n_panels
     d2h = E2E_PANELS * IMG_BYTES
     checksum = int(pinned[::257, 100, 100, 0].astype('int64').sum())
@@ -296,60 +444,113 @@ def run_ours(args):
     e1.record(stream)
     barrier(); r.sync()
     dd_ms = e0.elapsed_time(e1)
-    t = torch.tensor([dd_ms, hash_ms], dtype=torch.float64, device='cuda')
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dd_ms, hash_ms = float(t[0].item()), float(t[1].item())
+    dd_ms, hash_ms = env.max_over_ranks(dd_ms, hash_ms)
     pairs = n_total * (n_total - 1) // 2
 
-    if rank == 0:
-        peak, peak_src = fallback_peak()
-        raster_s = stats['raster_ms'] / 1e3
-        achieved = stats['timed_panels'] * IMG_BYTES / raster_s / 1e9 if raster_s > 0 else 0.0
-        per_launch = stats['timed_panels'] / max(1, stats['timed_launches'])
-        traffic = None
-        tp = os.path.join(ROOT, 'profiles', 'raster_traffic.json')
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp))['dram_bytes_per_panel'] * per_launch
-            except Exception:
-                traffic = None
-        cpu = None
-        if world == 1 and not args.no_cpu:
-            done, cdt, cores, backend = cpu_sample(seed=1000, budget_s=14.0)
-            cpu = {'value': done / cdt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                   'sample': 'first %d panels of the step scene (seed 1000), oracle/ref_render.py (%s backend), '
-                             'one process per core, %.1f s' % (done, backend, cdt)}
-        line = {
-            'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': n_warm, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'panels_per_step_per_gpu': n, 'l2': 'outputs (12.9 GB/step) exceed L2; no flush needed',
-                       'elements_per_step_per_gpu': scene.n_elements, 'out_layout': 'RGB'},
-            'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'panels_per_step_per_gpu': E2E_PANELS, 'note': 'Renderer.render: host SoA scene in, every pixel copied to '
-                    'pinned host memory (PCIe-bound); checksum %d' % checksum},
-            'gpu_launches': launches,
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'kernel': 'k_raster', 'peak_source': peak_src,
-                         'launches': stats['timed_launches'], 'panels_per_launch': per_launch,
-                         'expand_ms_per_step': stats['expand_ms'] / args.steps, 'raster_ms_per_step': stats['raster_ms'] / args.steps,
-                         'whole_step_frac': value / world * IMG_BYTES / 1e9 / peak},
-            'cpu_baseline': cpu,
-            'dedup': {'pairs_per_s': pairs / (dd_ms / 1e3), 'n_hashes': n_total, 'pairs': pairs, 'ms': dd_ms, 'threshold': 10,
-                      'hash_bits': 256, 'hit_pairs': int(hits.item()), 'dropped': int(drop.sum().item()),
-                      'input': 'uniform random 256-bit hashes, seed 0, 1 % planted near-duplicates (SURVEY 8d)',
-                      'exchange': 'nccl all_gather + max all_reduce' if dist is not None else 'none (1 rank)',
-                      'hash_images_per_s': world * n / (hash_ms / 1e3), 'hash_read_gbs_per_gpu': n * IMG_BYTES / (hash_ms / 1e3) / 1e9,
-                      'render_plus_fused_hash_ms_per_step': fused_ms, 'fused_hash_equals_standalone': fused_equal,
-                      'rendered_step_dropped': int(drop_r.sum().item())},
-            'clocks': clocks,
-        }
-        os.write(json_fd, (json.dumps(line) + '\n').encode())
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    peak, peak_src = fallback_peak()
+    raster_s = stats['raster_ms'] / 1e3
+    achieved = stats['timed_panels'] * IMG_BYTES / raster_s / 1e9 if raster_s > 0 else 0.0
+    per_launch = stats['timed_panels'] / max(1, stats['timed_launches'])
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'raster_traffic.json')
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp))['dram_bytes_per_panel'] * per_launch
+        except Exception:
+            traffic = None
+    cpu = None
+    if rank == 0 and world == 1 and with_cpu:
+        done, cdt, cores, backend = cpu_sample(seed=1000, budget_s=args.seq_cpu_budget)
+        cpu = {'value': done / cdt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+               'sample': 'first %d panels of the step scene (seed 1000), oracle/ref_render.py (%s backend), '
+                         'one process per core, %.1f s' % (done, backend, cdt)}
+    res = {
+        'metric': METRIC, 'value': value, 'unit': 'images/s', 'ms_per_step': ms_max / args.steps, 'warmup': n_warm,
+        'config': {'workload': WORKLOAD, 'panels_per_step_per_gpu': n, 'l2': 'outputs (12.9 GB/step) exceed L2; no flush needed',
+                   'elements_per_step_per_gpu': scene.n_elements, 'out_layout': 'RGB'},
+        'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'panels_per_step_per_gpu': E2E_PANELS, 'note': 'Renderer.render: host SoA scene in, every pixel copied to '
+                'pinned host memory (PCIe-bound); checksum %d' % checksum},
+        'gpu_launches': launches,
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': traffic, 'kernel': 'k_raster', 'peak_source': peak_src,
+                     'launches': stats['timed_launches'], 'panels_per_launch': per_launch,
+                     'expand_ms_per_step': stats['expand_ms'] / args.steps, 'raster_ms_per_step': stats['raster_ms'] / args.steps,
+                     'whole_step_frac': value / world * IMG_BYTES / 1e9 / peak},
+        'cpu_baseline': cpu,
+        'dedup': {'pairs_per_s': pairs / (dd_ms / 1e3), 'n_hashes': n_total, 'pairs': pairs, 'ms': dd_ms, 'threshold': 10,
+                  'hash_bits': 256, 'hit_pairs': int(hits.item()), 'dropped': int(drop.sum().item()),
+                  'input': 'uniform random 256-bit hashes, seed 0, 1 % planted near-duplicates (SURVEY 8d)',
+                  'exchange': 'nccl all_gather + max all_reduce' if dist is not None else 'none (1 rank)',
+                  'hash_images_per_s': world * n / (hash_ms / 1e3), 'hash_read_gbs_per_gpu': n * IMG_BYTES / (hash_ms / 1e3) / 1e9,
+                  'render_plus_fused_hash_ms_per_step': fused_ms, 'fused_hash_equals_standalone': fused_equal,
+                  'rendered_step_dropped': int(drop_r.sum().item())},
+        'clocks': clocks,
+    }
     r.close()
+    del out, table
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args):
+    # stdout carries exactly one JSON line: anything libraries print there (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    env = Env()
+    rank, world = env.rank, env.world
+    line = None
+    if args.workload == 'figure':
+        fig = figure_leg(env, args, ClockSampler(env.local) if rank == 0 else None)
+        seq = None if args.no_sequence else sequence_leg(env, args, None, with_cpu=not args.no_cpu)
+        if rank == 0:
+            peak, peak_src = fallback_peak()
+            stats, n = fig['stats'], fig['n']
+            cover_s = stats['cover_ms'] / 1e3
+            achieved = stats['timed_images'] * IMG_BYTES / cover_s / 1e9 if cover_s > 0 else 0.0
+            per_launch = stats['timed_images'] / max(1, stats['timed_launches'])
+            traffic = None
+            tp = os.path.join(ROOT, 'profiles', 'figure_traffic.json')
+            if os.path.exists(tp):
+                try:
+                    traffic = json.load(open(tp))['dram_bytes_per_image'] * per_launch
+                except Exception:
+                    traffic = None
+            cpu = None
+            if world == 1 and not args.no_cpu:
+                done, cdt, cores, backend = fig_cpu_sample(seed=1000, budget_s=14.0)
+                cpu = {'value': done / cdt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                       'sample': 'first %d images of the step scene (seed 1000), oracle/aggdraw.c (restated matplotlib/Agg pipeline; '
+                                 'matplotlib itself is not installable here), one process per core, %.1f s of rendering' % (done, cdt)}
+            line = {
+                'metric': FIG_METRIC, 'value': fig['value'], 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+                'warmup': fig['warmup'], 'ms_per_step': fig['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': fig['config'], 'e2e': fig['e2e'],
+                'gpu_launches': fig['launches'] + (seq['gpu_launches'] if seq else 0),
+                'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                             'traffic': traffic, 'kernel': 'k_figure', 'peak_source': peak_src, 'launches': stats['timed_launches'],
+                             'images_per_launch': per_launch, 'figure_ms_per_step': stats['cover_ms'] / args.steps,
+                             'whole_step_frac': fig['value'] / world * IMG_BYTES / 1e9 / peak},
+                'cpu_baseline': cpu, 'clocks': fig['clocks'],
+            }
+            if seq:
+                line['dedup'] = seq.pop('dedup')
+                seq.pop('clocks', None)
+                line['sequence_panels'] = seq
+    else:
+        seq = sequence_leg(env, args, ClockSampler(env.local) if rank == 0 else None, with_cpu=not args.no_cpu)
+        if rank == 0:
+            line = {'metric': seq['metric'], 'value': seq['value'], 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+                    'warmup': seq['warmup'], 'ms_per_step': seq['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+                    'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': seq['config'], 'e2e': seq['e2e'],
+                    'gpu_launches': seq['gpu_launches'], 'roofline': seq['roofline'], 'cpu_baseline': seq['cpu_baseline'],
+                    'dedup': seq['dedup'], 'clocks': seq['clocks']}
+    if rank == 0:
+        os.write(json_fd, (json.dumps(line) + '\n').encode())
+    if env.dist is not None:
+        env.dist.barrier()
+        env.dist.destroy_process_group()
 
 
 def main():
@@ -358,10 +559,17 @@ def main():
     ap.add_argument('--steps', type=int, default=6)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline legs')
+    ap.add_argument('--workload', default='figure', choices=['figure', 'sequence'],
+                    help='figure: BASELINE configs[1] (headline) + the sequence-panel path as a sub-object; sequence: that path only')
+    ap.add_argument('--no-sequence', action='store_true', help='figure workload: skip the sequence-panel leg')
+    ap.add_argument('--seq-cpu-budget', type=float, default=10.0, help='seconds of CPU work for the sequence-panel cpu_baseline')
     args = ap.parse_args()
     if args.impl == 'reference':
-        run_reference(args)
+        if args.workload == 'figure':
+            run_reference_figure(args)
+        else:
+            run_reference(args)
     else:
         run_ours(args)
 

@@ -68,8 +68,8 @@ k_expand(const DElem *__restrict__ elems, const uint32_t *__restrict__ eorder, u
         ElemHdr h;
         h.rec_begin = r0;
         h.nrec = fits ? plan.nrec : 0;
-        h.ymin = (int16_t)(fits ? plan.ymin : 1);
-        h.ymax = (int16_t)(fits ? plan.ymax : 0);
+        h.ymin = (int16_t)((fits && plan.ymin <= plan.ymax) ? plan.ymin : 32767);   // empty: a range no band overlaps
+        h.ymax = (int16_t)((fits && plan.ymin <= plan.ymax) ? plan.ymax : -32768);  // (1 > 0 would overlap the band of rows 0..4)
         h.nsum = nsum;
         hdrs[e] = h;
         if (!fits) atomicExch(&counters[CTR_OVERFLOW], 1u);
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const Raste
     uint32_t cur_slot = 0xffffffffu, panel = 0, eb = 0, ee = 0;
     bool use_grid = false;
     ElemHdr myh;
-    myh.rec_begin = 0; myh.nrec = 0; myh.ymin = 1; myh.ymax = 0; myh.nsum = 0;
+    myh.rec_begin = 0; myh.nrec = 0; myh.ymin = 32767; myh.ymax = -32768; myh.nsum = 0;
     RasterOps ops;
     ops.mine = rec_nop(); ops.j = 0; ops.base = P.recs;
 
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(RASTER_MAX_WARPS * 32, 1) k_raster(const Raste
                 eb = P.panel_begin[panel];
                 ee = P.panel_begin[panel + 1];
                 use_grid = P.panel_flags[panel] & 1;
-                myh.rec_begin = 0; myh.nrec = 0; myh.ymin = 1; myh.ymax = 0; myh.nsum = 0;
+                myh.rec_begin = 0; myh.nrec = 0; myh.ymin = 32767; myh.ymax = -32768; myh.nsum = 0;
                 if (eb + lane < ee) myh = P.hdrs[eb + lane];     // lane e keeps the header of the panel's e-th element
             }
             const uint32_t pl = panel - P.p0;
