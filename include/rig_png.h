@@ -1,0 +1,60 @@
+/* rig_png.h -- C ABI of the device-side PNG writer of librig.so.
+ *
+ * The reference turns every rendered image into a PNG file on the host:
+ *     save_image(path, img) -> cv2.imwrite(path, img)                  /root/reference/src/utils.py:18-21
+ *     (call sites: src/generator.py:342,390,415,501,538)
+ *     fig.savefig(save_path, dpi=dpi, ...)  (matplotlib -> libpng)     /root/reference/multigraph_generation/generator.py:256
+ * At GPU render rates that is the end-to-end bottleneck twice over: host zlib, and before it the PCIe copy of 786 KB of
+ * raw pixels per image.  These entry points encode the images where they are rendered: filter (Sub), LZ77 restricted to
+ * zero runs, fixed-Huffman deflate, Adler-32 and CRC-32 all run in CUDA kernels, and only the finished PNG byte streams
+ * (typically 5-20 KB per 512 x 512 image of this data set) cross PCIe.  The streams are standard PNG (8-bit RGB, one IDAT
+ * chunk, zlib stream of byte-aligned fixed-Huffman blocks): any decoder reads them; they are NOT byte-identical to what
+ * libpng would write, and the parity criterion is that they decode to exactly the rendered pixels.
+ * Plain C types only; every function returns 0 or a negative RIG_E_* code (include/rig.h).
+ */
+#ifndef RIG_PNG_H
+#define RIG_PNG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "rig.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rig_png_ctx rig_png_ctx;
+
+/* Context on CUDA device `device` for W x H x 3 images (W a multiple of 16), at most max_images per call. */
+int rig_png_create(int device, int W, int H, int max_images, rig_png_ctx **out);
+void rig_png_destroy(rig_png_ctx *ctx);
+const char *rig_png_last_error(const rig_png_ctx *ctx);
+
+/* Upper bound of the bytes n images can encode to (for sizing `out`). */
+size_t rig_png_bound(const rig_png_ctx *ctx, int n);
+
+/* Encodes n images of H*W*3 bytes at imgs_dev (device memory, as written by rig_render_* / rig_figure_render_*; `layout`
+ * says whether their channel order is RGB or BGR) into n PNG files stored back to back.
+ *   offsets_host  [n + 1] uint64, host memory: file i is out[offsets[i] .. offsets[i+1])
+ *   out_is_device = 0: `out` is host memory (pinned for full speed) of at least out_capacity bytes; the call returns after
+ *                      the copy.  RIG_E_CAPACITY if the files do not fit.
+ *   out_is_device = 1: `out` is device memory; the call returns after the kernels have finished (the sizes are needed on
+ *                      the host).
+ * `stream` (a cudaStream_t or NULL) is the stream the images were rendered on; encoding is ordered after it.           */
+int rig_png_encode(rig_png_ctx *ctx, const uint8_t *imgs_dev, int n, int layout, uint8_t *out, size_t out_capacity,
+                   uint64_t *offsets_host, int out_is_device, void *stream);
+
+typedef struct rig_png_stats {
+    uint64_t kernel_launches;
+    uint64_t images, png_bytes;      /* totals since creation */
+    double encode_ms;                /* summed CUDA-event time of the encode kernels since rig_png_set_profiling(ctx, 1) */
+    uint64_t timed_images;
+} rig_png_stats;
+int rig_png_get_stats(rig_png_ctx *ctx, rig_png_stats *out);
+int rig_png_set_profiling(rig_png_ctx *ctx, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIG_PNG_H */

@@ -1,0 +1,496 @@
+// rig_png.cuh -- device-side PNG writer: filter + deflate + checksums in CUDA.
+//
+// Replaces cv2.imwrite / fig.savefig's libpng on the host (src/utils.py:18-21; multigraph_generation/generator.py:256).
+// An image is cut into pieces of PNG_PIECE_ROWS rows; one warp encodes one piece into a byte-aligned run of deflate data:
+//     [fixed-Huffman block: per row, the Sub-filtered bytes as literals, zero runs as (length, distance 1) matches][EOB]
+//     [empty stored block 00 00 FF FF]                     <- zlib's "sync flush": the next piece starts on a byte boundary
+// so pieces can be produced independently and joined by byte offsets.  The puzzle images are flat colour with thin strokes:
+// after the Sub filter (x - left pixel) almost every byte is zero, and restricting LZ77 to zero runs loses little.
+//   k_png_pieces    lanes own 48-byte chunks (16 pixels) of a row; zero runs are merged across lanes with a ballot; bits are
+//                   counted, offsets come from a warp scan, then the same walk emits them with shared-memory ORs
+//   k_png_sizes / k_png_scan   bytes per file and their exclusive prefix sum (file offsets)
+//   k_png_assemble  one warp per file: header, pieces, final empty block, Adler-32 (combined from per-piece partial sums),
+//                   CRC-32 (per-lane table-driven CRC of a contiguous segment, combined by polynomial multiplication), IEND
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rig {
+
+#ifndef PNG_PIECE_ROWS
+#define PNG_PIECE_ROWS 4
+#endif
+constexpr int PNG_ROWS = PNG_PIECE_ROWS;
+constexpr int PNG_CHUNK = 48;                 // bytes per lane per pass = 16 pixels
+constexpr uint32_t PNG_SLOT = 512;            // bytes reserved per piece; larger pieces go to the overflow arena
+constexpr uint32_t PNG_FILE_OVERHEAD = 65;    // signature 8 + IHDR 25 + IDAT 12 + zlib header 2 + final block 2 + Adler 4 + IEND 12
+constexpr uint32_t ADLER_MOD = 65521u;
+constexpr uint32_t CRC_POLY = 0xedb88320u;
+
+struct PngPiece {
+    uint32_t nbytes;     // deflate bytes of the piece
+    uint32_t where;      // byte offset of the piece in the scratch area
+    uint32_t a, b;       // Adler partial sums over the piece's uncompressed bytes: sum d, sum d * (len - index), mod 65521
+};
+
+struct PngTables {
+    uint32_t crc[256];
+    uint32_t x2n[32];    // x^(2^n) mod P (reflected), as zlib's crc32_combine uses
+    uint8_t header[33];  // signature + IHDR chunk of this context's W x H
+};
+
+__host__ __device__ inline size_t png_piece_buf_bytes(int W)   // worst case of one piece, + tail, rounded to 16
+{
+    const size_t bits = (size_t)PNG_ROWS * (1 + 3 * (size_t)W) * 9 + 64;
+    return ((bits + 7) / 8 + 8 + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ uint32_t png_rev(uint32_t code, int nbits) { return __brev(code) >> (32 - nbits); }
+// fixed-Huffman literal: bits (already reversed for LSB-first packing) and length
+__device__ __forceinline__ void png_literal(uint32_t v, uint32_t &code, int &nbits)
+{
+    if (v < 144u) { code = png_rev(0x30u + v, 8); nbits = 8; }
+    else { code = png_rev(0x190u + (v - 144u), 9); nbits = 9; }
+}
+// match of `len` (3..258) at distance 1: length symbol + extra bits + 5-bit distance code 0
+__device__ __forceinline__ void png_match(uint32_t len, uint32_t &code, int &nbits)
+{
+    uint32_t sym, eb = 0, extra = 0;
+    if (len == 258u) sym = 285u;
+    else {
+        const uint32_t l = len - 3u;
+        if (l < 8u) sym = 257u + l;
+        else {
+            eb = (31u - (uint32_t)__clz(l)) - 2u;
+            sym = 257u + 4u * eb + 4u + ((l >> eb) & 3u);
+            extra = l & ((1u << eb) - 1u);
+        }
+    }
+    if (sym < 280u) { code = png_rev(sym - 256u, 7); nbits = 7; }
+    else { code = png_rev(0xc0u + (sym - 280u), 8); nbits = 8; }
+    code |= extra << nbits;
+    nbits += (int)eb;
+    nbits += 5;            // distance code 0 (distance 1): five zero bits
+}
+
+struct PngCount {
+    uint32_t bits = 0;
+    __device__ __forceinline__ void put(uint32_t, int n) { bits += (uint32_t)n; }
+};
+struct PngEmit {
+    uint32_t *buf;
+    uint32_t pos;
+    __device__ __forceinline__ void put(uint32_t code, int n)
+    {
+        const uint32_t w = pos >> 5, sh = pos & 31u;
+        atomicOr(buf + w, code << sh);
+        if (sh + (uint32_t)n > 32u) atomicOr(buf + w + 1, code >> (32u - sh));
+        pos += (uint32_t)n;
+    }
+};
+// r zeros whose predecessor in the stream is a zero byte
+template <class Sink>
+__device__ __forceinline__ void png_zero_matches(Sink &s, uint32_t r)
+{
+    while (r >= 3u) {
+        const uint32_t L = r > 258u ? 258u : r;
+        uint32_t code;
+        int nb;
+        png_match(L, code, nb);
+        s.put(code, nb);
+        r -= L;
+    }
+    while (r) { s.put(png_rev(0x30u, 8), 8); r--; }
+}
+// The tokens of one lane's chunk.  nz: bit i set = filtered byte i is non-zero; fb: the chunk's filtered bytes (shared memory);
+// skip: leading zeros that belong to a run an earlier lane emits; tail_extra: zeros after this chunk that continue its trailing
+// run (all-zero lanes that follow, plus the leading zeros of the lane after them).
+template <class Sink>
+__device__ __forceinline__ void png_chunk_tokens(Sink &s, unsigned long long nz, const uint8_t *fb, int skip, uint32_t tail_extra, bool filter_byte)
+{
+    if (filter_byte) s.put(png_rev(0x30u + 1u, 8), 8);       // filter type 1 (Sub) opens the row
+    int pos = skip;
+    while (pos < PNG_CHUNK) {
+        const unsigned long long rem = nz >> pos;
+        if (rem & 1ull) {
+            uint32_t code;
+            int nb;
+            png_literal(fb[pos], code, nb);
+            s.put(code, nb);
+            pos++;
+        } else {
+            const int gap = rem ? (__ffsll((long long)rem) - 1) : (PNG_CHUNK - pos);
+            uint32_t r = (uint32_t)gap;
+            if (!rem) r += tail_extra;
+            s.put(png_rev(0x30u, 8), 8);                      // the run's first zero is a literal
+            png_zero_matches(s, r - 1u);
+            pos += gap;
+        }
+    }
+}
+
+struct PngParams {
+    const uint8_t *imgs;
+    int n, W, H, bgr;
+    uint32_t pieces_per_image;
+    PngPiece *pieces;
+    uint8_t *scratch;               // [n * pieces_per_image * PNG_SLOT][overflow arena]
+    unsigned long long over_begin, over_cap;
+    unsigned long long *counters;   // [0] overflow arena cursor, [1] error flag
+};
+
+// shared memory per warp: bit buffer + 32 x 48 filtered bytes
+__host__ __device__ inline size_t png_warp_smem(int W) { return png_piece_buf_bytes(W) + 32 * PNG_CHUNK; }
+
+__global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = png_warp_smem(P.W);
+    uint32_t *buf = (uint32_t *)(smem + (size_t)warp * per_warp);
+    uint8_t *fbytes = (uint8_t *)buf + png_piece_buf_bytes(P.W) + lane * PNG_CHUNK;
+    const unsigned long long gp = (unsigned long long)blockIdx.x * wpc + warp;
+    if (gp >= (unsigned long long)P.n * P.pieces_per_image) return;
+    const uint32_t image = (uint32_t)(gp / P.pieces_per_image), piece = (uint32_t)(gp % P.pieces_per_image);
+    const int y0 = (int)piece * PNG_ROWS, y1 = min(P.H, y0 + PNG_ROWS);
+    const int row_bytes = 3 * P.W, chunks = P.W / 16;
+    const uint32_t RL = 1u + (uint32_t)row_bytes, L = (uint32_t)(y1 - y0) * RL;     // uncompressed bytes per row / in this piece
+    const uint32_t buf_words = (uint32_t)(png_piece_buf_bytes(P.W) / 4);
+    for (uint32_t i = lane; i < buf_words; i += 32) buf[i] = 0u;
+    __syncwarp();
+    uint32_t bitpos = 3;
+    if (lane == 0) buf[0] = 2u;          // BFINAL = 0, BTYPE = 01 (fixed Huffman), LSB first
+    unsigned long long ad_a = 0, ad_b = 0;
+    const uint8_t *img = P.imgs + (size_t)image * P.H * row_bytes;
+    for (int y = y0; y < y1; y++) {
+        const uint32_t row_pos = (uint32_t)(y - y0) * RL;        // position of the row's filter byte in the piece
+        if (lane == 0) { ad_a += 1u; ad_b += (unsigned long long)(L - row_pos); }
+        uint32_t pass_prev = 0u;           // last word of the previous pass's last chunk (rows wider than 512 pixels)
+        for (int c0 = 0; c0 < chunks; c0 += 32) {
+            const int c = c0 + lane;
+            const bool live = c < chunks;
+            uint32_t w[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) w[i] = 0u;
+            if (live) {
+                const uint4 *src = (const uint4 *)(img + (size_t)y * row_bytes + (size_t)c * PNG_CHUNK);
+                const uint4 a = __ldg(src), b = __ldg(src + 1), d = __ldg(src + 2);
+                w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+                w[8] = d.x; w[9] = d.y; w[10] = d.z; w[11] = d.w;
+                if (P.bgr) {
+#pragma unroll
+                    for (int g = 0; g < 12; g += 3) {
+                        const uint32_t t = __byte_perm(w[g], w[g + 2], 0x0043);
+                        const uint32_t o0 = __byte_perm(w[g], w[g + 1], 0x5012), o1 = __byte_perm(w[g + 1], t, 0x3540),
+                                       o2 = __byte_perm(w[g + 1], w[g + 2], 0x5672);
+                        w[g] = o0; w[g + 1] = o1; w[g + 2] = o2;
+                    }
+                }
+            }
+            // Sub filter: byte i minus byte i - 3 (the row's first pixel keeps its value)
+            uint32_t prev = __shfl_up_sync(0xffffffffu, w[11], 1);
+            if (lane == 0) prev = pass_prev;   // 0 at the start of the row: the first pixel keeps its value
+            pass_prev = __shfl_sync(0xffffffffu, w[11], 31);
+            uint32_t f[12];
+            uint32_t any = 0u;
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const uint32_t left = __funnelshift_r(i ? w[i - 1] : prev, w[i], 8);
+                f[i] = __vsub4(w[i], left);
+                any |= f[i];
+            }
+            // zero structure of the chunk
+            unsigned long long nz = 0ull;
+            if (any && live) {                                  // (a dead lane's chunk is all zeros but its left neighbour is not)
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    const uint32_t m = __vsetne4(f[i], 0u);       // 1 per non-zero byte
+                    const uint32_t nib = (m & 1u) | ((m >> 7) & 2u) | ((m >> 14) & 4u) | ((m >> 21) & 8u);
+                    nz |= (unsigned long long)nib << (4 * i);
+                }
+                uint4 *dst = (uint4 *)fbytes;
+                dst[0] = make_uint4(f[0], f[1], f[2], f[3]);
+                dst[1] = make_uint4(f[4], f[5], f[6], f[7]);
+                dst[2] = make_uint4(f[8], f[9], f[10], f[11]);
+                // Adler partial sums of this chunk
+                unsigned long long m = nz;
+                uint32_t s0 = 0, s1 = 0;
+                while (m) {
+                    const int i = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const uint32_t v = fbytes[i];
+                    s0 += v;
+                    s1 += v * (uint32_t)i;
+                }
+                const uint32_t base = row_pos + 1u + (uint32_t)c * PNG_CHUNK;
+                ad_a += s0;
+                ad_b += (unsigned long long)(L - base) * s0 - s1;
+            }
+            const int lead = live ? (nz ? (__ffsll((long long)nz) - 1) : PNG_CHUNK) : 0;      // leading zeros
+            const bool all_zero = live && nz == 0ull;
+            const bool last_zero = live && !((nz >> (PNG_CHUNK - 1)) & 1ull);
+            const uint32_t zmask = __ballot_sync(0xffffffffu, all_zero);
+            const uint32_t prev_last_zero = __shfl_up_sync(0xffffffffu, (uint32_t)last_zero, 1);
+            const int skip = (lane > 0 && prev_last_zero) ? lead : 0;
+            // zeros that continue this chunk's trailing run: the all-zero lanes after it and the next lane's leading zeros
+            uint32_t tail_extra = 0;
+            {
+                const uint32_t after = lane == 31 ? 0u : (zmask >> (lane + 1));
+                const int run = lane == 31 ? 0 : (__ffs((int)~after) - 1);          // consecutive all-zero lanes (~after has a set bit: lanes >= 32 - lane - 1 read 0)
+                const int nxt = lane + 1 + run;
+                const int nxt_lead = __shfl_sync(0xffffffffu, lead, nxt & 31);
+                tail_extra = (uint32_t)run * PNG_CHUNK + ((nxt < 32) ? (uint32_t)nxt_lead : 0u);
+            }
+            __syncwarp();
+            const bool mine = live && skip < PNG_CHUNK;          // a fully skipped chunk emits nothing
+            const bool fbyte = lane == 0 && c0 == 0;
+            PngCount cnt;
+            if (mine || fbyte) png_chunk_tokens(cnt, nz, fbytes, mine ? skip : PNG_CHUNK, tail_extra, fbyte);
+            uint32_t incl = cnt.bits;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            PngEmit em;
+            em.buf = buf;
+            em.pos = bitpos + incl - cnt.bits;
+            if (mine || fbyte) png_chunk_tokens(em, nz, fbytes, mine ? skip : PNG_CHUNK, tail_extra, fbyte);
+            bitpos += __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+        }
+    }
+    // end of block (7 zero bits), empty stored block (3 zero bits, pad to a byte, 00 00 FF FF)
+    bitpos += 10;
+    bitpos = (bitpos + 7u) & ~7u;
+    __syncwarp();
+    if (lane == 0) {
+        PngEmit em;
+        em.buf = buf;
+        em.pos = bitpos + 16;
+        em.put(0xffffu, 16);
+    }
+    const uint32_t nbytes = bitpos / 8 + 4;
+    // Adler partial sums of the piece
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        ad_a += __shfl_xor_sync(0xffffffffu, ad_a, o);
+        ad_b += __shfl_xor_sync(0xffffffffu, ad_b, o);
+    }
+    unsigned long long where = gp * PNG_SLOT;
+    if (nbytes > PNG_SLOT) {
+        unsigned long long off = 0;
+        if (lane == 0) off = atomicAdd(P.counters, (unsigned long long)((nbytes + 15u) & ~15u));
+        off = __shfl_sync(0xffffffffu, off, 0);
+        if (off + nbytes > P.over_cap) {
+            if (lane == 0) {
+                atomicExch(P.counters + 1, 1ull);
+                PngPiece pc;
+                pc.nbytes = 0; pc.where = 0; pc.a = 0; pc.b = 0;
+                P.pieces[gp] = pc;
+            }
+            return;
+        }
+        where = P.over_begin + off;
+    }
+    __syncwarp();
+    {
+        uint4 *dst = (uint4 *)(P.scratch + where);
+        const uint4 *src = (const uint4 *)buf;
+        for (uint32_t i = lane; i < (nbytes + 15u) / 16u; i += 32) dst[i] = src[i];
+    }
+    if (lane == 0) {
+        PngPiece pc;
+        pc.nbytes = nbytes;
+        pc.where = (uint32_t)(where / 16);      // scratch offsets are multiples of 16
+        pc.a = (uint32_t)(ad_a % ADLER_MOD);
+        pc.b = (uint32_t)(ad_b % ADLER_MOD);
+        P.pieces[gp] = pc;
+    }
+}
+
+__global__ void k_png_sizes(const PngPiece *__restrict__ pieces, int n, uint32_t ppi, unsigned long long *__restrict__ sizes)
+{
+    const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (img >= n) return;
+    unsigned long long s = 0;
+    for (uint32_t p = lane; p < ppi; p += 32) s += pieces[(size_t)img * ppi + p].nbytes;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sizes[img] = s + PNG_FILE_OVERHEAD;
+}
+
+// exclusive prefix sum of sizes[0..n) into offsets[0..n]; one CTA of 1024 threads
+__global__ void __launch_bounds__(1024) k_png_scan(const unsigned long long *__restrict__ sizes, int n, unsigned long long *__restrict__ offsets)
+{
+    __shared__ unsigned long long part[1024];
+    const int t = threadIdx.x;
+    const int per = (n + 1023) / 1024;
+    const int b = min(n, t * per), e = min(n, b + per);
+    unsigned long long s = 0;
+    for (int i = b; i < e; i++) s += sizes[i];
+    part[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned long long v = t >= o ? part[t - o] : 0ull;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    unsigned long long run = t ? part[t - 1] : 0ull;
+    for (int i = b; i < e; i++) {
+        offsets[i] = run;
+        run += sizes[i];
+    }
+    if (t == 1023) offsets[n] = part[1023];
+}
+
+// a * b mod P over GF(2), reflected bit order (zlib crc32.c multmodp)
+__device__ __forceinline__ uint32_t crc_multmodp(uint32_t a, uint32_t b)
+{
+    uint32_t p = 0;
+#pragma unroll 4
+    for (int i = 0; i < 32; i++) {
+        if (a & (0x80000000u >> i)) p ^= b;
+        b = (b & 1u) ? (b >> 1) ^ CRC_POLY : b >> 1;
+    }
+    return p;
+}
+// x^(8 * nbytes) mod P
+__device__ __forceinline__ uint32_t crc_x8n(const uint32_t *x2n, unsigned long long nbytes)
+{
+    uint32_t p = 0x80000000u;
+    unsigned k = 3;
+    while (nbytes) {
+        if (nbytes & 1ull) p = crc_multmodp(x2n[k & 31], p);
+        nbytes >>= 1;
+        k++;
+    }
+    return p;
+}
+
+struct PngAssembleParams {
+    const PngPiece *pieces;
+    const uint8_t *scratch;
+    const unsigned long long *offsets;
+    const PngTables *tables;
+    uint8_t *out;
+    int n, W, H;
+    uint32_t pieces_per_image;
+};
+
+__device__ __forceinline__ void put_be32(uint8_t *p, uint32_t v)
+{
+    p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v;
+}
+
+__global__ void __launch_bounds__(256) k_png_assemble(const PngAssembleParams P)
+{
+    __shared__ uint32_t crc_t[256];
+    __shared__ uint32_t x2n[32];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) crc_t[i] = P.tables->crc[i];
+    if (threadIdx.x < 32) x2n[threadIdx.x] = P.tables->x2n[threadIdx.x];
+    __syncthreads();
+    const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (img >= P.n) return;
+    const uint32_t ppi = P.pieces_per_image;
+    const PngPiece *pcs = P.pieces + (size_t)img * ppi;
+    uint8_t *file = P.out + P.offsets[img];
+    const unsigned long long total = P.offsets[img + 1] - P.offsets[img];
+    const uint32_t data_len = (uint32_t)(total - PNG_FILE_OVERHEAD) + 8u;       // zlib header + pieces + final block + Adler
+    const uint32_t RL = 1u + 3u * (uint32_t)P.W;
+    const unsigned long long ulen = (unsigned long long)P.H * RL;               // uncompressed (filtered) bytes
+    // lane l owns pieces [l * ppl, (l + 1) * ppl): a contiguous segment of the file
+    const uint32_t ppl = (ppi + 31u) / 32u;
+    const uint32_t p0 = min(ppi, (uint32_t)lane * ppl), p1 = min(ppi, p0 + ppl);
+    unsigned long long seg_bytes = 0, sa = 0, sb = 0;
+    for (uint32_t p = p0; p < p1; p++) {
+        const PngPiece pc = pcs[p];
+        seg_bytes += pc.nbytes;
+        const unsigned long long rows_before = (unsigned long long)p * PNG_ROWS, rows_p = min((unsigned long long)PNG_ROWS, (unsigned long long)P.H - rows_before);
+        const unsigned long long after = ulen - (rows_before + rows_p) * RL;
+        sa += pc.a;
+        sb += pc.b + (unsigned long long)pc.a * (after % ADLER_MOD);
+        sb %= ADLER_MOD;
+    }
+    // offsets of the segments, Adler-32 of the whole stream
+    unsigned long long incl = seg_bytes;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    const uint32_t adler = ((uint32_t)((ulen + sb) % ADLER_MOD) << 16) | (uint32_t)((1ull + sa) % ADLER_MOD);
+    // fixed parts
+    for (int i = lane; i < 33; i += 32) file[i] = P.tables->header[i];
+    uint8_t *idat = file + 33;
+    if (lane == 0) {
+        put_be32(idat, data_len);
+        idat[4] = 'I'; idat[5] = 'D'; idat[6] = 'A'; idat[7] = 'T';
+        idat[8] = 0x78; idat[9] = 0x01;
+    }
+    uint8_t *body = idat + 10;                                   // first piece byte
+    const unsigned long long pieces_total = __shfl_sync(0xffffffffu, incl, 31);
+    uint8_t *tail = body + pieces_total;
+    if (lane == 31) {
+        tail[0] = 0x03; tail[1] = 0x00;                           // final block: fixed Huffman, immediately end of block
+        put_be32(tail + 2, adler);
+        const uint8_t iend[12] = {0, 0, 0, 0, 'I', 'E', 'N', 'D', 0xae, 0x42, 0x60, 0x82};
+        for (int i = 0; i < 12; i++) tail[10 + i] = iend[i];
+    }
+    // copy this lane's pieces and take the CRC of its segment: lane 0 starts with "IDAT" + zlib header, lane 31 ends with
+    // the final block and the Adler-32
+    uint32_t crc = 0xffffffffu;
+    unsigned long long my_len = seg_bytes;
+    if (lane == 0) {
+        const uint8_t pre[6] = {'I', 'D', 'A', 'T', 0x78, 0x01};
+        for (int i = 0; i < 6; i++) crc = crc_t[(crc ^ pre[i]) & 0xffu] ^ (crc >> 8);
+        my_len += 6;
+    }
+    uint8_t *dst = body + (incl - seg_bytes);
+    for (uint32_t p = p0; p < p1; p++) {
+        const PngPiece pc = pcs[p];
+        const uint4 *src = (const uint4 *)(P.scratch + (size_t)pc.where * 16);
+        uint32_t left = pc.nbytes;
+        for (uint32_t q = 0; left; q++) {
+            const uint4 v = __ldg(src + q);
+            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if ((uint32_t)k < left) {
+                    const uint32_t b = (wv[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                    dst[k] = (uint8_t)b;
+                    crc = crc_t[(crc ^ b) & 0xffu] ^ (crc >> 8);
+                }
+            }
+            const uint32_t step = left < 16u ? left : 16u;
+            dst += step;
+            left -= step;
+        }
+    }
+    if (lane == 31) {
+        const uint8_t post[6] = {0x03, 0x00, (uint8_t)(adler >> 24), (uint8_t)(adler >> 16), (uint8_t)(adler >> 8), (uint8_t)adler};
+        for (int i = 0; i < 6; i++) crc = crc_t[(crc ^ post[i]) & 0xffu] ^ (crc >> 8);
+        my_len += 6;
+    }
+    crc ^= 0xffffffffu;
+    // combine the 32 segment CRCs in order: crc(A || B) = crc(A) * x^(8 len B) + crc(B)   (zlib crc32_combine)
+    unsigned long long len = my_len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t rc = __shfl_down_sync(0xffffffffu, crc, o);
+        const unsigned long long rl = __shfl_down_sync(0xffffffffu, len, o);
+        if ((lane & (2 * o - 1)) == 0) {
+            if (rl) crc = crc_multmodp(crc_x8n(x2n, rl), crc) ^ rc;
+            len += rl;
+        }
+    }
+    if (lane == 0) put_be32(tail + 6, crc);
+}
+
+}  // namespace rig

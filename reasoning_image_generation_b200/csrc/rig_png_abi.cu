@@ -1,0 +1,256 @@
+// rig_png_abi.cu -- the extern "C" boundary declared in include/rig_png.h.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/rig_png.h"
+#include "rig_png.cuh"
+
+using namespace rig;
+
+namespace {
+thread_local char g_png_create_err[512] = "";
+
+uint32_t host_multmodp(uint32_t a, uint32_t b)
+{
+    uint32_t p = 0;
+    for (int i = 0; i < 32; i++) {
+        if (a & (0x80000000u >> i)) p ^= b;
+        b = (b & 1u) ? (b >> 1) ^ CRC_POLY : b >> 1;
+    }
+    return p;
+}
+}  // namespace
+
+struct rig_png_ctx {
+    int device = 0, W = 0, H = 0, max_images = 0;
+    uint32_t ppi = 0;
+    int wpc = 4;
+    size_t smem = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev0 = nullptr, ev1 = nullptr;
+    PngTables *d_tables = nullptr;
+    PngPiece *d_pieces = nullptr;
+    uint8_t *d_scratch = nullptr, *d_out = nullptr;
+    size_t scratch_bytes = 0, over_begin = 0, out_cap = 0;
+    unsigned long long *d_sizes = nullptr, *d_offsets = nullptr, *d_counters = nullptr;
+    unsigned long long *h_offsets = nullptr;     // pinned
+    rig_png_stats stats = {};
+    bool profiling = false;
+    char err[512] = "";
+};
+
+namespace {
+int pfail(rig_png_ctx *c, int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c ? c->err : g_png_create_err, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define PCK(ctx, call)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return pfail(ctx, RIG_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+}  // namespace
+
+extern "C" {
+
+const char *rig_png_last_error(const rig_png_ctx *ctx) { return ctx ? ctx->err : g_png_create_err; }
+
+size_t rig_png_bound(const rig_png_ctx *c, int n)
+{
+    if (!c || n <= 0) return 0;
+    // literal-only worst case: 9 bits per filtered byte, plus per-piece and per-file framing
+    const size_t per_piece = ((size_t)PNG_ROWS * (1 + 3 * (size_t)c->W) * 9 + 7) / 8 + 8;
+    return (size_t)n * ((size_t)c->ppi * per_piece + PNG_FILE_OVERHEAD);
+}
+
+int rig_png_create(int device, int W, int H, int max_images, rig_png_ctx **out)
+{
+    if (!out) return pfail(nullptr, RIG_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (W <= 0 || H <= 0 || W % 16 || W > 4096 || H > 4096)
+        return pfail(nullptr, RIG_E_INVALID, "unsupported image %dx%d (W %% 16 == 0, <= 4096)", W, H);
+    if (max_images <= 0) return pfail(nullptr, RIG_E_INVALID, "max_images must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return pfail(nullptr, RIG_E_NODEVICE, "no usable CUDA device (%s); this library has no CPU path",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return pfail(nullptr, RIG_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    rig_png_ctx *c = new rig_png_ctx();
+    c->device = device; c->W = W; c->H = H; c->max_images = max_images;
+    c->ppi = (uint32_t)((H + PNG_ROWS - 1) / PNG_ROWS);
+    auto bail = [&](int code) {
+        snprintf(g_png_create_err, sizeof g_png_create_err, "%s", c->err);
+        rig_png_destroy(c);
+        return code;
+    };
+#define PCKC(call)                                                                                 \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            pfail(c, RIG_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                  \
+            return bail(RIG_E_CUDA);                                                               \
+        }                                                                                          \
+    } while (0)
+    PCKC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PCKC(cudaGetDeviceProperties(&prop, device));
+    c->wpc = 8;
+    while (c->wpc > 1 && c->wpc * png_warp_smem(W) > 96 * 1024) c->wpc--;
+    c->smem = c->wpc * png_warp_smem(W);
+    if (c->smem > prop.sharedMemPerBlockOptin) {
+        pfail(c, RIG_E_UNSUPPORTED, "image width %d needs %zu B of shared memory per piece", W, c->smem);
+        return bail(RIG_E_UNSUPPORTED);
+    }
+    PCKC(cudaFuncSetAttribute(k_png_pieces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+    PCKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PCKC(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+    PCKC(cudaEventCreate(&c->ev0));
+    PCKC(cudaEventCreate(&c->ev1));
+    PngTables T;
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t v = i;
+        for (int k = 0; k < 8; k++) v = (v & 1u) ? (v >> 1) ^ CRC_POLY : v >> 1;
+        T.crc[i] = v;
+    }
+    T.x2n[0] = 1u << 30;
+    for (int i = 1; i < 32; i++) T.x2n[i] = host_multmodp(T.x2n[i - 1], T.x2n[i - 1]);
+    {
+        const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+        memcpy(T.header, sig, 8);
+        uint8_t *h = T.header + 8;
+        h[0] = 0; h[1] = 0; h[2] = 0; h[3] = 13;
+        memcpy(h + 4, "IHDR", 4);
+        h[8] = (uint8_t)(W >> 24); h[9] = (uint8_t)(W >> 16); h[10] = (uint8_t)(W >> 8); h[11] = (uint8_t)W;
+        h[12] = (uint8_t)(H >> 24); h[13] = (uint8_t)(H >> 16); h[14] = (uint8_t)(H >> 8); h[15] = (uint8_t)H;
+        h[16] = 8; h[17] = 2; h[18] = 0; h[19] = 0; h[20] = 0;      // 8-bit RGB, deflate, adaptive filtering, no interlace
+        uint32_t crc = 0xffffffffu;
+        for (int i = 4; i < 21; i++) crc = T.crc[(crc ^ h[i]) & 0xff] ^ (crc >> 8);
+        crc ^= 0xffffffffu;
+        h[21] = (uint8_t)(crc >> 24); h[22] = (uint8_t)(crc >> 16); h[23] = (uint8_t)(crc >> 8); h[24] = (uint8_t)crc;
+    }
+    PCKC(cudaMalloc(&c->d_tables, sizeof T));
+    PCKC(cudaMemcpy(c->d_tables, &T, sizeof T, cudaMemcpyHostToDevice));
+    const size_t npieces = (size_t)max_images * c->ppi;
+    PCKC(cudaMalloc(&c->d_pieces, sizeof(PngPiece) * npieces));
+    c->over_begin = npieces * PNG_SLOT;
+    c->scratch_bytes = 2 * c->over_begin + (1u << 20);
+    PCKC(cudaMalloc(&c->d_scratch, c->scratch_bytes));
+    PCKC(cudaMalloc(&c->d_sizes, sizeof(unsigned long long) * ((size_t)max_images + 1)));
+    PCKC(cudaMalloc(&c->d_offsets, sizeof(unsigned long long) * ((size_t)max_images + 1)));
+    PCKC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 2));
+    PCKC(cudaMallocHost(&c->h_offsets, sizeof(unsigned long long) * ((size_t)max_images + 1)));
+#undef PCKC
+    *out = c;
+    return RIG_OK;
+}
+
+void rig_png_destroy(rig_png_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_tables); cudaFree(c->d_pieces); cudaFree(c->d_scratch); cudaFree(c->d_out); cudaFree(c->d_sizes); cudaFree(c->d_offsets);
+    cudaFree(c->d_counters);
+    cudaFreeHost(c->h_offsets);
+    if (c->ev_in) cudaEventDestroy(c->ev_in);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int rig_png_encode(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, uint8_t *out, size_t out_capacity, uint64_t *offsets_host,
+                   int out_is_device, void *stream)
+{
+    if (!c) return RIG_E_INVALID;
+    if (n < 0 || !offsets_host || (n && (!imgs_dev || !out))) return pfail(c, RIG_E_INVALID, "bad arguments to rig_png_encode");
+    if (n > c->max_images) return pfail(c, RIG_E_CAPACITY, "%d images > max_images %d", n, c->max_images);
+    if (layout != RIG_LAYOUT_RGB && layout != RIG_LAYOUT_BGR) return pfail(c, RIG_E_INVALID, "bad layout %d", layout);
+    if (((uintptr_t)imgs_dev) % 16) return pfail(c, RIG_E_INVALID, "imgs_dev must be 16-byte aligned");
+    offsets_host[0] = 0;
+    if (n == 0) return RIG_OK;
+    PCK(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    // order the encoder after the stream the images were rendered on
+    PCK(c, cudaEventRecord(c->ev_in, (cudaStream_t)stream));
+    PCK(c, cudaStreamWaitEvent(st, c->ev_in, 0));
+    PCK(c, cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), st));
+    if (c->profiling) PCK(c, cudaEventRecord(c->ev0, st));
+    PngParams P;
+    P.imgs = imgs_dev; P.n = n; P.W = c->W; P.H = c->H; P.bgr = layout == RIG_LAYOUT_BGR;
+    P.pieces_per_image = c->ppi; P.pieces = c->d_pieces; P.scratch = c->d_scratch;
+    P.over_begin = c->over_begin; P.over_cap = c->scratch_bytes - c->over_begin; P.counters = c->d_counters;
+    const unsigned long long npieces = (unsigned long long)n * c->ppi;
+    k_png_pieces<<<(unsigned)((npieces + c->wpc - 1) / c->wpc), c->wpc * 32, c->smem, st>>>(P);
+    k_png_sizes<<<(n + 7) / 8, 256, 0, st>>>(c->d_pieces, n, c->ppi, c->d_sizes);
+    k_png_scan<<<1, 1024, 0, st>>>(c->d_sizes, n, c->d_offsets);
+    c->stats.kernel_launches += 3;
+    PCK(c, cudaGetLastError());
+    PCK(c, cudaMemcpyAsync(c->h_offsets, c->d_offsets, sizeof(unsigned long long) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
+    unsigned long long h_counters[2] = {0, 0};
+    PCK(c, cudaMemcpyAsync(h_counters, c->d_counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
+    PCK(c, cudaStreamSynchronize(st));
+    if (h_counters[1]) return pfail(c, RIG_E_CAPACITY, "the images are too incompressible for the piece scratch area (%d images); encode fewer per call", n);
+    const unsigned long long total = c->h_offsets[n];
+    if (total > out_capacity) return pfail(c, RIG_E_CAPACITY, "the PNG files need %llu bytes, out_capacity is %zu", total, out_capacity);
+    uint8_t *dev_out = out;
+    if (!out_is_device) {
+        if (c->out_cap < total) {
+            if (c->d_out) PCK(c, cudaFree(c->d_out));
+            c->d_out = nullptr;
+            const size_t want = (size_t)(total + total / 2 + (1u << 20));
+            PCK(c, cudaMalloc(&c->d_out, want));
+            c->out_cap = want;
+        }
+        dev_out = c->d_out;
+    }
+    PngAssembleParams A;
+    A.pieces = c->d_pieces; A.scratch = c->d_scratch; A.offsets = c->d_offsets; A.tables = c->d_tables; A.out = dev_out;
+    A.n = n; A.W = c->W; A.H = c->H; A.pieces_per_image = c->ppi;
+    k_png_assemble<<<(n + 7) / 8, 256, 0, st>>>(A);
+    c->stats.kernel_launches++;
+    PCK(c, cudaGetLastError());
+    if (c->profiling) PCK(c, cudaEventRecord(c->ev1, st));
+    if (!out_is_device) PCK(c, cudaMemcpyAsync(out, dev_out, total, cudaMemcpyDeviceToHost, st));
+    PCK(c, cudaStreamSynchronize(st));
+    if (c->profiling) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) {
+            c->stats.encode_ms += ms;
+            c->stats.timed_images += (uint64_t)n;
+        }
+    }
+    for (int i = 0; i <= n; i++) offsets_host[i] = c->h_offsets[i];
+    c->stats.images += (uint64_t)n;
+    c->stats.png_bytes += total;
+    return RIG_OK;
+}
+
+int rig_png_get_stats(rig_png_ctx *c, rig_png_stats *out)
+{
+    if (!c || !out) return RIG_E_INVALID;
+    *out = c->stats;
+    return RIG_OK;
+}
+
+int rig_png_set_profiling(rig_png_ctx *c, int on)
+{
+    if (!c) return RIG_E_INVALID;
+    c->profiling = on != 0;
+    if (on) { c->stats.encode_ms = 0; c->stats.timed_images = 0; }
+    return RIG_OK;
+}
+
+}  // extern "C"

