@@ -139,8 +139,22 @@ struct PngParams {
     unsigned long long *counters;   // [0] overflow arena cursor, [1] error flag
 };
 
-// shared memory per warp: bit buffer + 32 x 48 filtered bytes
-__host__ __device__ inline size_t png_warp_smem(int W) { return png_piece_buf_bytes(W) + 32 * PNG_CHUNK; }
+// shared memory per warp: bit buffer + 32 x 48 filtered bytes + the bits of an all-white row
+__host__ __device__ inline size_t png_warp_smem(int W) { return png_piece_buf_bytes(W) + 32 * PNG_CHUNK + 32; }
+
+// ORs the nbits bits that start at bit src_start of src into dst at bit dst_pos (dst is zero there); lanes share the words
+__device__ __forceinline__ void png_copy_bits(uint32_t *dst, uint32_t dst_pos, const uint32_t *src, uint32_t src_start, uint32_t nbits, int lane)
+{
+    for (uint32_t o = (uint32_t)lane * 32u; o < nbits; o += 1024u) {
+        const uint32_t sp = src_start + o, sw = sp >> 5, ss = sp & 31u;
+        uint32_t v = __funnelshift_r(src[sw], src[sw + 1], ss);           // 32 source bits from bit sp
+        const uint32_t left = nbits - o;
+        if (left < 32u) v &= (1u << left) - 1u;
+        const uint32_t dp = dst_pos + o, dw = dp >> 5, ds = dp & 31u;
+        atomicOr(dst + dw, v << ds);
+        if (ds) atomicOr(dst + dw + 1, v >> (32u - ds));
+    }
+}
 
 __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
 {
@@ -149,163 +163,221 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
     const size_t per_warp = png_warp_smem(P.W);
     uint32_t *buf = (uint32_t *)(smem + (size_t)warp * per_warp);
     uint8_t *fbytes = (uint8_t *)buf + png_piece_buf_bytes(P.W) + lane * PNG_CHUNK;
-    const unsigned long long gp = (unsigned long long)blockIdx.x * wpc + warp;
-    if (gp >= (unsigned long long)P.n * P.pieces_per_image) return;
-    const uint32_t image = (uint32_t)(gp / P.pieces_per_image), piece = (uint32_t)(gp % P.pieces_per_image);
-    const int y0 = (int)piece * PNG_ROWS, y1 = min(P.H, y0 + PNG_ROWS);
+    uint32_t *wrow = (uint32_t *)((uint8_t *)buf + png_piece_buf_bytes(P.W) + 32 * PNG_CHUNK);
     const int row_bytes = 3 * P.W, chunks = P.W / 16;
-    const uint32_t RL = 1u + (uint32_t)row_bytes, L = (uint32_t)(y1 - y0) * RL;     // uncompressed bytes per row / in this piece
+    const uint32_t RL = 1u + (uint32_t)row_bytes;
     const uint32_t buf_words = (uint32_t)(png_piece_buf_bytes(P.W) / 4);
+    const bool one_pass = chunks <= 32;        // rows of up to 512 pixels: a row that repeats the row above copies its bits
+    // the bits of an all-white row (what most rows of this data set are): the virtual "row above" of every piece
+    uint32_t white_bits = 0;
+    if (lane < 8) wrow[lane] = 0u;
     for (uint32_t i = lane; i < buf_words; i += 32) buf[i] = 0u;
     __syncwarp();
-    uint32_t bitpos = 3;
-    if (lane == 0) buf[0] = 2u;          // BFINAL = 0, BTYPE = 01 (fixed Huffman), LSB first
-    unsigned long long ad_a = 0, ad_b = 0;
-    const uint8_t *img = P.imgs + (size_t)image * P.H * row_bytes;
-    for (int y = y0; y < y1; y++) {
-        const uint32_t row_pos = (uint32_t)(y - y0) * RL;        // position of the row's filter byte in the piece
-        if (lane == 0) { ad_a += 1u; ad_b += (unsigned long long)(L - row_pos); }
-        uint32_t pass_prev = 0u;           // last word of the previous pass's last chunk (rows wider than 512 pixels)
-        for (int c0 = 0; c0 < chunks; c0 += 32) {
-            const int c = c0 + lane;
-            const bool live = c < chunks;
-            uint32_t w[12];
+    if (one_pass) {
+        if (lane == 0) {
+            PngEmit em;
+            em.buf = wrow;
+            em.pos = 0;
+            uint32_t code;
+            int nb;
+            em.put(png_rev(0x30u + 1u, 8), 8);
+            png_literal(255u, code, nb);
+            em.put(code, nb); em.put(code, nb); em.put(code, nb);
+            em.put(png_rev(0x30u, 8), 8);
+            png_zero_matches(em, (uint32_t)row_bytes - 4u);
+            white_bits = em.pos;
+        }
+        white_bits = __shfl_sync(0xffffffffu, white_bits, 0);
+    }
+    __syncwarp();
+    const unsigned long long total_pieces = (unsigned long long)P.n * P.pieces_per_image;
+    uint32_t used_words = 0;                   // words of buf the previous piece dirtied
+    for (unsigned long long gp = (unsigned long long)blockIdx.x * wpc + warp; gp < total_pieces; gp += (unsigned long long)gridDim.x * wpc) {
+        const uint32_t image = (uint32_t)(gp / P.pieces_per_image), piece = (uint32_t)(gp % P.pieces_per_image);
+        const int y0 = (int)piece * PNG_ROWS, y1 = min(P.H, y0 + PNG_ROWS);
+        const uint32_t L = (uint32_t)(y1 - y0) * RL;              // uncompressed bytes in this piece
+        for (uint32_t i = lane; i < used_words; i += 32) buf[i] = 0u;
+        __syncwarp();
+        uint32_t bitpos = 3;
+        if (lane == 0) buf[0] = 2u;          // BFINAL = 0, BTYPE = 01 (fixed Huffman), LSB first
+        unsigned long long ad_a = 0, ad_b = 0;
+        const uint8_t *img = P.imgs + (size_t)image * P.H * row_bytes;
+        // the row above, as this lane saw it: raw words, Adler sums of its filtered chunk, where its bits are
+        uint32_t pw[12];
 #pragma unroll
-            for (int i = 0; i < 12; i++) w[i] = 0u;
-            if (live) {
-                const uint4 *src = (const uint4 *)(img + (size_t)y * row_bytes + (size_t)c * PNG_CHUNK);
-                const uint4 a = __ldg(src), b = __ldg(src + 1), d = __ldg(src + 2);
-                w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-                w[8] = d.x; w[9] = d.y; w[10] = d.z; w[11] = d.w;
-                if (P.bgr) {
+        for (int i = 0; i < 12; i++) pw[i] = 0xffffffffu;
+        uint32_t p_s0 = lane == 0 ? 765u : 0u, p_s1 = lane == 0 ? 765u : 0u;
+        const uint32_t *p_src = wrow;
+        uint32_t p_start = 0, p_bits = white_bits;
+        for (int y = y0; y < y1; y++) {
+            const uint32_t row_pos = (uint32_t)(y - y0) * RL;        // position of the row's filter byte in the piece
+            if (lane == 0) { ad_a += 1u; ad_b += (unsigned long long)(L - row_pos); }
+            uint32_t pass_prev = 0u;           // last word of the previous pass's last chunk (rows wider than 512 pixels)
+            const uint32_t row_start = bitpos;
+            for (int c0 = 0; c0 < chunks; c0 += 32) {
+                const int c = c0 + lane;
+                const bool live = c < chunks;
+                uint32_t w[12];
 #pragma unroll
-                    for (int g = 0; g < 12; g += 3) {
-                        const uint32_t t = __byte_perm(w[g], w[g + 2], 0x0043);
-                        const uint32_t o0 = __byte_perm(w[g], w[g + 1], 0x5012), o1 = __byte_perm(w[g + 1], t, 0x3540),
-                                       o2 = __byte_perm(w[g + 1], w[g + 2], 0x5672);
-                        w[g] = o0; w[g + 1] = o1; w[g + 2] = o2;
+                for (int i = 0; i < 12; i++) w[i] = 0xffffffffu;
+                if (live) {
+                    const uint4 *src = (const uint4 *)(img + (size_t)y * row_bytes + (size_t)c * PNG_CHUNK);
+                    const uint4 a = __ldg(src), b = __ldg(src + 1), d = __ldg(src + 2);
+                    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+                    w[8] = d.x; w[9] = d.y; w[10] = d.z; w[11] = d.w;
+                    if (P.bgr) {
+#pragma unroll
+                        for (int g = 0; g < 12; g += 3) {
+                            const uint32_t t = __byte_perm(w[g], w[g + 2], 0x0043);
+                            const uint32_t o0 = __byte_perm(w[g], w[g + 1], 0x5012), o1 = __byte_perm(w[g + 1], t, 0x3540),
+                                           o2 = __byte_perm(w[g + 1], w[g + 2], 0x5672);
+                            w[g] = o0; w[g + 1] = o1; w[g + 2] = o2;
+                        }
                     }
                 }
-            }
-            // Sub filter: byte i minus byte i - 3 (the row's first pixel keeps its value)
-            uint32_t prev = __shfl_up_sync(0xffffffffu, w[11], 1);
-            if (lane == 0) prev = pass_prev;   // 0 at the start of the row: the first pixel keeps its value
-            pass_prev = __shfl_sync(0xffffffffu, w[11], 31);
-            uint32_t f[12];
-            uint32_t any = 0u;
+                const uint32_t base = row_pos + 1u + (uint32_t)c * PNG_CHUNK;
+                if (one_pass) {
+                    uint32_t diff = 0u;
 #pragma unroll
-            for (int i = 0; i < 12; i++) {
-                const uint32_t left = __funnelshift_r(i ? w[i - 1] : prev, w[i], 8);
-                f[i] = __vsub4(w[i], left);
-                any |= f[i];
-            }
-            // zero structure of the chunk
-            unsigned long long nz = 0ull;
-            if (any && live) {                                  // (a dead lane's chunk is all zeros but its left neighbour is not)
+                    for (int i = 0; i < 12; i++) diff |= w[i] ^ pw[i];
+                    if (__all_sync(0xffffffffu, diff == 0u)) {       // same row as the one above: same filtered bytes, same bits
+                        png_copy_bits(buf, bitpos, p_src, p_start, p_bits, lane);
+                        ad_a += p_s0;
+                        ad_b += (unsigned long long)(L - base) * p_s0 - p_s1;
+                        p_src = buf;
+                        p_start = bitpos;
+                        bitpos += p_bits;
+                        __syncwarp();
+                        continue;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 12; i++) pw[i] = w[i];
+                }
+                // Sub filter: byte i minus byte i - 3 (the row's first pixel keeps its value)
+                uint32_t prev = __shfl_up_sync(0xffffffffu, w[11], 1);
+                if (lane == 0) prev = pass_prev;   // 0 at the start of the row: the first pixel keeps its value
+                pass_prev = __shfl_sync(0xffffffffu, w[11], 31);
+                uint32_t f[12];
+                uint32_t any = 0u;
 #pragma unroll
                 for (int i = 0; i < 12; i++) {
-                    const uint32_t m = __vsetne4(f[i], 0u);       // 1 per non-zero byte
-                    const uint32_t nib = (m & 1u) | ((m >> 7) & 2u) | ((m >> 14) & 4u) | ((m >> 21) & 8u);
-                    nz |= (unsigned long long)nib << (4 * i);
+                    const uint32_t left = __funnelshift_r(i ? w[i - 1] : prev, w[i], 8);
+                    f[i] = __vsub4(w[i], left);
+                    any |= f[i];
                 }
-                uint4 *dst = (uint4 *)fbytes;
-                dst[0] = make_uint4(f[0], f[1], f[2], f[3]);
-                dst[1] = make_uint4(f[4], f[5], f[6], f[7]);
-                dst[2] = make_uint4(f[8], f[9], f[10], f[11]);
-                // Adler partial sums of this chunk
-                unsigned long long m = nz;
+                // zero structure of the chunk
+                unsigned long long nz = 0ull;
                 uint32_t s0 = 0, s1 = 0;
-                while (m) {
-                    const int i = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    const uint32_t v = fbytes[i];
-                    s0 += v;
-                    s1 += v * (uint32_t)i;
-                }
-                const uint32_t base = row_pos + 1u + (uint32_t)c * PNG_CHUNK;
-                ad_a += s0;
-                ad_b += (unsigned long long)(L - base) * s0 - s1;
-            }
-            const int lead = live ? (nz ? (__ffsll((long long)nz) - 1) : PNG_CHUNK) : 0;      // leading zeros
-            const bool all_zero = live && nz == 0ull;
-            const bool last_zero = live && !((nz >> (PNG_CHUNK - 1)) & 1ull);
-            const uint32_t zmask = __ballot_sync(0xffffffffu, all_zero);
-            const uint32_t prev_last_zero = __shfl_up_sync(0xffffffffu, (uint32_t)last_zero, 1);
-            const int skip = (lane > 0 && prev_last_zero) ? lead : 0;
-            // zeros that continue this chunk's trailing run: the all-zero lanes after it and the next lane's leading zeros
-            uint32_t tail_extra = 0;
-            {
-                const uint32_t after = lane == 31 ? 0u : (zmask >> (lane + 1));
-                const int run = lane == 31 ? 0 : (__ffs((int)~after) - 1);          // consecutive all-zero lanes (~after has a set bit: lanes >= 32 - lane - 1 read 0)
-                const int nxt = lane + 1 + run;
-                const int nxt_lead = __shfl_sync(0xffffffffu, lead, nxt & 31);
-                tail_extra = (uint32_t)run * PNG_CHUNK + ((nxt < 32) ? (uint32_t)nxt_lead : 0u);
-            }
-            __syncwarp();
-            const bool mine = live && skip < PNG_CHUNK;          // a fully skipped chunk emits nothing
-            const bool fbyte = lane == 0 && c0 == 0;
-            PngCount cnt;
-            if (mine || fbyte) png_chunk_tokens(cnt, nz, fbytes, mine ? skip : PNG_CHUNK, tail_extra, fbyte);
-            uint32_t incl = cnt.bits;
+                if (any && live) {                                  // (a dead lane's chunk is all zeros but its left neighbour is not)
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
+                    for (int i = 0; i < 12; i++) {
+                        const uint32_t m = __vsetne4(f[i], 0u);       // 1 per non-zero byte
+                        const uint32_t nib = (m & 1u) | ((m >> 7) & 2u) | ((m >> 14) & 4u) | ((m >> 21) & 8u);
+                        nz |= (unsigned long long)nib << (4 * i);
+                    }
+                    uint4 *dst = (uint4 *)fbytes;
+                    dst[0] = make_uint4(f[0], f[1], f[2], f[3]);
+                    dst[1] = make_uint4(f[4], f[5], f[6], f[7]);
+                    dst[2] = make_uint4(f[8], f[9], f[10], f[11]);
+                    // Adler partial sums of this chunk
+                    unsigned long long m = nz;
+                    while (m) {
+                        const int i = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const uint32_t v = fbytes[i];
+                        s0 += v;
+                        s1 += v * (uint32_t)i;
+                    }
+                    ad_a += s0;
+                    ad_b += (unsigned long long)(L - base) * s0 - s1;
+                }
+                p_s0 = s0; p_s1 = s1;
+                const int lead = live ? (nz ? (__ffsll((long long)nz) - 1) : PNG_CHUNK) : 0;      // leading zeros
+                const bool all_zero = live && nz == 0ull;
+                const bool last_zero = live && !((nz >> (PNG_CHUNK - 1)) & 1ull);
+                const uint32_t zmask = __ballot_sync(0xffffffffu, all_zero);
+                const uint32_t prev_last_zero = __shfl_up_sync(0xffffffffu, (uint32_t)last_zero, 1);
+                const int skip = (lane > 0 && prev_last_zero) ? lead : 0;
+                // zeros that continue this chunk's trailing run: the all-zero lanes after it and the next lane's leading zeros
+                uint32_t tail_extra = 0;
+                {
+                    const uint32_t after = lane == 31 ? 0u : (zmask >> (lane + 1));
+                    const int run = lane == 31 ? 0 : (__ffs((int)~after) - 1);          // consecutive all-zero lanes that follow
+                    const int nxt = lane + 1 + run;
+                    const int nxt_lead = __shfl_sync(0xffffffffu, lead, nxt & 31);
+                    tail_extra = (uint32_t)run * PNG_CHUNK + ((nxt < 32) ? (uint32_t)nxt_lead : 0u);
+                }
+                __syncwarp();
+                const bool mine = live && skip < PNG_CHUNK;          // a fully skipped chunk emits nothing
+                const bool fbyte = lane == 0 && c0 == 0;
+                PngCount cnt;
+                if (mine || fbyte) png_chunk_tokens(cnt, nz, fbytes, mine ? skip : PNG_CHUNK, tail_extra, fbyte);
+                uint32_t incl = cnt.bits;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                PngEmit em;
+                em.buf = buf;
+                em.pos = bitpos + incl - cnt.bits;
+                if (mine || fbyte) png_chunk_tokens(em, nz, fbytes, mine ? skip : PNG_CHUNK, tail_extra, fbyte);
+                bitpos += __shfl_sync(0xffffffffu, incl, 31);
+                __syncwarp();
             }
+            if (one_pass && p_start != row_start) {    // (a copied row has already moved the reference to itself)
+                p_src = buf;
+                p_start = row_start;
+                p_bits = bitpos - row_start;
+            } else if (one_pass) {
+                p_bits = bitpos - row_start;
+            }
+        }
+        // end of block (7 zero bits), empty stored block (3 zero bits, pad to a byte, 00 00 FF FF)
+        bitpos += 10;
+        bitpos = (bitpos + 7u) & ~7u;
+        __syncwarp();
+        if (lane == 0) {
             PngEmit em;
             em.buf = buf;
-            em.pos = bitpos + incl - cnt.bits;
-            if (mine || fbyte) png_chunk_tokens(em, nz, fbytes, mine ? skip : PNG_CHUNK, tail_extra, fbyte);
-            bitpos += __shfl_sync(0xffffffffu, incl, 31);
-            __syncwarp();
+            em.pos = bitpos + 16;
+            em.put(0xffffu, 16);
         }
-    }
-    // end of block (7 zero bits), empty stored block (3 zero bits, pad to a byte, 00 00 FF FF)
-    bitpos += 10;
-    bitpos = (bitpos + 7u) & ~7u;
-    __syncwarp();
-    if (lane == 0) {
-        PngEmit em;
-        em.buf = buf;
-        em.pos = bitpos + 16;
-        em.put(0xffffu, 16);
-    }
-    const uint32_t nbytes = bitpos / 8 + 4;
-    // Adler partial sums of the piece
+        const uint32_t nbytes = bitpos / 8 + 4;
+        used_words = (nbytes + 3u) / 4u + 2u;
+        // Adler partial sums of the piece
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        ad_a += __shfl_xor_sync(0xffffffffu, ad_a, o);
-        ad_b += __shfl_xor_sync(0xffffffffu, ad_b, o);
-    }
-    unsigned long long where = gp * PNG_SLOT;
-    if (nbytes > PNG_SLOT) {
-        unsigned long long off = 0;
-        if (lane == 0) off = atomicAdd(P.counters, (unsigned long long)((nbytes + 15u) & ~15u));
-        off = __shfl_sync(0xffffffffu, off, 0);
-        if (off + nbytes > P.over_cap) {
-            if (lane == 0) {
-                atomicExch(P.counters + 1, 1ull);
-                PngPiece pc;
-                pc.nbytes = 0; pc.where = 0; pc.a = 0; pc.b = 0;
-                P.pieces[gp] = pc;
-            }
-            return;
+        for (int o = 16; o; o >>= 1) {
+            ad_a += __shfl_xor_sync(0xffffffffu, ad_a, o);
+            ad_b += __shfl_xor_sync(0xffffffffu, ad_b, o);
         }
-        where = P.over_begin + off;
-    }
-    __syncwarp();
-    {
-        uint4 *dst = (uint4 *)(P.scratch + where);
-        const uint4 *src = (const uint4 *)buf;
-        for (uint32_t i = lane; i < (nbytes + 15u) / 16u; i += 32) dst[i] = src[i];
-    }
-    if (lane == 0) {
-        PngPiece pc;
-        pc.nbytes = nbytes;
-        pc.where = (uint32_t)(where / 16);      // scratch offsets are multiples of 16
-        pc.a = (uint32_t)(ad_a % ADLER_MOD);
-        pc.b = (uint32_t)(ad_b % ADLER_MOD);
-        P.pieces[gp] = pc;
+        unsigned long long where = gp * PNG_SLOT;
+        bool failed = false;
+        if (nbytes > PNG_SLOT) {
+            unsigned long long off = 0;
+            if (lane == 0) off = atomicAdd(P.counters, (unsigned long long)((nbytes + 15u) & ~15u));
+            off = __shfl_sync(0xffffffffu, off, 0);
+            if (off + nbytes > P.over_cap) {
+                failed = true;
+                if (lane == 0) atomicExch(P.counters + 1, 1ull);
+            }
+            where = P.over_begin + off;
+        }
+        __syncwarp();
+        if (!failed) {
+            uint4 *dst = (uint4 *)(P.scratch + where);
+            const uint4 *src = (const uint4 *)buf;
+            for (uint32_t i = lane; i < (nbytes + 15u) / 16u; i += 32) dst[i] = src[i];
+        }
+        if (lane == 0) {
+            PngPiece pc;
+            pc.nbytes = failed ? 0u : nbytes;
+            pc.where = failed ? 0u : (uint32_t)(where / 16);      // scratch offsets are multiples of 16
+            pc.a = (uint32_t)(ad_a % ADLER_MOD);
+            pc.b = (uint32_t)(ad_b % ADLER_MOD);
+            P.pieces[gp] = pc;
+        }
+        __syncwarp();
     }
 }
 

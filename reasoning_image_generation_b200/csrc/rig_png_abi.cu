@@ -30,14 +30,14 @@ uint32_t host_multmodp(uint32_t a, uint32_t b)
 struct rig_png_ctx {
     int device = 0, W = 0, H = 0, max_images = 0;
     uint32_t ppi = 0;
-    int wpc = 4;
+    int wpc = 4, sm_count = 1, ctas_per_sm = 1;
     size_t smem = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev0 = nullptr, ev1 = nullptr;
     PngTables *d_tables = nullptr;
     PngPiece *d_pieces = nullptr;
-    uint8_t *d_scratch = nullptr, *d_out = nullptr;
-    size_t scratch_bytes = 0, over_begin = 0, out_cap = 0;
+    uint8_t *d_scratch = nullptr, *d_out = nullptr, *d_stage = nullptr;
+    size_t scratch_bytes = 0, over_begin = 0, out_cap = 0, stage_cap = 0;
     unsigned long long *d_sizes = nullptr, *d_offsets = nullptr, *d_counters = nullptr;
     unsigned long long *h_offsets = nullptr;     // pinned
     rig_png_stats stats = {};
@@ -109,6 +109,8 @@ int rig_png_create(int device, int W, int H, int max_images, rig_png_ctx **out)
     c->wpc = 8;
     while (c->wpc > 1 && c->wpc * png_warp_smem(W) > 96 * 1024) c->wpc--;
     c->smem = c->wpc * png_warp_smem(W);
+    c->sm_count = prop.multiProcessorCount;
+    c->ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (c->wpc * 32), (prop.sharedMemPerMultiprocessor - 2048) / (c->smem + 1024)));
     if (c->smem > prop.sharedMemPerBlockOptin) {
         pfail(c, RIG_E_UNSUPPORTED, "image width %d needs %zu B of shared memory per piece", W, c->smem);
         return bail(RIG_E_UNSUPPORTED);
@@ -162,7 +164,7 @@ void rig_png_destroy(rig_png_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tables); cudaFree(c->d_pieces); cudaFree(c->d_scratch); cudaFree(c->d_out); cudaFree(c->d_sizes); cudaFree(c->d_offsets);
-    cudaFree(c->d_counters);
+    cudaFree(c->d_counters); cudaFree(c->d_stage);
     cudaFreeHost(c->h_offsets);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -193,7 +195,12 @@ int rig_png_encode(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, u
     P.pieces_per_image = c->ppi; P.pieces = c->d_pieces; P.scratch = c->d_scratch;
     P.over_begin = c->over_begin; P.over_cap = c->scratch_bytes - c->over_begin; P.counters = c->d_counters;
     const unsigned long long npieces = (unsigned long long)n * c->ppi;
-    k_png_pieces<<<(unsigned)((npieces + c->wpc - 1) / c->wpc), c->wpc * 32, c->smem, st>>>(P);
+    {
+        // persistent warps: every warp prepares the bits of a white row once, then walks pieces with a grid stride
+        const unsigned long long want = (npieces + c->wpc - 1) / c->wpc;
+        const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)c->sm_count * c->ctas_per_sm);
+        k_png_pieces<<<grid, c->wpc * 32, c->smem, st>>>(P);
+    }
     k_png_sizes<<<(n + 7) / 8, 256, 0, st>>>(c->d_pieces, n, c->ppi, c->d_sizes);
     k_png_scan<<<1, 1024, 0, st>>>(c->d_sizes, n, c->d_offsets);
     c->stats.kernel_launches += 3;
@@ -235,6 +242,22 @@ int rig_png_encode(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, u
     for (int i = 0; i <= n; i++) offsets_host[i] = c->h_offsets[i];
     c->stats.images += (uint64_t)n;
     c->stats.png_bytes += total;
+    return RIG_OK;
+}
+
+int rig_png_staging(rig_png_ctx *c, int n, uint8_t **out_dev)
+{
+    if (!c || !out_dev || n < 0) return RIG_E_INVALID;
+    PCK(c, cudaSetDevice(c->device));
+    const size_t need = (size_t)std::max(n, 1) * c->W * c->H * 3;
+    if (c->stage_cap < need) {
+        PCK(c, cudaDeviceSynchronize());
+        if (c->d_stage) PCK(c, cudaFree(c->d_stage));
+        c->d_stage = nullptr;
+        PCK(c, cudaMalloc(&c->d_stage, need));
+        c->stage_cap = need;
+    }
+    *out_dev = c->d_stage;
     return RIG_OK;
 }
 

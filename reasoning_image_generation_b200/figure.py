@@ -293,6 +293,51 @@ class FigureRenderer:
         with self._lock:
             self._check(self._lib.rig_figure_render_batch(self._h, ctypes.byref(s), out_ptr, 1, _LAYOUTS[layout], stream or None))
 
+    def iter_png(self, scene: FigureScene, encoder, chunk: int = 4096, overlap: bool = True):
+        """``fig.savefig`` for a whole batch (multigraph_generation/generator.py:256): renders `chunk` figures at a time into
+        the encoder's device staging buffer and encodes them there, so only PNG bytes cross PCIe.  Yields
+        (first_image_index, buffer, offsets): file i of the chunk is buffer[offsets[i]:offsets[i + 1]] (pinned host memory,
+        valid until the next iteration).  With `overlap` the host path pipeline + rendering of chunk k + 1 run on a worker
+        thread while chunk k is encoded and copied (two halves of the staging buffer)."""
+        self._check_scene(scene)
+        chunk = max(1, min(int(chunk), encoder.max_images, self.max_images))
+        starts = list(range(0, scene.n_images, chunk))
+        if not starts:
+            return
+        img_bytes = self.W * self.H * 3
+        base = encoder.staging(2 * chunk if (overlap and len(starts) > 1) else chunk)
+
+        def sub_scene(i0):
+            return scene if (i0 == 0 and scene.n_images <= chunk) else scene.slice(i0, min(scene.n_images, i0 + chunk))
+
+        def render(k, box):
+            try:
+                sub = sub_scene(starts[k])
+                ptr = base + (k & 1) * chunk * img_bytes if (overlap and len(starts) > 1) else base
+                self.render_to_device(sub, ptr, 'rgb', 0)
+                self.sync()              # rendered on the context's own stream: finish before the encoder reads
+                box.append((sub.n_images, ptr))
+            except BaseException as e:   # re-raised on the consumer's thread
+                box.append(e)
+
+        box: list = []
+        render(0, box)
+        for k, i0 in enumerate(starts):
+            cur = box[0]
+            if isinstance(cur, BaseException):
+                raise cur
+            box, worker = [], None
+            if k + 1 < len(starts):
+                if overlap:
+                    worker = threading.Thread(target=render, args=(k + 1, box))
+                    worker.start()
+            buf, off = encoder.encode(cur[1], cur[0], 'rgb', 0)
+            if worker is not None:
+                worker.join()
+            yield i0, buf, off
+            if k + 1 < len(starts) and not overlap:
+                render(k + 1, box)
+
     def upload(self, scene: FigureScene, layout: str = 'rgb', stream: int = 0):
         self._check_scene(scene)
         s = scene.as_struct()

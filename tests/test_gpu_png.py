@@ -109,3 +109,25 @@ def test_empty_batch_and_capacity(built):
     with pytest.raises(ValueError):
         enc.encode(noise.data_ptr(), 5)
     enc.close()
+
+
+def test_iter_png_is_savefig_for_a_batch(built):
+    """FigureRenderer.iter_png: render + encode chunk by chunk on the device; the files decode to the oracle's pixels."""
+    import cv2
+    from oracle.agg_oracle import AggOracle
+    from reasoning_image_generation_b200.figure import FigureRenderer
+    from reasoning_image_generation_b200.png import PngEncoder
+    from reasoning_image_generation_b200.synth_figure import synthetic_figure_scene
+    sc = synthetic_figure_scene(50, 256, 256, seed=12, kind='multi')
+    ref = AggOracle().render(sc, 256, 256)
+    r = FigureRenderer(256, 256, max_images=16)
+    enc = PngEncoder(256, 256, max_images=16)
+    seen = 0
+    for i0, buf, off in r.iter_png(sc, enc, chunk=16):
+        for k in range(len(off) - 1):
+            img = cv2.imdecode(np.asarray(buf[int(off[k]):int(off[k + 1])]), cv2.IMREAD_UNCHANGED)
+            assert (img[:, :, ::-1] == ref[i0 + k]).all()
+            seen += 1
+    assert seen == 50
+    r.close()
+    enc.close()
