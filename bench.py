@@ -35,7 +35,8 @@ PANELS_PER_STEP = 16384        # 12.9 GB of pixels per step per GPU: far larger 
 E2E_PANELS = 4096              # 3.2 GB pinned host destination per e2e step
 DEDUP_N = 1 << 20              # hashes in the all-pairs timing input (5.5e11 pairs)
 FIG_PER_STEP = 32768           # 25.8 GB of pixels per step per GPU
-FIG_E2E = 4096
+FIG_E2E = 16384               # images per e2e step ...
+FIG_E2E_CHUNK = 4096          # ... rendered + encoded 4096 at a time
 FIG_METRIC = 'rendered images/sec at 512x512 (multigraph single-shape variants)'
 FIG_WORKLOAD = ('BASELINE configs[1]: multigraph single-shape variants, synthetic (SURVEY 8d: one outlined base patch -- circle / '
                 'ellipse / rectangle / rounded box / regular polygon / wedge, 1.5-2.0 pt, alpha 0.9 -- plus 1-6 internal lines or 1-3 '
@@ -147,11 +148,24 @@ def _fig_cpu_worker(args):
     from reasoning_image_generation_b200.synth_figure import synthetic_figure_scene
     sc = synthetic_figure_scene(i1 - i0, 512, 512, seed=seed, kind='single', first=i0)
     o = AggOracle()
-    t = time.time()
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+    except Exception:
+        cv2 = None
+    t_render = t_png = 0.0
     acc = 0
     for i in range(sc.n_images):
-        acc += int(o.render_rgba(sc, i, 512, 512)[0, 0, 0])
-    return i1 - i0, time.time() - t, 'aggdraw.c'
+        t = time.time()
+        img = o.render_rgba(sc, i, 512, 512)
+        t_render += time.time() - t
+        if cv2 is not None:
+            # fig.savefig writes the RGBA canvas as a PNG (generator.py:256); libpng through cv2.imencode, default settings
+            t = time.time()
+            ok, png = cv2.imencode('.png', img)
+            t_png += time.time() - t
+            acc += len(png)
+    return i1 - i0, t_render, t_png, acc
 
 
 def fig_cpu_sample(seed, budget_s=14.0, cores=None):
@@ -159,16 +173,28 @@ def fig_cpu_sample(seed, budget_s=14.0, cores=None):
     (scene emission is outside each worker's own timer but inside the wall clock used for the rate)."""
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
-    per = 96
-    done, render_s = 0, 0.0
+    per = 48
+    done, render_s, total_s, png_bytes = 0, 0.0, 0.0, 0
     t0 = time.time()
     with mp.get_context('fork').Pool(cores) as pool:
-        while time.time() - t0 < budget_s and done + per * cores <= FIG_PER_STEP:
-            jobs = [(seed, done + i * per, done + (i + 1) * per) for i in range(cores)]
+        while time.time() - t0 < budget_s:
+            first = done % FIG_PER_STEP
+            jobs = [(seed, first + i * per, first + (i + 1) * per) for i in range(cores)]
             res = pool.map(_fig_cpu_worker, jobs)
             done += sum(r[0] for r in res)
             render_s += max(r[1] for r in res)
-    return done, render_s, cores, 'aggdraw.c'
+            total_s += max(r[1] + r[2] for r in res)
+            png_bytes += sum(r[3] for r in res)
+    return {'images': done, 'render_s': render_s, 'total_s': total_s, 'cores': cores, 'png_bytes': png_bytes}
+
+
+def fig_cpu_dict(c):
+    return {'value': c['images'] / c['total_s'], 'unit': 'images/s', 'cores': c['cores'], 'kind': 'port',
+            'render_only_value': c['images'] / c['render_s'], 'png_bytes_per_image': c['png_bytes'] / max(1, c['images']),
+            'sample': '%d images of the step scene (seed 1000), one process per core: oracle/aggdraw.c (restated matplotlib/Agg '
+                      'pipeline; matplotlib itself is not installable here) + the PNG encode savefig ends with (libpng via '
+                      'cv2.imencode, RGBA, default settings); value = render + PNG, %.1f s; render_only_value = rasterisation alone, '
+                      '%.1f s; scene emission is outside both' % (c['images'], c['total_s'], c['render_s'])}
 
 
 def run_reference_figure(args):
@@ -179,22 +205,24 @@ def run_reference_figure(args):
     build_agg_oracle()
     steps = max(1, args.steps)
     budget = max(4.0, min(20.0, 90.0 / (steps + args.warmup)))
-    sample, total_s, cores = 0, 0.0, os.cpu_count() or 1
+    tot = None
     for s in range(args.warmup + steps):
-        n, dt, cores, backend = fig_cpu_sample(seed=1000, budget_s=budget)
+        c = fig_cpu_sample(seed=1000, budget_s=budget)
         if s >= args.warmup:
-            sample += n
-            total_s += dt
-    v = sample / total_s
+            if tot is None:
+                tot = c
+            else:
+                for k in ('images', 'render_s', 'total_s', 'png_bytes'):
+                    tot[k] += c[k]
+    cpu = fig_cpu_dict(tot)
+    v = cpu['value']
     line = {
         'impl': 'reference', 'metric': FIG_METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
-        'warmup': args.warmup, 'ms_per_step': 1e3 * total_s / steps, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': args.warmup, 'ms_per_step': 1e3 * tot['total_s'] / steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-        'config': {'workload': FIG_WORKLOAD, 'images_per_step_per_gpu': FIG_PER_STEP},
-        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                         'sample': '%d images of the step (first slices of the seed-1000 scene) per timed step, oracle/aggdraw.c '
-                                   '(restated matplotlib/Agg pipeline; matplotlib itself is not installable here), one process per '
-                                   'core, render time only' % (sample // steps)},
+        'config': {'workload': FIG_WORKLOAD, 'images_per_step_per_gpu': FIG_PER_STEP,
+                   'deliverable': 'PNG files in host memory (what fig.savefig produces), as in the GPU arm\'s e2e'},
+        'cpu_baseline': cpu,
         'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -314,32 +342,61 @@ def figure_leg(env, args, sampler):
     del out
     torch.cuda.empty_cache()
 
-    # ---- e2e: public API, host artist arrays in, pinned host pixels out
+    # ---- e2e (headline): fig.savefig for a batch -- host artist arrays in, PNG files in pinned host memory out
+    from reasoning_image_generation_b200.png import PngEncoder
     from reasoning_image_generation_b200.render import PinnedBuffer
     sub = scene.slice(0, FIG_E2E)
-    pin = PinnedBuffer(FIG_E2E * IMG_BYTES)
-    pinned = pin.array.reshape(FIG_E2E, 512, 512, 3)
+    enc = PngEncoder(512, 512, device=env.local, max_images=FIG_E2E_CHUNK)
+    r2 = FigureRenderer(512, 512, device=env.local, max_images=FIG_E2E_CHUNK, max_artists=max(sub.n_artists, 1))
+    png_bytes = 0
     for _ in range(2):
-        r.render(sub, 'rgb', out=pinned)
+        for i0, buf, off in r2.iter_png(sub, enc, FIG_E2E_CHUNK):
+            pass
     env.barrier()
+    l0 = r2.stats()['kernel_launches'] + enc.stats()['kernel_launches']
     t0 = time.perf_counter()
     e2e_steps = max(2, min(args.steps, 4))
+    digest = 0
     for _ in range(e2e_steps):
-        r.render(sub, 'rgb', out=pinned)
+        for i0, buf, off in r2.iter_png(sub, enc, FIG_E2E_CHUNK):
+            png_bytes += int(off[-1])
+            digest ^= int(buf[int(off[1]) - 16]) if len(off) > 1 else 0
     torch.cuda.synchronize()
     (dt,) = env.max_over_ranks(time.perf_counter() - t0)
-    st2 = r.stats()
+    st2 = r2.stats()
+    e2e_launches = st2['kernel_launches'] + enc.stats()['kernel_launches'] - l0
     e2e_value = env.world * FIG_E2E * e2e_steps / dt
+    h2d = int((16 * st2['edges'] + 32 * st2['layers']) * (FIG_E2E / FIG_E2E_CHUNK) + 8 * (FIG_E2E + 1))
+    enc.close()
+    r2.close()
+    # ---- the same through the raw-pixel API: every pixel copied to pinned host memory (PCIe-bound)
+    pin = PinnedBuffer(FIG_E2E_CHUNK * IMG_BYTES)
+    pinned = pin.array.reshape(FIG_E2E_CHUNK, 512, 512, 3)
+    sub_px = scene.slice(0, FIG_E2E_CHUNK)
+    for _ in range(2):
+        r.render(sub_px, 'rgb', out=pinned)
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r.render(sub_px, 'rgb', out=pinned)
+    torch.cuda.synchronize()
+    (dt_px,) = env.max_over_ranks(time.perf_counter() - t0)
+    px_value = env.world * FIG_E2E_CHUNK * e2e_steps / dt_px
     per_img_edges = stats['edges'] / n
-    h2d = int(16 * st2['edges'] + 32 * st2['layers'] + 4 * (FIG_E2E + 1) + 4 * FIG_E2E)
     checksum = int(pinned[::257, 200:312, 200:312, 0].astype('int64').sum())
     res = {
         'value': value, 'ms_per_step': ms_max / args.steps, 'warmup': n_warm, 'clocks': clocks,
         'launches': stats['kernel_launches'] - launches0, 'stats': stats, 'n': n,
-        'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': FIG_E2E * IMG_BYTES,
-                'images_per_step_per_gpu': FIG_E2E, 'host_prepare_ms_per_step': st2['prepare_ms'],
-                'note': 'FigureRenderer.render: host artist arrays in (path pipeline on host threads, edges uploaded), every pixel '
-                        'copied to pinned host memory (PCIe-bound); checksum %d' % checksum},
+        'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': png_bytes // e2e_steps,
+                'images_per_step_per_gpu': FIG_E2E, 'chunk': FIG_E2E_CHUNK, 'host_prepare_ms_per_chunk': st2['prepare_ms'],
+                'png_bytes_per_image': png_bytes / (e2e_steps * FIG_E2E), 'gpu_launches': e2e_launches,
+                'note': 'FigureRenderer.iter_png = fig.savefig for a batch: host artist arrays in (path pipeline on host threads, '
+                        'edges uploaded), k_figure, device-side PNG encode, finished PNG files copied to pinned host memory; host '
+                        'work of chunk k + 1 overlaps GPU work of chunk k; digest %d' % digest},
+        'e2e_pixels': {'value': px_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d // max(1, FIG_E2E // FIG_E2E_CHUNK),
+                       'd2h_bytes_per_step': FIG_E2E_CHUNK * IMG_BYTES, 'images_per_step_per_gpu': FIG_E2E_CHUNK,
+                       'note': 'FigureRenderer.render: the same with every raw pixel copied to pinned host memory instead of PNG '
+                               'files (PCIe-bound: 786,432 B per image); checksum %d' % checksum},
         'config': {'workload': FIG_WORKLOAD, 'images_per_step_per_gpu': n, 'l2': 'outputs (25.8 GB/step) exceed L2; no flush needed',
                    'artists_per_step_per_gpu': scene.n_artists, 'edges_per_image': per_img_edges,
                    'layers_per_image': stats['layers'] / n, 'out_layout': 'RGB', 'checksum': checksum_dev},
@@ -519,15 +576,12 @@ def run_ours(args):
                     traffic = None
             cpu = None
             if world == 1 and not args.no_cpu:
-                done, cdt, cores, backend = fig_cpu_sample(seed=1000, budget_s=14.0)
-                cpu = {'value': done / cdt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                       'sample': 'first %d images of the step scene (seed 1000), oracle/aggdraw.c (restated matplotlib/Agg pipeline; '
-                                 'matplotlib itself is not installable here), one process per core, %.1f s of rendering' % (done, cdt)}
+                cpu = fig_cpu_dict(fig_cpu_sample(seed=1000, budget_s=14.0))
             line = {
                 'metric': FIG_METRIC, 'value': fig['value'], 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': fig['warmup'], 'ms_per_step': fig['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': fig['config'], 'e2e': fig['e2e'],
-                'gpu_launches': fig['launches'] + (seq['gpu_launches'] if seq else 0),
+                'e2e_pixels': fig['e2e_pixels'], 'gpu_launches': fig['launches'],
                 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                              'traffic': traffic, 'kernel': 'k_figure', 'peak_source': peak_src, 'launches': stats['timed_launches'],
                              'images_per_launch': per_launch, 'figure_ms_per_step': stats['cover_ms'] / args.steps,

@@ -18,7 +18,7 @@
 namespace rig {
 
 #ifndef PNG_PIECE_ROWS
-#define PNG_PIECE_ROWS 4
+#define PNG_PIECE_ROWS 2
 #endif
 constexpr int PNG_ROWS = PNG_PIECE_ROWS;
 constexpr int PNG_CHUNK = 48;                 // bytes per lane per pass = 16 pixels
@@ -76,6 +76,29 @@ __device__ __forceinline__ void png_match(uint32_t len, uint32_t &code, int &nbi
 struct PngCount {
     uint32_t bits = 0;
     __device__ __forceinline__ void put(uint32_t, int n) { bits += (uint32_t)n; }
+};
+// single-walk sink: the lane's bits go to its own staging words; they are moved to the piece buffer once the warp scan has
+// placed them
+constexpr int PNG_STAGE_WORDS = 20;      // >= (48 * 9 + 8 + 8 * 13 + 18 + 31) / 32 bits a chunk can need
+struct PngStage {
+    uint32_t *stage;
+    unsigned long long acc = 0;
+    uint32_t nacc = 0, k = 0;
+    __device__ __forceinline__ void put(uint32_t code, int n)
+    {
+        acc |= (unsigned long long)code << nacc;
+        nacc += (uint32_t)n;
+        if (nacc >= 32u) {
+            stage[k++] = (uint32_t)acc;
+            acc >>= 32;
+            nacc -= 32u;
+        }
+    }
+    __device__ __forceinline__ uint32_t finish()      // flushes the tail, returns the number of bits
+    {
+        stage[k] = (uint32_t)acc;
+        return 32u * k + nacc;
+    }
 };
 struct PngEmit {
     uint32_t *buf;
@@ -140,7 +163,7 @@ struct PngParams {
 };
 
 // shared memory per warp: bit buffer + 32 x 48 filtered bytes + the bits of an all-white row
-__host__ __device__ inline size_t png_warp_smem(int W) { return png_piece_buf_bytes(W) + 32 * PNG_CHUNK + 32; }
+__host__ __device__ inline size_t png_warp_smem(int W) { return png_piece_buf_bytes(W) + 32 * PNG_CHUNK + 32 * 4 * PNG_STAGE_WORDS + 32; }
 
 // ORs the nbits bits that start at bit src_start of src into dst at bit dst_pos (dst is zero there); lanes share the words
 __device__ __forceinline__ void png_copy_bits(uint32_t *dst, uint32_t dst_pos, const uint32_t *src, uint32_t src_start, uint32_t nbits, int lane)
@@ -163,7 +186,8 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
     const size_t per_warp = png_warp_smem(P.W);
     uint32_t *buf = (uint32_t *)(smem + (size_t)warp * per_warp);
     uint8_t *fbytes = (uint8_t *)buf + png_piece_buf_bytes(P.W) + lane * PNG_CHUNK;
-    uint32_t *wrow = (uint32_t *)((uint8_t *)buf + png_piece_buf_bytes(P.W) + 32 * PNG_CHUNK);
+    uint32_t *stage = (uint32_t *)((uint8_t *)buf + png_piece_buf_bytes(P.W) + 32 * PNG_CHUNK) + lane * PNG_STAGE_WORDS;
+    uint32_t *wrow = (uint32_t *)((uint8_t *)buf + png_piece_buf_bytes(P.W) + 32 * PNG_CHUNK + 32 * 4 * PNG_STAGE_WORDS);
     const int row_bytes = 3 * P.W, chunks = P.W / 16;
     const uint32_t RL = 1u + (uint32_t)row_bytes;
     const uint32_t buf_words = (uint32_t)(png_piece_buf_bytes(P.W) / 4);
@@ -310,18 +334,31 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
                 __syncwarp();
                 const bool mine = live && skip < PNG_CHUNK;          // a fully skipped chunk emits nothing
                 const bool fbyte = lane == 0 && c0 == 0;
-                PngCount cnt;
-                if (mine || fbyte) png_chunk_tokens(cnt, nz, fbytes, mine ? skip : PNG_CHUNK, tail_extra, fbyte);
-                uint32_t incl = cnt.bits;
+                // one walk: tokens into the lane's staging words, a warp scan of the bit counts, then a shifted move
+                uint32_t nbits_mine = 0;
+                if (mine || fbyte) {
+                    PngStage sg;
+                    sg.stage = stage;
+                    png_chunk_tokens(sg, nz, fbytes, mine ? skip : PNG_CHUNK, tail_extra, fbyte);
+                    nbits_mine = sg.finish();
+                }
+                uint32_t incl = nbits_mine;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
                     if (lane >= o) incl += t;
                 }
-                PngEmit em;
-                em.buf = buf;
-                em.pos = bitpos + incl - cnt.bits;
-                if (mine || fbyte) png_chunk_tokens(em, nz, fbytes, mine ? skip : PNG_CHUNK, tail_extra, fbyte);
+                {
+                    const uint32_t at = bitpos + incl - nbits_mine;
+                    for (uint32_t o = 0; o < nbits_mine; o += 32u) {
+                        uint32_t v = stage[o >> 5];
+                        const uint32_t left = nbits_mine - o;
+                        if (left < 32u) v &= (1u << left) - 1u;
+                        const uint32_t dp = at + o, dw = dp >> 5, ds = dp & 31u;
+                        atomicOr(buf + dw, v << ds);
+                        if (ds) atomicOr(buf + dw + 1, v >> (32u - ds));
+                    }
+                }
                 bitpos += __shfl_sync(0xffffffffu, incl, 31);
                 __syncwarp();
             }
