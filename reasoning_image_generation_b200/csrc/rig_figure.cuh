@@ -51,7 +51,7 @@ __host__ __device__ inline size_t figure_warp_bytes(int W)
 {
     return (size_t)FIG_ROWS * ((size_t)3 * W + (size_t)8 * FIG_ACC) + (size_t)FIG_ROWS * 8;
 }
-inline size_t figure_smem_bytes(int W, int nwarps) { return (size_t)3 * W * FIG_ROWS + (size_t)nwarps * figure_warp_bytes(W); }
+inline size_t figure_smem_bytes(int W, int nwarps) { return (size_t)3 * W * FIG_ROWS + 1024 + (size_t)nwarps * figure_warp_bytes(W); }
 
 struct FigAcc {
     int *cover, *area;
@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(FIG_MAX_WARPS * 32, 1) k_figure(const FigurePa
     const int W = P.W;
     const uint32_t band_bytes = (uint32_t)(3 * W * FIG_ROWS);
     uint8_t *tmpl = smem;
-    uint8_t *wbase = smem + band_bytes + (size_t)warp * figure_warp_bytes(W);
+    const uint32_t *magic = (const uint32_t *)(smem + band_bytes);       // 256 division multipliers (fig_div_magic)
+    uint8_t *wbase = smem + band_bytes + 1024 + (size_t)warp * figure_warp_bytes(W);
     uint8_t *mine = wbase;
     int *cover = (int *)(wbase + band_bytes);
     int *area = cover + FIG_ROWS * FIG_ACC;
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(FIG_MAX_WARPS * 32, 1) k_figure(const FigurePa
             const uint32_t m = i % 3;
             t0[i] = m == 0 ? w0 : (m == 1 ? w1 : w2);
         }
+        for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) ((uint32_t *)(smem + band_bytes))[i] = fig_div_magic(i);
         for (int i = lane; i < 2 * FIG_ROWS * FIG_ACC; i += 32) cover[i] = 0;     // cover and area are contiguous
         if (lane < 2 * FIG_ROWS) gmask[lane] = 0u;                                 // masks and carry-ins
         fence_async_smem();
@@ -152,8 +154,10 @@ __global__ void __launch_bounds__(FIG_MAX_WARPS * 32, 1) k_figure(const FigurePa
         first = __shfl_sync(0xffffffffu, first, 0);
         take = __shfl_sync(0xffffffffu, take, 0);
         if (first >= total_bands) break;
+        uint32_t slot = first / bands_per_image;
+        int band = (int)(first - slot * bands_per_image) - 1;
         for (uint32_t bi = first; bi < first + take && bi < total_bands; bi++) {
-            const uint32_t slot = bi / bands_per_image;
+            if (++band == bands_per_image) { band = 0; slot++; }
             if (slot != cur_slot) {
                 cur_slot = slot;
                 image = P.order[slot];
@@ -163,7 +167,6 @@ __global__ void __launch_bounds__(FIG_MAX_WARPS * 32, 1) k_figure(const FigurePa
                 myh.n_edges = 0u;
                 if (lb + lane < le) myh = fig_load_hdr(P.layers + lb + lane);
             }
-            const int band = (int)(bi - slot * bands_per_image);
             const int r0 = band * FIG_ROWS;
             int r1 = r0 + FIG_ROWS - 1;
             if (r1 > P.H - 1) r1 = P.H - 1;
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(FIG_MAX_WARPS * 32, 1) k_figure(const FigurePa
                             const int xs = x0 + g * 32;
                             if (carry != 0 && xs > prev_end) {          // interior run at constant coverage
                                 const uint32_t al = fig_alpha(carry, 0);
-                                for (int x = prev_end + lane; x < xs; x += 32) fig_put3(rowpx + x * 3, fig_blend_px(fig_get3(rowpx + x * 3), L.rgba, al));
+                                for (int x = prev_end + lane; x < xs; x += 32) fig_put3(rowpx + x * 3, fig_blend_px_m(fig_get3(rowpx + x * 3), L.rgba, al, magic));
                             }
                             const int x = xs + lane;
                             const int c = cover[ro + g * 32 + lane], a = area[ro + g * 32 + lane];
@@ -259,13 +262,13 @@ __global__ void __launch_bounds__(FIG_MAX_WARPS * 32, 1) k_figure(const FigurePa
                                 if (lane >= o) ci += t;
                             }
                             const uint32_t al = fig_alpha(carry + ci, a);
-                            if (x < W && al) fig_put3(rowpx + x * 3, fig_blend_px(fig_get3(rowpx + x * 3), L.rgba, al));
+                            if (x < W && al) fig_put3(rowpx + x * 3, fig_blend_px_m(fig_get3(rowpx + x * 3), L.rgba, al, magic));
                             carry += __shfl_sync(0xffffffffu, ci, 31);
                             prev_end = xs + 32;
                         }
                         if (carry != 0 && prev_end < fill_end) {        // interior continues to the next chunk / the right canvas edge
                             const uint32_t al = fig_alpha(carry, 0);
-                            for (int x = prev_end + lane; x < fill_end; x += 32) fig_put3(rowpx + x * 3, fig_blend_px(fig_get3(rowpx + x * 3), L.rgba, al));
+                            for (int x = prev_end + lane; x < fill_end; x += 32) fig_put3(rowpx + x * 3, fig_blend_px_m(fig_get3(rowpx + x * 3), L.rgba, al, magic));
                         }
                     }
                     __syncwarp();

@@ -40,7 +40,7 @@ struct rig_figure_ctx {
     size_t cap_layers = 0, cap_edges = 0, cap_dir = 0, cap_images = 0;
     uint8_t *d_stage[2] = {nullptr, nullptr};
     size_t stage_images = 0;
-    uint32_t max_claim = 16;
+    uint32_t max_claim = 32;
     rig_figure_stats stats = {};
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool, ev_used;

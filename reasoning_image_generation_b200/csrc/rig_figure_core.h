@@ -182,4 +182,40 @@ RIG_HD uint32_t fig_blend_px(uint32_t px, uint32_t rgba, uint32_t cover)
     return (v0 & 0xffu) | ((v1 & 0xffu) << 8) | ((v2 & 0xffu) << 16);
 }
 
+
+// ---- the same blend without divisions ---------------------------------------------------------------
+// Every numerator is below 2^24 and the divisor 65280 + alpha is below 2^16, so floor(n / d) == (n * ceil(2^40 / d)) >> 40
+// exactly (the error term n * (m d - 2^40) < 2^24 * 2^16).  The kernel keeps the 256 multipliers in shared memory.
+RIG_HD uint32_t fig_div_magic(uint32_t alpha)
+{
+    const unsigned long long d = 65280ull + alpha;
+    return (uint32_t)(((1ull << 40) + d - 1ull) / d);
+}
+RIG_HD uint32_t fig_mulhi(uint32_t a, uint32_t b)
+{
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((unsigned long long)a * b) >> 32);
+#endif
+}
+RIG_HD uint32_t fig_blend1_m(uint32_t p, uint32_t c, uint32_t alpha, uint32_t magic)
+{
+    const uint32_t r = p * 255u;
+    return fig_mulhi((((c << 8) - r) * alpha + (r << 8)), magic) >> 8;
+}
+// magic: table of fig_div_magic(alpha), alpha = 0 .. 255
+RIG_HD uint32_t fig_blend_px_m(uint32_t px, uint32_t rgba, uint32_t cover, const uint32_t *magic)
+{
+    const uint32_t ca = rgba >> 24;
+    if (ca == 255u && cover == 255u) return rgba & 0x00ffffffu;
+    const uint32_t alpha = fig_mult_cover(ca, cover);
+    if (alpha == 0u) return px;
+    const uint32_t m = magic[alpha];
+    const uint32_t v0 = fig_blend1_m(px & 0xffu, rgba & 0xffu, alpha, m);
+    const uint32_t v1 = fig_blend1_m((px >> 8) & 0xffu, (rgba >> 8) & 0xffu, alpha, m);
+    const uint32_t v2 = fig_blend1_m((px >> 16) & 0xffu, (rgba >> 16) & 0xffu, alpha, m);
+    return v0 | (v1 << 8) | (v2 << 16);
+}
+
 }  // namespace rig

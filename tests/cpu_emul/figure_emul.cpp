@@ -78,3 +78,22 @@ extern "C" void figure_emul_render(int W, int H, int n_layers, const uint32_t *l
         }
     }
 }
+
+// exhaustive check of the division-free blend used by the kernel against the plain one: every destination value, colour
+// value and alpha; returns the number of mismatches
+extern "C" long figure_emul_check_magic()
+{
+    uint32_t magic[256];
+    for (uint32_t a = 0; a < 256; a++) magic[a] = fig_div_magic(a);
+    long bad = 0;
+    for (uint32_t alpha = 1; alpha < 256; alpha++)
+        for (uint32_t p = 0; p < 256; p++)
+            for (uint32_t c = 0; c < 256; c++)
+                bad += fig_blend1(p, c, alpha) != fig_blend1_m(p, c, alpha, magic[alpha]);
+    for (uint32_t ca = 0; ca < 256; ca += 5)
+        for (uint32_t cover = 1; cover < 256; cover += 3) {
+            const uint32_t px = (ca * 2654435761u + cover * 40503u) & 0xffffffu, rgba = ((cover * 97u + ca * 13u) & 0xffffffu) | (ca << 24);
+            bad += fig_blend_px(px, rgba, cover) != fig_blend_px_m(px, rgba, cover, magic);
+        }
+    return bad;
+}

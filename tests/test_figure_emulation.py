@@ -132,3 +132,10 @@ def test_scene_slicing_and_tiling_keep_images(agg):
     # shards generated independently equal slices of the whole
     again = synthetic_figure_scene(3, 128, 128, seed=2, first=2)
     assert (agg.render(again, 128, 128) == ref[2:5]).all()
+
+
+def test_division_free_blend_is_exact(femul):
+    """k_figure blends with a multiply by ceil(2^40 / (65280 + alpha)) instead of three divisions per pixel: checked
+    exhaustively (every destination value x colour value x alpha) against fixed_blender_rgba_plain's division."""
+    femul.figure_emul_check_magic.restype = ctypes.c_long
+    assert femul.figure_emul_check_magic() == 0
