@@ -72,3 +72,52 @@ def test_two_rank_exchange_equals_single_rank_scan():
         assert p.exitcode == 0
     want = dedup_oracle.drop_flags(allh, thr, block=512)
     assert (drop == want).all() and set(np.nonzero(want)[0]) >= {7, n // 2 + 1, n - 5}
+
+
+# ---- figure path: image blocks per rank, no collective on the render path; each rank's "kernel" here is the host path
+# pipeline (librig.so, no GPU needed) + the CPU emulation of k_figure's per-lane arithmetic
+def _figure_worker(rank, world, port, n, q):
+    import ctypes
+    from conftest import ROOT
+    from reasoning_image_generation_b200.figure import host_edges
+    from reasoning_image_generation_b200.synth_figure import synthetic_figure_scene
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    i0, i1 = shard_panels(n, world, rank)
+    sc = synthetic_figure_scene(i1 - i0, 128, 128, seed=5, kind='single', first=i0)     # shards are generated independently
+    layers, edges = host_edges(sc)
+    lib = ctypes.CDLL(os.path.join(ROOT, 'tests', 'cpu_emul', 'libfigure_emul.so'))
+    lib.figure_emul_render.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    out = np.zeros((i1 - i0, 128, 128, 3), np.uint8)
+    for i in range(i1 - i0):
+        L = np.ascontiguousarray(layers[layers[:, 0] == i])
+        lib.figure_emul_render(128, 128, len(L), L.ctypes.data, edges.ctypes.data, 2, 256, out[i].ctypes.data)
+    sums = torch.from_numpy(out.reshape(i1 - i0, -1).astype(np.int64).sum(axis=1))
+    cap = (n + world - 1) // world                   # ragged shards: pad to the largest one for the gather
+    padded = torch.full((cap,), -1, dtype=torch.int64)
+    padded[:i1 - i0] = sums
+    parts = [torch.empty(cap, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(parts, padded)                   # only the test gathers: the render path itself has no exchange
+    if rank == 0:
+        allv = torch.cat(parts).numpy()
+        q.put(allv[allv >= 0].copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_figure_shards_equal_the_whole_scene(built):
+    from oracle.agg_oracle import AggOracle
+    from reasoning_image_generation_b200.synth_figure import synthetic_figure_scene
+    n = 21
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_figure_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    sums = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = AggOracle().render(synthetic_figure_scene(n, 128, 128, seed=5, kind='single'), 128, 128)
+    assert (sums == ref.reshape(n, -1).astype(np.int64).sum(axis=1)).all()
