@@ -51,7 +51,7 @@ int rig_grid_sync(rig_grid_ctx *ctx);
 
 typedef struct rig_grid_stats {
     uint64_t kernel_launches;
-    double compose_ms;           /* summed CUDA-event time of k_grid since rig_grid_set_profiling(ctx, 1) */
+    double compose_ms;           /* summed CUDA-event time of the compose kernels since rig_grid_set_profiling(ctx, 1) */
     uint64_t timed_samples;
 } rig_grid_stats;
 int rig_grid_get_stats(rig_grid_ctx *ctx, rig_grid_stats *out);

@@ -1,6 +1,6 @@
-// rig_grid.cuh -- k_grid: the overview-image compositor (/root/reference/src/layout.py:17-31,49-192).
+// rig_grid.cuh -- k_grid_overlay + k_grid_cells: the overview-image compositor (/root/reference/src/layout.py:17-31,49-192).
 //
-// One thread per pixel of the overview canvas.  Overlay pixels (background, borders, labels, the '?' cell) are copied;
+// Overlay pixels (background, borders, labels, the '?' cell) are copied;
 // a pixel inside a panel cell is cv2.resize(INTER_AREA) of that panel, evaluated the way OpenCV's ResizeArea_ does it
 // (resize.cpp: computeResizeAreaTab + ResizeArea_Invoker, float32 work type): for every contributing source row, in order,
 //     buf = 0;  for every contributing source column, in order:  buf = buf + S * alpha      (separate multiply and add)
@@ -40,33 +40,66 @@ __device__ __forceinline__ uint32_t grid_round_u8(float v)
     return (uint32_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
 }
 
-__global__ void __launch_bounds__(256) k_grid(const GridParams P)
+// overlay pixels of every sample: a straight 16-byte copy of the constant canvas (cell pixels are overwritten by k_grid_cells)
+__global__ void __launch_bounds__(256) k_grid_overlay(const GridParams P)
 {
-    const int npix = P.grid_w * P.grid_h;
+    const size_t bytes = (size_t)P.grid_w * P.grid_h * 3;
     const int sample = blockIdx.y;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
-        uint8_t *o = P.out + ((size_t)sample * npix + i) * 3;
-        const int cell = P.cell_of_pixel[i];
-        if (cell < 0) {
-            o[0] = P.overlay[3 * i]; o[1] = P.overlay[3 * i + 1]; o[2] = P.overlay[3 * i + 2];
-            continue;
-        }
-        const int pi = P.panel_index[sample * P.n_cells + cell];
-        if (pi < 0) { o[0] = o[1] = o[2] = 255; continue; }
-        const int y = i / P.grid_w, x = i - y * P.grid_w;
-        const GridTap ty = P.taps[y - P.cell_y[cell]], tx = P.taps[x - P.cell_x[cell]];
-        const uint8_t *S = P.panels + (size_t)pi * P.panel_h * P.panel_w * 3;
+    uint8_t *o = P.out + (size_t)sample * bytes;
+    const size_t vec = (((uintptr_t)o | (uintptr_t)P.overlay) & 15u) == 0 ? bytes / 16 : 0;
+    for (size_t i = blockIdx.x * blockDim.x + threadIdx.x; i < vec; i += (size_t)gridDim.x * blockDim.x)
+        ((uint4 *)o)[i] = __ldg((const uint4 *)P.overlay + i);
+    for (size_t i = vec * 16 + blockIdx.x * blockDim.x + threadIdx.x; i < bytes; i += (size_t)gridDim.x * blockDim.x) o[i] = P.overlay[i];
+}
+
+// One CTA per (sample, cell, destination row): the source rows that row draws from are staged in shared memory with
+// 16-byte coalesced loads (each panel byte leaves HBM once, plus the row shared by two neighbouring destination rows),
+// then thread x evaluates destination pixel x in OpenCV's order.
+__global__ void __launch_bounds__(128) k_grid_cells(const GridParams P)
+{
+    extern __shared__ __align__(16) uint8_t rows[];
+    const int sample = blockIdx.y;
+    const int cell = blockIdx.x / P.cell_size, yc = blockIdx.x - cell * P.cell_size;
+    const int pi = P.panel_index[sample * P.n_cells + cell];
+    const int gy = P.cell_y[cell] + yc, gx0 = P.cell_x[cell];
+    const size_t npix = (size_t)P.grid_w * P.grid_h;
+    uint8_t *orow = P.out + ((size_t)sample * npix + (size_t)gy * P.grid_w + gx0) * 3;
+    const int8_t *cmap = P.cell_of_pixel + (size_t)gy * P.grid_w + gx0;
+    if (pi < 0) {                                            // blank cell: white
+        for (int x = threadIdx.x; x < P.cell_size; x += blockDim.x)
+            if (cmap[x] == cell) { orow[3 * x] = 255; orow[3 * x + 1] = 255; orow[3 * x + 2] = 255; }
+        return;
+    }
+    const GridTap *ty = P.taps + yc;                          // (read in place: a by-value copy indexed by k would live in local memory)
+    const int ty_first = ty->first, ty_count = ty->count;
+    const int row_bytes = P.panel_w * 3;
+    {
+        const uint4 *src = (const uint4 *)(P.panels + ((size_t)pi * P.panel_h + ty_first) * row_bytes);
+        uint4 *dst = (uint4 *)rows;
+        const int n16 = ty_count * row_bytes / 16;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < P.cell_size; x += blockDim.x) {
+        if (cmap[x] != cell) continue;                       // border ring / overlay pixels inside the cell square
+        const GridTap *tx = P.taps + x;
+        const int tx_first = tx->first, tx_count = tx->count;
+        float wx[GRID_MAX_TAPS];
+#pragma unroll
+        for (int k = 0; k < GRID_MAX_TAPS; k++) wx[k] = __ldg(&tx->w[k]);
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        for (int j = 0; j < ty.count; j++) {
-            const uint8_t *row = S + ((size_t)(ty.first + j) * P.panel_w + tx.first) * 3;
+        for (int j = 0; j < ty_count; j++) {
+            const uint8_t *row = rows + (size_t)j * row_bytes + tx_first * 3;
             float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-            for (int k = 0; k < tx.count; k++) {
-                const float a = tx.w[k];
+#pragma unroll
+            for (int k = 0; k < GRID_MAX_TAPS; k++) {
+                if (k >= tx_count) break;
+                const float a = wx[k];
                 b0 = __fadd_rn(b0, __fmul_rn((float)row[3 * k], a));
                 b1 = __fadd_rn(b1, __fmul_rn((float)row[3 * k + 1], a));
                 b2 = __fadd_rn(b2, __fmul_rn((float)row[3 * k + 2], a));
             }
-            const float beta = ty.w[j];
+            const float beta = __ldg(&ty->w[j]);
             if (j == 0) { s0 = __fmul_rn(beta, b0); s1 = __fmul_rn(beta, b1); s2 = __fmul_rn(beta, b2); }
             else {
                 s0 = __fadd_rn(s0, __fmul_rn(beta, b0));
@@ -74,7 +107,7 @@ __global__ void __launch_bounds__(256) k_grid(const GridParams P)
                 s2 = __fadd_rn(s2, __fmul_rn(beta, b2));
             }
         }
-        o[0] = (uint8_t)grid_round_u8(s0); o[1] = (uint8_t)grid_round_u8(s1); o[2] = (uint8_t)grid_round_u8(s2);
+        orow[3 * x] = (uint8_t)grid_round_u8(s0); orow[3 * x + 1] = (uint8_t)grid_round_u8(s1); orow[3 * x + 2] = (uint8_t)grid_round_u8(s2);
     }
 }
 

@@ -26,7 +26,7 @@ struct rig_grid_ctx {
     int8_t *d_cellmap = nullptr;
     GridTap *d_taps = nullptr;
     int32_t *d_index = nullptr;
-    size_t out_cap = 0;
+    size_t out_cap = 0, cells_smem = 0;
     int sm_count = 1;
     rig_grid_stats stats = {};
     bool profiling = false, pending_profile = false;
@@ -87,6 +87,7 @@ int rig_grid_create(int device, const rig_grid_layout *L, int max_samples, rig_g
     if (!out) return gfail(nullptr, RIG_E_INVALID, "out is NULL");
     *out = nullptr;
     if (!L || !L->cell_x || !L->cell_y || !L->overlay || !L->cell_of_pixel) return gfail(nullptr, RIG_E_INVALID, "layout or one of its arrays is NULL");
+    if (L->panel_w % 16) return gfail(nullptr, RIG_E_UNSUPPORTED, "panel width must be a multiple of 16 (16-byte rows)");
     if (L->panel_w <= 0 || L->panel_w != L->panel_h) return gfail(nullptr, RIG_E_UNSUPPORTED, "panels must be square (got %dx%d)", L->panel_w, L->panel_h);
     if (L->cell_size <= 0 || L->cell_size >= L->panel_w) return gfail(nullptr, RIG_E_UNSUPPORTED, "cell_size must be in 1 .. panel size - 1 (INTER_AREA down-scale)");
     if (L->n_cells < 0 || L->n_cells > GRID_MAX_CELLS) return gfail(nullptr, RIG_E_UNSUPPORTED, "at most %d cells", GRID_MAX_CELLS);
@@ -133,6 +134,12 @@ int rig_grid_create(int device, const rig_grid_layout *L, int max_samples, rig_g
     cudaDeviceProp prop;
     GCKC(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    c->cells_smem = (size_t)GRID_MAX_TAPS * L->panel_w * 3;
+    if (c->cells_smem > prop.sharedMemPerBlockOptin) {
+        gfail(c, RIG_E_UNSUPPORTED, "panel width %d needs %zu B of shared memory", L->panel_w, c->cells_smem);
+        return bail(RIG_E_UNSUPPORTED);
+    }
+    GCKC(cudaFuncSetAttribute(k_grid_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->cells_smem));
     GCKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     GCKC(cudaEventCreate(&c->ev0));
     GCKC(cudaEventCreate(&c->ev1));
@@ -191,11 +198,14 @@ int rig_grid_compose(rig_grid_ctx *c, const uint8_t *panels_dev, const int32_t *
     GridParams P = c->P;
     P.panels = panels_dev; P.out = dev_out; P.n_samples = n_samples;
     const int npix = c->P.grid_w * c->P.grid_h;
-    dim3 grid((unsigned)std::min((npix + 255) / 256, 64), (unsigned)n_samples);
     if (n_samples > 65535) return gfail(c, RIG_E_CAPACITY, "at most 65535 samples per call");
     if (c->profiling) GCK(c, cudaEventRecord(c->ev0, st));
-    k_grid<<<grid, 256, 0, st>>>(P);
+    k_grid_overlay<<<dim3((unsigned)std::min((npix * 3 / 16 + 255) / 256 + 1, 32), (unsigned)n_samples), 256, 0, st>>>(P);
     c->stats.kernel_launches++;
+    if (c->P.n_cells) {
+        k_grid_cells<<<dim3((unsigned)(c->P.n_cells * c->P.cell_size), (unsigned)n_samples), 128, c->cells_smem, st>>>(P);
+        c->stats.kernel_launches++;
+    }
     GCK(c, cudaGetLastError());
     if (c->profiling) {
         GCK(c, cudaEventRecord(c->ev1, st));
