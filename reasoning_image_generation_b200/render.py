@@ -123,6 +123,22 @@ class Renderer:
         with self._lock:
             self._check(self._lib.rig_render_batch(self._h, ctypes.byref(s), out_ptr, 1, _LAYOUTS[layout], stream or None))
 
+    def iter_png(self, scene: Scene, encoder, chunk: int = 4096, layout: str = 'bgr'):
+        """``save_image(path, img)`` = ``cv2.imwrite`` (src/utils.py:18-21) for a whole batch of panels: renders `chunk` panels at
+        a time into the encoder's device staging buffer and encodes them there, so only PNG bytes cross PCIe.  `layout` is the
+        channel order the panels are rendered in ('bgr' = what the reference hands to cv2.imwrite; the files hold RGB either
+        way).  Yields (first_panel_index, buffer, offsets); file i of the chunk is buffer[offsets[i]:offsets[i + 1]] (pinned
+        host memory, valid until the next iteration)."""
+        self._check_scene(scene)
+        chunk = max(1, min(int(chunk), encoder.max_images, self.max_panels))
+        for p0 in range(0, scene.n_panels, chunk):
+            sub = scene if (p0 == 0 and scene.n_panels <= chunk) else scene.slice(p0, min(scene.n_panels, p0 + chunk))
+            ptr = encoder.staging(sub.n_panels)
+            self.render_to_device(sub, ptr, layout, 0)
+            self.sync()                  # rendered on the context's own stream: finish before the encoder reads
+            buf, off = encoder.encode(ptr, sub.n_panels, layout, 0)
+            yield p0, buf, off
+
     def upload(self, scene: Scene, layout: str = 'bgr', stream: int = 0):
         self._check_scene(scene)
         s = scene.as_struct()

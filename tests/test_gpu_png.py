@@ -131,3 +131,28 @@ def test_iter_png_is_savefig_for_a_batch(built):
     assert seen == 50
     r.close()
     enc.close()
+
+
+def test_sequence_iter_png_is_imwrite_for_a_batch(built):
+    """Renderer.iter_png: panels rendered in cv2's BGR order and encoded on the device decode (libpng) to the oracle's
+    pixels, like files written by the reference's save_image (src/utils.py:18-21)."""
+    import cv2
+    from oracle import ref_render
+    from reasoning_image_generation_b200 import Renderer
+    from reasoning_image_generation_b200.png import PngEncoder
+    from reasoning_image_generation_b200.synth import scene_to_elements, synthetic_scene
+    sc = synthetic_scene(40, seed=31)
+    r = Renderer(512, 512, max_panels=16)
+    enc = PngEncoder(512, 512, max_images=16)
+    be = ref_render.CBackend()
+    seen = 0
+    for p0, buf, off in r.iter_png(sc, enc, chunk=16):
+        for k in range(len(off) - 1):
+            img = cv2.imdecode(np.asarray(buf[int(off[k]):int(off[k + 1])]), cv2.IMREAD_UNCHANGED)      # BGR, as cv2.imread gives
+            els, ug = scene_to_elements(sc, p0 + k)
+            ref = ref_render.render_panel(512, 512, (255, 255, 255), els, ug, 3, backend=be)
+            assert (img == ref).all()
+            seen += 1
+    assert seen == 40
+    r.close()
+    enc.close()
