@@ -141,14 +141,15 @@ RIG_HD Rec rec_nop()
 {
     Rec r;
     for (int i = 0; i < 8; i++) r.w[i] = 0;
-    r.w[0] = REC_NOP | (1u << 16);  // ymin=1 > ymax=0
+    r.w[0] = REC_NOP | (0x7fffu << 16);  // ymin = 32767 > ymax = -32768: overlaps no band (1 > 0 would overlap rows 0..1)
+    r.w[1] = 0x8000u;
     return r;
 }
 RIG_HD void rec_head(Rec &r, uint32_t type, uint32_t flags, int ymin, int ymax, int hi1, uint32_t color, int H)
 {
     if (ymin < 0) ymin = 0;
     if (ymax > H - 1) ymax = H - 1;
-    if (ymin > ymax) { ymin = 1; ymax = 0; }
+    if (ymin > ymax) { ymin = 32767; ymax = -32768; }
     r.w[0] = type | (flags << 8) | ((uint32_t)(uint16_t)ymin << 16);
     r.w[1] = (uint32_t)(uint16_t)ymax | ((uint32_t)(uint16_t)hi1 << 16);
     r.w[7] = color;
@@ -577,7 +578,7 @@ constexpr int CONVEX_SLOTS = 4;
 RIG_HD Rec rec_cont()
 {
     Rec r = rec_nop();
-    r.w[0] = (uint32_t)REC_CONT | (1u << 16);   // ymin = 1 > ymax = 0: never selected
+    r.w[0] = (uint32_t)REC_CONT | (0x7fffu << 16);   // ymin > ymax: never selected
     return r;
 }
 RIG_FN void pack_convex(const ConvexChains &C, uint32_t color, int H, Rec *out)

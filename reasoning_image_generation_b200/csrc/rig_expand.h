@@ -303,7 +303,7 @@ RIG_HD void write_summaries(Rec *recs, uint32_t sum_begin, uint32_t payload_begi
     uint32_t *sum = (uint32_t *)(recs + sum_begin);
     const uint32_t nwin = (nrec + 31u) / 32u, cap = summary_slots(nrec) * 8u;
     for (uint32_t w = lane; w < cap; w += LANES) {
-        int lo = 1, hi = 0;
+        int lo = 32767, hi = -32768;          // empty: a range no band overlaps
         if (w < nwin) {
             lo = 1 << 20; hi = -(1 << 20);
             const uint32_t end = (w + 1) * 32u < nrec ? (w + 1) * 32u : nrec;
@@ -312,7 +312,7 @@ RIG_HD void write_summaries(Rec *recs, uint32_t sum_begin, uint32_t payload_begi
                 const int a = rec_ymin(r), b = rec_ymax(r);
                 if (a <= b) { lo = a < lo ? a : lo; hi = b > hi ? b : hi; }
             }
-            if (lo > hi) { lo = 1; hi = 0; }
+            if (lo > hi) { lo = 32767; hi = -32768; }
         }
         sum[w] = (uint32_t)(uint16_t)(int16_t)lo | ((uint32_t)(uint16_t)(int16_t)hi << 16);
     }
