@@ -163,7 +163,7 @@ struct SV {
 };
 class StrokeGen {
 public:
-    StrokeGen(double linewidth, int cap, int join, ClipToCells &sink) : sink_(sink), cap_(cap), join_(join)
+    StrokeGen(std::vector<SV> &storage, double linewidth, int cap, int join, ClipToCells &sink) : sink_(sink), seq_(storage), cap_(cap), join_(join)
     {
         w_ = linewidth * 0.5;
         if (w_ < 0) { wabs_ = -w_; wsign_ = -1; }
@@ -370,7 +370,7 @@ private:
     }
 
     ClipToCells &sink_;
-    std::vector<SV> seq_;
+    std::vector<SV> &seq_;        // caller-owned, so that its capacity survives from artist to artist
     double w_, wabs_, weps_, miter_limit_;
     int wsign_, cap_, join_;
     bool first_ = true;
@@ -505,14 +505,10 @@ void walk_flat(const std::vector<Node> &path, OnMove on_move, OnLine on_line, On
     }
 }
 
-void finish_layer(FigurePrepared &out, size_t e0, uint32_t image, uint32_t rgba, int W, int H)
+void finish_layer(FigurePrepared &out, size_t e0, uint32_t rgba, int W, int H, std::vector<FEdge> &tmp, std::vector<uint32_t> &count)
 {
     const size_t n = out.edges.size() - e0;
     if (n == 0) return;
-    // sort the layer's edges by their first row (stable: equal rows keep contour order), build the slab directory
-    std::stable_sort(out.edges.begin() + e0, out.edges.end(), [](const FEdge &a, const FEdge &b) {
-        return (std::min(a.y1, a.y2) >> 8) < (std::min(b.y1, b.y2) >> 8);
-    });
     int ymin = 1 << 30, ymax = -(1 << 30), xmin = 1 << 30, xmax = -(1 << 30), maxspan = 0;
     for (size_t i = e0; i < out.edges.size(); i++) {
         const FEdge &e = out.edges[i];
@@ -526,23 +522,26 @@ void finish_layer(FigurePrepared &out, size_t e0, uint32_t image, uint32_t rgba,
     L.edge_begin = (uint32_t)e0;
     L.n_edges = (uint32_t)n;
     L.rgba = rgba;
-    L.ymin = (int16_t)std::max(ymin, 0);
+    L.ymin = (int16_t)std::max(ymin, 0);      // (edges are clipped to the canvas: ymin >= 0 already)
     L.ymax = (int16_t)std::min(ymax, H - 1);
     L.xmin = (int16_t)std::max(xmin, 0);
     L.xmax = (int16_t)std::min(xmax, W - 1);
     L.maxspan = (uint16_t)std::min(maxspan, 65535);
     L.dir_begin = (uint32_t)out.dir.size();
-    // dir[s] = index (relative to edge_begin) of the first edge whose first row >= ymin0 + 16 s, ymin0 = the unclamped ymin
-    // (edges are clipped to the canvas, so ymin0 >= 0 and equals L.ymin)
+    // Counting sort of the layer's edges by the 16-row slab of their first row (the cell sums commute, so the order inside
+    // a slab is irrelevant), and the slab directory: dir[s] = index (relative to edge_begin) of the first edge whose first
+    // row >= ymin + 16 s.
     const int slabs = (ymax - ymin) / FIG_SLAB_ROWS + 2;
-    size_t k = e0;
-    for (int s = 0; s < slabs; s++) {
-        const int row = ymin + s * FIG_SLAB_ROWS;
-        while (k < out.edges.size() && (std::min(out.edges[k].y1, out.edges[k].y2) >> 8) < row) k++;
-        out.dir.push_back((uint32_t)(k - e0));
+    count.assign((size_t)slabs + 1, 0u);
+    for (size_t i = e0; i < out.edges.size(); i++) {
+        const FEdge &e = out.edges[i];
+        count[(size_t)(((std::min(e.y1, e.y2) >> 8) - ymin) / FIG_SLAB_ROWS) + 1]++;
     }
+    for (int s = 0; s < slabs; s++) count[s + 1] += count[s];
+    for (int s = 0; s < slabs; s++) out.dir.push_back(count[s]);
+    tmp.assign(out.edges.begin() + e0, out.edges.end());
+    for (const FEdge &e : tmp) out.edges[e0 + count[(size_t)(((std::min(e.y1, e.y2) >> 8) - ymin) / FIG_SLAB_ROWS)]++] = e;
     L.ndir = (uint16_t)slabs;
-    (void)image;
     out.layers.push_back(L);
 }
 
@@ -551,6 +550,9 @@ void finish_layer(FigurePrepared &out, size_t e0, uint32_t image, uint32_t rgba,
 int figure_prepare(const rig_figure_scene &s, int W, int H, bool bgr, int i0, int i1, FigurePrepared &out, char *err, int errlen)
 {
     std::vector<Node> path;
+    std::vector<SV> stroke_storage;
+    std::vector<FEdge> sort_tmp;
+    std::vector<uint32_t> sort_count;
     for (int img = i0; img < i1; img++) {
         out.image_layer_begin.push_back((uint32_t)out.layers.size());
         for (uint32_t a = s.image_artist_begin[img]; a < s.image_artist_begin[img + 1]; a++) {
@@ -620,12 +622,12 @@ int figure_prepare(const rig_figure_scene &s, int W, int H, bool bgr, int i0, in
                 walk_flat(path, [&](double x, double y) { sink.move_to(x, y); }, [&](double x, double y) { sink.line_to(x, y); },
                           [&](bool closed) { if (closed) sink.close(); });
                 sink.close();
-                finish_layer(out, e0, (uint32_t)img, pack(s.face_rgba + 4 * (size_t)a), W, H);
+                finish_layer(out, e0, pack(s.face_rgba + 4 * (size_t)a), W, H, sort_tmp, sort_count);
             }
             if (lw != 0.0 && s.edge_rgba[4 * (size_t)a + 3] != 0) {
                 const size_t e0 = out.edges.size();
                 ClipToCells sink(out.edges, bx1, by1, bx2, by2);
-                StrokeGen gen(lw, s.cap[a], s.join[a], sink);
+                StrokeGen gen(stroke_storage, lw, s.cap[a], s.join[a], sink);
                 // conv_adaptor_vcgen: every generator run starts from the last MOVETO seen
                 bool have = false;
                 double mx = 0, my = 0;
@@ -647,7 +649,7 @@ int figure_prepare(const rig_figure_scene &s, int W, int H, bool bgr, int i0, in
                           },
                           [&](bool closed) { flush(closed); });
                 if (have) gen.finish(false);
-                finish_layer(out, e0, (uint32_t)img, pack(s.edge_rgba + 4 * (size_t)a), W, H);
+                finish_layer(out, e0, pack(s.edge_rgba + 4 * (size_t)a), W, H, sort_tmp, sort_count);
             }
         }
     }
