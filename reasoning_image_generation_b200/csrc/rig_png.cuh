@@ -73,10 +73,6 @@ __device__ __forceinline__ void png_match(uint32_t len, uint32_t &code, int &nbi
     nbits += 5;            // distance code 0 (distance 1): five zero bits
 }
 
-struct PngCount {
-    uint32_t bits = 0;
-    __device__ __forceinline__ void put(uint32_t, int n) { bits += (uint32_t)n; }
-};
 // single-walk sink: the lane's bits go to its own staging words; they are moved to the piece buffer once the warp scan has
 // placed them
 constexpr int PNG_STAGE_WORDS = 20;      // >= (48 * 9 + 8 + 8 * 13 + 18 + 31) / 32 bits a chunk can need
@@ -111,42 +107,56 @@ struct PngEmit {
         pos += (uint32_t)n;
     }
 };
-// r zeros whose predecessor in the stream is a zero byte
-template <class Sink>
-__device__ __forceinline__ void png_zero_matches(Sink &s, uint32_t r)
+// token tables (static shared memory, filled once per CTA): code bits | number of bits << 24
+struct PngLut {
+    uint32_t lit[256];      // literal byte
+    uint32_t match[259];    // match of length 3..258 at distance 1
+};
+__device__ __forceinline__ void png_fill_lut(PngLut &T)
 {
-    while (r >= 3u) {
-        const uint32_t L = r > 258u ? 258u : r;
+    for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) {
         uint32_t code;
         int nb;
-        png_match(L, code, nb);
-        s.put(code, nb);
-        r -= L;
+        png_literal(i, code, nb);
+        T.lit[i] = code | ((uint32_t)nb << 24);
     }
-    while (r) { s.put(png_rev(0x30u, 8), 8); r--; }
+    for (uint32_t i = 3u + threadIdx.x; i <= 258u; i += blockDim.x) {
+        uint32_t code;
+        int nb;
+        png_match(i, code, nb);
+        T.match[i] = code | ((uint32_t)nb << 24);
+    }
+}
+// r zeros whose predecessor in the stream is a zero byte
+template <class Sink>
+__device__ __forceinline__ void png_zero_matches(Sink &s, uint32_t r, const PngLut &T)
+{
+    const uint32_t full = T.match[258];
+    while (r >= 258u) { s.put(full & 0xffffffu, (int)(full >> 24)); r -= 258u; }
+    if (r >= 3u) { const uint32_t t = T.match[r]; s.put(t & 0xffffffu, (int)(t >> 24)); r = 0; }
+    while (r) { s.put(T.lit[0] & 0xffffffu, 8); r--; }
 }
 // The tokens of one lane's chunk.  nz: bit i set = filtered byte i is non-zero; fb: the chunk's filtered bytes (shared memory);
 // skip: leading zeros that belong to a run an earlier lane emits; tail_extra: zeros after this chunk that continue its trailing
 // run (all-zero lanes that follow, plus the leading zeros of the lane after them).
 template <class Sink>
-__device__ __forceinline__ void png_chunk_tokens(Sink &s, unsigned long long nz, const uint8_t *fb, int skip, uint32_t tail_extra, bool filter_byte)
+__device__ __forceinline__ void png_chunk_tokens(Sink &s, unsigned long long nz, const uint8_t *fb, int skip, uint32_t tail_extra, bool filter_byte,
+                                                 const PngLut &T)
 {
-    if (filter_byte) s.put(png_rev(0x30u + 1u, 8), 8);       // filter type 1 (Sub) opens the row
+    if (filter_byte) s.put(T.lit[1] & 0xffffffu, 8);          // filter type 1 (Sub) opens the row
     int pos = skip;
     while (pos < PNG_CHUNK) {
         const unsigned long long rem = nz >> pos;
         if (rem & 1ull) {
-            uint32_t code;
-            int nb;
-            png_literal(fb[pos], code, nb);
-            s.put(code, nb);
+            const uint32_t t = T.lit[fb[pos]];
+            s.put(t & 0xffffffu, (int)(t >> 24));
             pos++;
         } else {
             const int gap = rem ? (__ffsll((long long)rem) - 1) : (PNG_CHUNK - pos);
             uint32_t r = (uint32_t)gap;
             if (!rem) r += tail_extra;
-            s.put(png_rev(0x30u, 8), 8);                      // the run's first zero is a literal
-            png_zero_matches(s, r - 1u);
+            s.put(T.lit[0] & 0xffffffu, 8);                    // the run's first zero is a literal
+            png_zero_matches(s, r - 1u, T);
             pos += gap;
         }
     }
@@ -182,6 +192,9 @@ __device__ __forceinline__ void png_copy_bits(uint32_t *dst, uint32_t dst_pos, c
 __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ PngLut lut;
+    png_fill_lut(lut);
+    __syncthreads();
     const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = png_warp_smem(P.W);
     uint32_t *buf = (uint32_t *)(smem + (size_t)warp * per_warp);
@@ -208,7 +221,7 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
             png_literal(255u, code, nb);
             em.put(code, nb); em.put(code, nb); em.put(code, nb);
             em.put(png_rev(0x30u, 8), 8);
-            png_zero_matches(em, (uint32_t)row_bytes - 4u);
+            png_zero_matches(em, (uint32_t)row_bytes - 4u, lut);
             white_bits = em.pos;
         }
         white_bits = __shfl_sync(0xffffffffu, white_bits, 0);
@@ -339,7 +352,7 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
                 if (mine || fbyte) {
                     PngStage sg;
                     sg.stage = stage;
-                    png_chunk_tokens(sg, nz, fbytes, mine ? skip : PNG_CHUNK, tail_extra, fbyte);
+                    png_chunk_tokens(sg, nz, fbytes, mine ? skip : PNG_CHUNK, tail_extra, fbyte, lut);
                     nbits_mine = sg.finish();
                 }
                 uint32_t incl = nbits_mine;

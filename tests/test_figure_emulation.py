@@ -46,7 +46,7 @@ def test_synthetic_figures_match_the_oracle(agg, femul, kind):
 
 
 def test_other_canvas_sizes(agg, femul):
-    for (W, H) in ((256, 256), (640, 480), (1600, 1600)):
+    for (W, H) in ((256, 256), (640, 480), (1600, 1600), (48, 33), (16, 3), (2048, 37)):
         sc = synthetic_figure_scene(3, W, H, seed=5, kind='single')
         ref = agg.render(sc, W, H)
         got = emul_render(femul, sc, 4)

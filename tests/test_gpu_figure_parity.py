@@ -117,7 +117,7 @@ def test_fuzz_paths_caps_joins(agg):
     r.close()
 
 
-@pytest.mark.parametrize('size', [(256, 256), (640, 480), (1600, 1600)])
+@pytest.mark.parametrize('size', [(256, 256), (640, 480), (1600, 1600), (48, 33), (16, 3), (2048, 37)])
 def test_other_canvas_sizes(agg, size):
     W, H = size
     sc = synthetic_figure_scene(5, W, H, seed=5, kind='single')
