@@ -341,6 +341,25 @@ def figure_leg(env, args, sampler):
     (ms_max,) = env.max_over_ranks(ms)
     value = env.world * n * args.steps / (ms_max / 1e3)
     checksum_dev = int(out[::509, 200:312, 200:312, 0].to(torch.int64).sum().item())
+    # ---- BASELINE configs[2] shape: multi-shape combinations (nested / adjacent / intersecting), resident render only
+    n_multi = n // 2
+    multi = synthetic_figure_scene(n_multi, 512, 512, seed=2000, kind='multi', first=env.rank * n_multi)
+    r.upload(multi, 'rgb')
+    for _ in range(3):
+        r.render_resident(out.data_ptr(), stream=env.st)
+    r.sync()
+    r.set_profiling(True)
+    for _ in range(max(2, args.steps // 2)):
+        r.render_resident(out.data_ptr(), stream=env.st)
+    r.sync()
+    mst = r.stats()
+    r.set_profiling(False)
+    (multi_ms,) = env.max_over_ranks(mst['cover_ms'] / max(1, mst['timed_launches']))
+    multi_info = {'value': env.world * n_multi / (multi_ms / 1e3), 'unit': 'images/s', 'images_per_step_per_gpu': n_multi,
+                  'ms_per_step': multi_ms, 'edges_per_image': mst['edges'] / n_multi, 'layers_per_image': mst['layers'] / n_multi,
+                  'hbm_frac': n_multi * IMG_BYTES / (multi_ms / 1e3) / 1e9 / fallback_peak()[0],
+                  'workload': 'BASELINE configs[2] shape: 2-3 outlined base patches, nested / adjacent / intersecting (synthetic), '
+                              'k_figure only, scenes resident in HBM'}
     del out
     torch.cuda.empty_cache()
 
@@ -388,7 +407,7 @@ def figure_leg(env, args, sampler):
     checksum = int(pinned[::257, 200:312, 200:312, 0].astype('int64').sum())
     res = {
         'value': value, 'ms_per_step': ms_max / args.steps, 'warmup': n_warm, 'clocks': clocks,
-        'launches': stats['kernel_launches'] - launches0, 'stats': stats, 'n': n,
+        'launches': stats['kernel_launches'] - launches0, 'stats': stats, 'n': n, 'multi_shape': multi_info,
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': png_bytes // e2e_steps,
                 'images_per_step_per_gpu': FIG_E2E, 'chunk': FIG_E2E_CHUNK, 'host_prepare_ms_per_chunk': st2['prepare_ms'],
                 'png_bytes_per_image': png_bytes / (e2e_steps * FIG_E2E), 'gpu_launches': e2e_launches,
@@ -628,7 +647,7 @@ def run_ours(args):
                 'metric': FIG_METRIC, 'value': fig['value'], 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': fig['warmup'], 'ms_per_step': fig['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': fig['config'], 'e2e': fig['e2e'],
-                'e2e_pixels': fig['e2e_pixels'], 'gpu_launches': fig['launches'],
+                'e2e_pixels': fig['e2e_pixels'], 'multi_shape': fig['multi_shape'], 'gpu_launches': fig['launches'],
                 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                              'traffic': traffic, 'kernel': 'k_figure', 'peak_source': peak_src, 'launches': stats['timed_launches'],
                              'images_per_launch': per_launch, 'figure_ms_per_step': stats['cover_ms'] / args.steps,
