@@ -35,7 +35,7 @@ PANELS_PER_STEP = 16384        # 12.9 GB of pixels per step per GPU: far larger 
 E2E_PANELS = 4096              # 3.2 GB pinned host destination per e2e step
 DEDUP_N = 1 << 20              # hashes in the all-pairs timing input (5.5e11 pairs)
 FIG_PER_STEP = 32768           # 25.8 GB of pixels per step per GPU
-FIG_E2E = 16384               # images per e2e step ...
+FIG_E2E = 32768               # images per e2e step (the whole step scene) ...
 FIG_E2E_CHUNK = 4096          # ... rendered + encoded 4096 at a time
 FIG_METRIC = 'rendered images/sec at 512x512 (multigraph single-shape variants)'
 FIG_WORKLOAD = ('BASELINE configs[1]: multigraph single-shape variants, synthetic (SURVEY 8d: one outlined base patch -- circle / '

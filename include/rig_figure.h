@@ -89,6 +89,9 @@ int rig_figure_render_batch(rig_figure_ctx *ctx, const rig_figure_scene *scene, 
 int rig_figure_upload(rig_figure_ctx *ctx, const rig_figure_scene *scene, int out_layout, void *stream);
 int rig_figure_render_resident(rig_figure_ctx *ctx, uint8_t *out_device, void *stream);
 int rig_figure_sync(rig_figure_ctx *ctx);
+/* The context's own stream (a cudaStream_t): what asynchronous calls run on when `stream` is NULL.  Hand it to a consumer of the
+ * rendered images (e.g. rig_png_encode) to order it after the render without a host synchronisation.                     */
+void *rig_figure_stream(rig_figure_ctx *ctx);
 
 typedef struct rig_figure_stats {
     uint64_t kernel_launches;   /* kernels launched by this context since creation */

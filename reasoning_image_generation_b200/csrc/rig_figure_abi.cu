@@ -350,6 +350,8 @@ int rig_figure_render_resident(rig_figure_ctx *c, uint8_t *out_device, void *str
     return launch(c, 0, (uint32_t)c->n_images, out_device, 0, stream ? (cudaStream_t)stream : c->stream);
 }
 
+void *rig_figure_stream(rig_figure_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
 int rig_figure_sync(rig_figure_ctx *c)
 {
     if (!c) return RIG_E_INVALID;

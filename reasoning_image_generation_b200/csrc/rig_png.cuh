@@ -565,52 +565,47 @@ __global__ void __launch_bounds__(256) k_png_assemble(const PngAssembleParams P)
         const uint8_t iend[12] = {0, 0, 0, 0, 'I', 'E', 'N', 'D', 0xae, 0x42, 0x60, 0x82};
         for (int i = 0; i < 12; i++) tail[10 + i] = iend[i];
     }
-    // copy this lane's pieces and take the CRC of its segment: lane 0 starts with "IDAT" + zlib header, lane 31 ends with
-    // the final block and the Adler-32
-    uint32_t crc = 0xffffffffu;
-    unsigned long long my_len = seg_bytes;
-    if (lane == 0) {
-        const uint8_t pre[6] = {'I', 'D', 'A', 'T', 0x78, 0x01};
-        for (int i = 0; i < 6; i++) crc = crc_t[(crc ^ pre[i]) & 0xffu] ^ (crc >> 8);
-        my_len += 6;
-    }
-    uint8_t *dst = body + (incl - seg_bytes);
-    for (uint32_t p = p0; p < p1; p++) {
-        const PngPiece pc = pcs[p];
-        const uint4 *src = (const uint4 *)(P.scratch + (size_t)pc.where * 16);
-        uint32_t left = pc.nbytes;
-        for (uint32_t q = 0; left; q++) {
-            const uint4 v = __ldg(src + q);
-            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    // ---- pass 1: the pieces, copied cooperatively (consecutive lanes write consecutive bytes of the file)
+    {
+        unsigned long long run = 0;                          // bytes of the pieces before this group of 32
+        for (uint32_t base = 0; base < ppi; base += 32u) {
+            const uint32_t p = base + (uint32_t)lane;
+            PngPiece pc;
+            pc.nbytes = 0; pc.where = 0; pc.a = 0; pc.b = 0;
+            if (p < ppi) pc = pcs[p];
+            uint32_t pre = pc.nbytes;
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                if ((uint32_t)k < left) {
-                    const uint32_t b = (wv[k >> 2] >> (8 * (k & 3))) & 0xffu;
-                    dst[k] = (uint8_t)b;
-                    crc = crc_t[(crc ^ b) & 0xffu] ^ (crc >> 8);
-                }
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
+                if (lane >= o) pre += t;
             }
-            const uint32_t step = left < 16u ? left : 16u;
-            dst += step;
-            left -= step;
+            const uint32_t cnt = min(32u, ppi - base);
+            for (uint32_t j = 0; j < cnt; j++) {
+                const uint32_t nb = __shfl_sync(0xffffffffu, pc.nbytes, (int)j), wh = __shfl_sync(0xffffffffu, pc.where, (int)j);
+                const uint32_t off = __shfl_sync(0xffffffffu, pre, (int)j) - nb;
+                const uint8_t *src = P.scratch + (size_t)wh * 16;
+                uint8_t *dst = body + run + off;
+                for (uint32_t i = (uint32_t)lane; i < nb; i += 32u) dst[i] = src[i];
+            }
+            run += __shfl_sync(0xffffffffu, pre, 31);
         }
     }
-    if (lane == 31) {
-        const uint8_t post[6] = {0x03, 0x00, (uint8_t)(adler >> 24), (uint8_t)(adler >> 16), (uint8_t)(adler >> 8), (uint8_t)adler};
-        for (int i = 0; i < 6; i++) crc = crc_t[(crc ^ post[i]) & 0xffu] ^ (crc >> 8);
-        my_len += 6;
-    }
+    __syncwarp();
+    // ---- pass 2: CRC-32 of "IDAT" + data: every lane takes a contiguous segment of the file (lane 0 the odd-sized first one),
+    //      then the 32 CRCs are combined in order: crc(A || B) = crc(A) * x^(8 len B) + crc(B)   (zlib crc32_combine)
+    const uint32_t crc_len = 4u + data_len;
+    const uint32_t seg = crc_len / 32u, first = crc_len - 31u * seg;
+    const uint8_t *cp = idat + 4 + (lane == 0 ? 0u : first + (uint32_t)(lane - 1) * seg);
+    const uint32_t my_len = lane == 0 ? first : seg;
+    uint32_t crc = 0xffffffffu;
+    for (uint32_t i = 0; i < my_len; i++) crc = crc_t[(crc ^ cp[i]) & 0xffu] ^ (crc >> 8);
     crc ^= 0xffffffffu;
-    // combine the 32 segment CRCs in order: crc(A || B) = crc(A) * x^(8 len B) + crc(B)   (zlib crc32_combine)
-    unsigned long long len = my_len;
+    uint32_t xpow = crc_x8n(x2n, seg);                       // x^(8 * seg): the right operand of level o is o segments long
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t rc = __shfl_down_sync(0xffffffffu, crc, o);
-        const unsigned long long rl = __shfl_down_sync(0xffffffffu, len, o);
-        if ((lane & (2 * o - 1)) == 0) {
-            if (rl) crc = crc_multmodp(crc_x8n(x2n, rl), crc) ^ rc;
-            len += rl;
-        }
+        if ((lane & (2 * o - 1)) == 0) crc = crc_multmodp(xpow, crc) ^ rc;
+        xpow = crc_multmodp(xpow, xpow);
     }
     if (lane == 0) put_be32(tail + 6, crc);
 }

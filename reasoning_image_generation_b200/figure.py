@@ -182,7 +182,7 @@ class RigFigureStats(ctypes.Structure):
 
 FIGURE_EXPORTS = ('rig_figure_create', 'rig_figure_destroy', 'rig_figure_last_error', 'rig_figure_render_batch',
                   'rig_figure_upload', 'rig_figure_render_resident', 'rig_figure_sync', 'rig_figure_get_stats',
-                  'rig_figure_set_profiling', 'rig_figure_debug_edges')
+                  'rig_figure_set_profiling', 'rig_figure_debug_edges', 'rig_figure_stream')
 
 _bound = False
 
@@ -206,6 +206,8 @@ def _lib():
         lib.rig_figure_render_resident.restype = ctypes.c_int
         lib.rig_figure_sync.argtypes = [vp]
         lib.rig_figure_sync.restype = ctypes.c_int
+        lib.rig_figure_stream.argtypes = [vp]
+        lib.rig_figure_stream.restype = vp
         lib.rig_figure_get_stats.argtypes = [vp, ctypes.POINTER(RigFigureStats)]
         lib.rig_figure_get_stats.restype = ctypes.c_int
         lib.rig_figure_set_profiling.argtypes = [vp, ctypes.c_int]
@@ -293,50 +295,71 @@ class FigureRenderer:
         with self._lock:
             self._check(self._lib.rig_figure_render_batch(self._h, ctypes.byref(s), out_ptr, 1, _LAYOUTS[layout], stream or None))
 
+    def stream(self) -> int:
+        """The context's own CUDA stream (what asynchronous calls run on when no stream is given)."""
+        return int(self._lib.rig_figure_stream(self._h) or 0)
+
     def iter_png(self, scene: FigureScene, encoder, chunk: int = 4096, overlap: bool = True):
         """``fig.savefig`` for a whole batch (multigraph_generation/generator.py:256): renders `chunk` figures at a time into
         the encoder's device staging buffer and encodes them there, so only PNG bytes cross PCIe.  Yields
         (first_image_index, buffer, offsets): file i of the chunk is buffer[offsets[i]:offsets[i + 1]] (pinned host memory,
-        valid until the next iteration).  With `overlap` the host path pipeline + rendering of chunk k + 1 run on a worker
-        thread while chunk k is encoded and copied (two halves of the staging buffer)."""
+        valid until the next iteration).  With `overlap` a worker thread runs the host path pipeline and launches k_figure
+        for the chunks ahead (two halves of the staging buffer) while this thread encodes and copies; the encoder is ordered
+        after each render on the GPU (the context's stream), not by a host synchronisation."""
+        import queue
         self._check_scene(scene)
         chunk = max(1, min(int(chunk), encoder.max_images, self.max_images))
         starts = list(range(0, scene.n_images, chunk))
         if not starts:
             return
         img_bytes = self.W * self.H * 3
-        base = encoder.staging(2 * chunk if (overlap and len(starts) > 1) else chunk)
+        two = overlap and len(starts) > 1
+        base = encoder.staging(2 * chunk if two else chunk)
+        fig_stream = self.stream()
 
         def sub_scene(i0):
             return scene if (i0 == 0 and scene.n_images <= chunk) else scene.slice(i0, min(scene.n_images, i0 + chunk))
 
-        def render(k, box):
-            try:
-                sub = sub_scene(starts[k])
-                ptr = base + (k & 1) * chunk * img_bytes if (overlap and len(starts) > 1) else base
-                self.render_to_device(sub, ptr, 'rgb', 0)
-                self.sync()              # rendered on the context's own stream: finish before the encoder reads
-                box.append((sub.n_images, ptr))
-            except BaseException as e:   # re-raised on the consumer's thread
-                box.append(e)
+        if not two:
+            for i0 in starts:
+                sub = sub_scene(i0)
+                self.render_to_device(sub, base, 'rgb', 0)
+                buf, off = encoder.encode(base, sub.n_images, 'rgb', fig_stream)
+                yield i0, buf, off
+            return
+        free = threading.Semaphore(2)            # staging halves the worker may render into
+        ready: 'queue.Queue' = queue.Queue()
+        stop = threading.Event()
 
-        box: list = []
-        render(0, box)
-        for k, i0 in enumerate(starts):
-            cur = box[0]
-            if isinstance(cur, BaseException):
-                raise cur
-            box, worker = [], None
-            if k + 1 < len(starts):
-                if overlap:
-                    worker = threading.Thread(target=render, args=(k + 1, box))
-                    worker.start()
-            buf, off = encoder.encode(cur[1], cur[0], 'rgb', 0)
-            if worker is not None:
-                worker.join()
-            yield i0, buf, off
-            if k + 1 < len(starts) and not overlap:
-                render(k + 1, box)
+        def worker():
+            try:
+                for k, i0 in enumerate(starts):
+                    free.acquire()
+                    if stop.is_set():
+                        return
+                    sub = sub_scene(i0)
+                    ptr = base + (k & 1) * chunk * img_bytes
+                    self.render_to_device(sub, ptr, 'rgb', 0)        # asynchronous: returns once k_figure is enqueued
+                    ready.put((i0, sub.n_images, ptr))
+            except BaseException as e:                               # re-raised on the consumer's thread
+                ready.put(e)
+
+        t = threading.Thread(target=worker, daemon=True)
+        t.start()
+        try:
+            for _ in starts:
+                item = ready.get()
+                if isinstance(item, BaseException):
+                    raise item
+                i0, n_img, ptr = item
+                buf, off = encoder.encode(ptr, n_img, 'rgb', fig_stream)
+                free.release()                                       # the encoder has read this half
+                yield i0, buf, off
+        finally:
+            stop.set()
+            free.release()
+            free.release()
+            t.join()
 
     def upload(self, scene: FigureScene, layout: str = 'rgb', stream: int = 0):
         self._check_scene(scene)
