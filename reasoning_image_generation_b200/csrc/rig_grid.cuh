@@ -88,16 +88,52 @@ __global__ void __launch_bounds__(128) k_grid_cells(const GridParams P)
 #pragma unroll
         for (int k = 0; k < GRID_MAX_TAPS; k++) wx[k] = __ldg(&tx->w[k]);
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        const int byte0 = tx_first * 3, base16 = byte0 & ~15, sw = (byte0 & 15) >> 2;
+        const uint32_t sh = 8u * (uint32_t)(byte0 & 3);
         for (int j = 0; j < ty_count; j++) {
-            const uint8_t *row = rows + (size_t)j * row_bytes + tx_first * 3;
             float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+            if (tx_count <= 8) {
+                // the span's (at most 24) bytes with three conflict-free 16-byte loads, re-aligned in registers: byte loads at a
+                // 16-byte stride between neighbouring threads would serialise four ways in shared memory
+                const uint4 *rp = (const uint4 *)(rows + (size_t)j * row_bytes + base16);
+                const uint4 A = rp[0], B = rp[1], C = rp[2];
+                uint32_t v[6];
+                switch (sw) {
+                case 0:
+                    v[0] = __funnelshift_r(A.x, A.y, sh); v[1] = __funnelshift_r(A.y, A.z, sh); v[2] = __funnelshift_r(A.z, A.w, sh);
+                    v[3] = __funnelshift_r(A.w, B.x, sh); v[4] = __funnelshift_r(B.x, B.y, sh); v[5] = __funnelshift_r(B.y, B.z, sh);
+                    break;
+                case 1:
+                    v[0] = __funnelshift_r(A.y, A.z, sh); v[1] = __funnelshift_r(A.z, A.w, sh); v[2] = __funnelshift_r(A.w, B.x, sh);
+                    v[3] = __funnelshift_r(B.x, B.y, sh); v[4] = __funnelshift_r(B.y, B.z, sh); v[5] = __funnelshift_r(B.z, B.w, sh);
+                    break;
+                case 2:
+                    v[0] = __funnelshift_r(A.z, A.w, sh); v[1] = __funnelshift_r(A.w, B.x, sh); v[2] = __funnelshift_r(B.x, B.y, sh);
+                    v[3] = __funnelshift_r(B.y, B.z, sh); v[4] = __funnelshift_r(B.z, B.w, sh); v[5] = __funnelshift_r(B.w, C.x, sh);
+                    break;
+                default:
+                    v[0] = __funnelshift_r(A.w, B.x, sh); v[1] = __funnelshift_r(B.x, B.y, sh); v[2] = __funnelshift_r(B.y, B.z, sh);
+                    v[3] = __funnelshift_r(B.z, B.w, sh); v[4] = __funnelshift_r(B.w, C.x, sh); v[5] = __funnelshift_r(C.x, C.y, sh);
+                    break;
+                }
 #pragma unroll
-            for (int k = 0; k < GRID_MAX_TAPS; k++) {
-                if (k >= tx_count) break;
-                const float a = wx[k];
-                b0 = __fadd_rn(b0, __fmul_rn((float)row[3 * k], a));
-                b1 = __fadd_rn(b1, __fmul_rn((float)row[3 * k + 1], a));
-                b2 = __fadd_rn(b2, __fmul_rn((float)row[3 * k + 2], a));
+                for (int k = 0; k < 8; k++) {
+                    if (k >= tx_count) break;
+                    const float a = wx[k];
+                    b0 = __fadd_rn(b0, __fmul_rn((float)((v[(3 * k) >> 2] >> (8 * ((3 * k) & 3))) & 0xffu), a));
+                    b1 = __fadd_rn(b1, __fmul_rn((float)((v[(3 * k + 1) >> 2] >> (8 * ((3 * k + 1) & 3))) & 0xffu), a));
+                    b2 = __fadd_rn(b2, __fmul_rn((float)((v[(3 * k + 2) >> 2] >> (8 * ((3 * k + 2) & 3))) & 0xffu), a));
+                }
+            } else {
+                const uint8_t *row = rows + (size_t)j * row_bytes + byte0;
+#pragma unroll
+                for (int k = 0; k < GRID_MAX_TAPS; k++) {
+                    if (k >= tx_count) break;
+                    const float a = wx[k];
+                    b0 = __fadd_rn(b0, __fmul_rn((float)row[3 * k], a));
+                    b1 = __fadd_rn(b1, __fmul_rn((float)row[3 * k + 1], a));
+                    b2 = __fadd_rn(b2, __fmul_rn((float)row[3 * k + 2], a));
+                }
             }
             const float beta = __ldg(&ty->w[j]);
             if (j == 0) { s0 = __fmul_rn(beta, b0); s1 = __fmul_rn(beta, b1); s2 = __fmul_rn(beta, b2); }

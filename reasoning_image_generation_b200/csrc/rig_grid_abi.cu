@@ -134,7 +134,7 @@ int rig_grid_create(int device, const rig_grid_layout *L, int max_samples, rig_g
     cudaDeviceProp prop;
     GCKC(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    c->cells_smem = (size_t)GRID_MAX_TAPS * L->panel_w * 3;
+    c->cells_smem = (size_t)GRID_MAX_TAPS * L->panel_w * 3 + 64;      // + slack: the 16-byte loads of the last span may run past the row
     if (c->cells_smem > prop.sharedMemPerBlockOptin) {
         gfail(c, RIG_E_UNSUPPORTED, "panel width %d needs %zu B of shared memory", L->panel_w, c->cells_smem);
         return bail(RIG_E_UNSUPPORTED);
