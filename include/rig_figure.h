@@ -92,6 +92,10 @@ int rig_figure_sync(rig_figure_ctx *ctx);
 /* The context's own stream (a cudaStream_t): what asynchronous calls run on when `stream` is NULL.  Hand it to a consumer of the
  * rendered images (e.g. rig_png_encode) to order it after the render without a host synchronisation.                     */
 void *rig_figure_stream(rig_figure_ctx *ctx);
+/* Records an event (a cudaEvent_t from a ring of 8, so the handle stays valid for the next 7 calls) behind everything enqueued
+ * on the context's stream so far, e.g. right after an asynchronous rig_figure_render_batch: a consumer waits on exactly that
+ * render (rig_png_wait_event), not on whatever another thread enqueues later.                                             */
+int rig_figure_fence(rig_figure_ctx *ctx, void **event_out);
 
 typedef struct rig_figure_stats {
     uint64_t kernel_launches;   /* kernels launched by this context since creation */

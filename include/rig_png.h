@@ -45,6 +45,9 @@ size_t rig_png_bound(const rig_png_ctx *ctx, int n);
 int rig_png_encode(rig_png_ctx *ctx, const uint8_t *imgs_dev, int n, int layout, uint8_t *out, size_t out_capacity,
                    uint64_t *offsets_host, int out_is_device, void *stream);
 
+/* Makes the encoder's stream wait for `event` (a cudaEvent_t, e.g. from rig_figure_fence) before the next rig_png_encode runs. */
+int rig_png_wait_event(rig_png_ctx *ctx, void *event);
+
 /* A device buffer of at least n * H * W * 3 bytes owned by the context (grown on demand, 16-byte aligned, valid until the
  * next rig_png_staging call or rig_png_destroy): a place to render into before encoding, for callers that have no device
  * allocator of their own.                                                                                             */

@@ -29,6 +29,8 @@ struct rig_figure_ctx {
     size_t smem = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fence[8] = {};
+    unsigned fence_next = 0;
     // resident scene
     FigurePrepared prep;
     std::vector<uint32_t> order;
@@ -329,6 +331,7 @@ void rig_figure_destroy(rig_figure_ctx *c)
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
     }
+    for (cudaEvent_t e : c->ev_fence) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -351,6 +354,17 @@ int rig_figure_render_resident(rig_figure_ctx *c, uint8_t *out_device, void *str
 }
 
 void *rig_figure_stream(rig_figure_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int rig_figure_fence(rig_figure_ctx *c, void **event_out)
+{
+    if (!c || !event_out) return RIG_E_INVALID;
+    FCK(c, cudaSetDevice(c->device));
+    cudaEvent_t &e = c->ev_fence[c->fence_next++ & 7u];
+    if (!e) FCK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    FCK(c, cudaEventRecord(e, c->stream));
+    *event_out = (void *)e;
+    return RIG_OK;
+}
 
 int rig_figure_sync(rig_figure_ctx *c)
 {

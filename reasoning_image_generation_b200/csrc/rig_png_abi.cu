@@ -245,6 +245,14 @@ int rig_png_encode(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, u
     return RIG_OK;
 }
 
+int rig_png_wait_event(rig_png_ctx *c, void *event)
+{
+    if (!c || !event) return RIG_E_INVALID;
+    PCK(c, cudaSetDevice(c->device));
+    PCK(c, cudaStreamWaitEvent(c->stream, (cudaEvent_t)event, 0));
+    return RIG_OK;
+}
+
 int rig_png_staging(rig_png_ctx *c, int n, uint8_t **out_dev)
 {
     if (!c || !out_dev || n < 0) return RIG_E_INVALID;

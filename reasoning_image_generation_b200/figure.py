@@ -182,7 +182,7 @@ class RigFigureStats(ctypes.Structure):
 
 FIGURE_EXPORTS = ('rig_figure_create', 'rig_figure_destroy', 'rig_figure_last_error', 'rig_figure_render_batch',
                   'rig_figure_upload', 'rig_figure_render_resident', 'rig_figure_sync', 'rig_figure_get_stats',
-                  'rig_figure_set_profiling', 'rig_figure_debug_edges', 'rig_figure_stream')
+                  'rig_figure_set_profiling', 'rig_figure_debug_edges', 'rig_figure_stream', 'rig_figure_fence')
 
 _bound = False
 
@@ -208,6 +208,8 @@ def _lib():
         lib.rig_figure_sync.restype = ctypes.c_int
         lib.rig_figure_stream.argtypes = [vp]
         lib.rig_figure_stream.restype = vp
+        lib.rig_figure_fence.argtypes = [vp, ctypes.POINTER(vp)]
+        lib.rig_figure_fence.restype = ctypes.c_int
         lib.rig_figure_get_stats.argtypes = [vp, ctypes.POINTER(RigFigureStats)]
         lib.rig_figure_get_stats.restype = ctypes.c_int
         lib.rig_figure_set_profiling.argtypes = [vp, ctypes.c_int]
@@ -299,13 +301,19 @@ class FigureRenderer:
         """The context's own CUDA stream (what asynchronous calls run on when no stream is given)."""
         return int(self._lib.rig_figure_stream(self._h) or 0)
 
+    def fence(self) -> int:
+        """An event handle behind everything enqueued on the context's stream so far (valid for the next 7 calls)."""
+        e = ctypes.c_void_p()
+        self._check(self._lib.rig_figure_fence(self._h, ctypes.byref(e)))
+        return int(e.value)
+
     def iter_png(self, scene: FigureScene, encoder, chunk: int = 4096, overlap: bool = True):
         """``fig.savefig`` for a whole batch (multigraph_generation/generator.py:256): renders `chunk` figures at a time into
         the encoder's device staging buffer and encodes them there, so only PNG bytes cross PCIe.  Yields
         (first_image_index, buffer, offsets): file i of the chunk is buffer[offsets[i]:offsets[i + 1]] (pinned host memory,
         valid until the next iteration).  With `overlap` a worker thread runs the host path pipeline and launches k_figure
         for the chunks ahead (two halves of the staging buffer) while this thread encodes and copies; the encoder is ordered
-        after each render on the GPU (the context's stream), not by a host synchronisation."""
+        after each render on the GPU (an event recorded right behind it), not by a host synchronisation."""
         import queue
         self._check_scene(scene)
         chunk = max(1, min(int(chunk), encoder.max_images, self.max_images))
@@ -315,7 +323,6 @@ class FigureRenderer:
         img_bytes = self.W * self.H * 3
         two = overlap and len(starts) > 1
         base = encoder.staging(2 * chunk if two else chunk)
-        fig_stream = self.stream()
 
         def sub_scene(i0):
             return scene if (i0 == 0 and scene.n_images <= chunk) else scene.slice(i0, min(scene.n_images, i0 + chunk))
@@ -324,7 +331,8 @@ class FigureRenderer:
             for i0 in starts:
                 sub = sub_scene(i0)
                 self.render_to_device(sub, base, 'rgb', 0)
-                buf, off = encoder.encode(base, sub.n_images, 'rgb', fig_stream)
+                encoder.wait_event(self.fence())
+                buf, off = encoder.encode(base, sub.n_images, 'rgb', 0)
                 yield i0, buf, off
             return
         free = threading.Semaphore(2)            # staging halves the worker may render into
@@ -340,7 +348,7 @@ class FigureRenderer:
                     sub = sub_scene(i0)
                     ptr = base + (k & 1) * chunk * img_bytes
                     self.render_to_device(sub, ptr, 'rgb', 0)        # asynchronous: returns once k_figure is enqueued
-                    ready.put((i0, sub.n_images, ptr))
+                    ready.put((i0, sub.n_images, ptr, self.fence()))
             except BaseException as e:                               # re-raised on the consumer's thread
                 ready.put(e)
 
@@ -351,8 +359,9 @@ class FigureRenderer:
                 item = ready.get()
                 if isinstance(item, BaseException):
                     raise item
-                i0, n_img, ptr = item
-                buf, off = encoder.encode(ptr, n_img, 'rgb', fig_stream)
+                i0, n_img, ptr, ev = item
+                encoder.wait_event(ev)                               # exactly this chunk's render, not what the worker enqueues next
+                buf, off = encoder.encode(ptr, n_img, 'rgb', 0)
                 free.release()                                       # the encoder has read this half
                 yield i0, buf, off
         finally:

@@ -26,7 +26,7 @@ class RigPngStats(ctypes.Structure):
 
 
 PNG_EXPORTS = ('rig_png_create', 'rig_png_destroy', 'rig_png_last_error', 'rig_png_bound', 'rig_png_encode', 'rig_png_get_stats',
-               'rig_png_set_profiling', 'rig_png_staging')
+               'rig_png_set_profiling', 'rig_png_staging', 'rig_png_wait_event')
 
 _bound = False
 _LAYOUTS = {'rgb': _abi.RIG_LAYOUT_RGB, 'bgr': _abi.RIG_LAYOUT_BGR}
@@ -47,6 +47,8 @@ def _lib():
         lib.rig_png_bound.restype = ctypes.c_size_t
         lib.rig_png_encode.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_size_t, vp, ctypes.c_int, vp]
         lib.rig_png_encode.restype = ctypes.c_int
+        lib.rig_png_wait_event.argtypes = [vp, vp]
+        lib.rig_png_wait_event.restype = ctypes.c_int
         lib.rig_png_staging.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp)]
         lib.rig_png_staging.restype = ctypes.c_int
         lib.rig_png_get_stats.argtypes = [vp, ctypes.POINTER(RigPngStats)]
@@ -117,6 +119,10 @@ class PngEncoder:
             self._check(rc)
         off = self._offsets[:n + 1]
         return self._pin.array[:int(off[n])], off
+
+    def wait_event(self, event: int):
+        """The next `encode` starts only after `event` (a cudaEvent_t handle, e.g. FigureRenderer.fence()) has completed on the GPU."""
+        self._check(self._lib.rig_png_wait_event(self._h, event))
 
     def staging(self, n: int) -> int:
         """Device pointer of a context-owned buffer for n images (render into it, then `encode` it)."""
