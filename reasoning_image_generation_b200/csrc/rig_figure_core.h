@@ -24,8 +24,8 @@ struct alignas(16) FEdge {
 };
 
 // One rasteriser pass (the face or the stroke of one artist): a closed set of edges and a colour.
-// Edges are grouped by the 16-row slab of their first row; dir[] (ndir entries, slabs from ymin) holds, per slab, the index
-// of the first edge that starts in or after it, so a band only looks at edges that can reach it.
+// Edges are sorted by their first row; dir[] (ndir entries, 16-row slabs from ymin) holds, per slab, the index of the
+// first edge that starts in or after it, so a band only looks at edges that can reach it.
 struct alignas(16) FLayer {
     uint32_t edge_begin, n_edges;
     uint32_t rgba;                   // r | g << 8 | b << 16 | a << 24, non-premultiplied, in output channel order
