@@ -367,7 +367,7 @@ def figure_leg(env, args, sampler):
     from reasoning_image_generation_b200.png import PngEncoder
     from reasoning_image_generation_b200.render import PinnedBuffer
     sub = scene.slice(0, FIG_E2E)
-    enc = PngEncoder(512, 512, device=env.local, max_images=FIG_E2E_CHUNK)
+    enc = PngEncoder(512, 512, device=env.local, max_images=FIG_E2E_CHUNK, channels=4)      # RGBA files, as fig.savefig writes them
     r2 = FigureRenderer(512, 512, device=env.local, max_images=FIG_E2E_CHUNK, max_artists=max(sub.n_artists, 1))
     png_bytes = 0
     for _ in range(2):
@@ -412,7 +412,7 @@ def figure_leg(env, args, sampler):
                 'images_per_step_per_gpu': FIG_E2E, 'chunk': FIG_E2E_CHUNK, 'host_prepare_ms_per_chunk': st2['prepare_ms'],
                 'png_bytes_per_image': png_bytes / (e2e_steps * FIG_E2E), 'gpu_launches': e2e_launches,
                 'note': 'FigureRenderer.iter_png = fig.savefig for a batch: host artist arrays in (path pipeline on host threads, '
-                        'edges uploaded), k_figure, device-side PNG encode, finished PNG files copied to pinned host memory; host '
+                        'edges uploaded), k_figure, device-side PNG encode (RGBA files), finished files copied to pinned host memory; host '
                         'work of chunk k + 1 overlaps GPU work of chunk k; digest %d' % digest},
         'e2e_pixels': {'value': px_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d // max(1, FIG_E2E // FIG_E2E_CHUNK),
                        'd2h_bytes_per_step': FIG_E2E_CHUNK * IMG_BYTES, 'images_per_step_per_gpu': FIG_E2E_CHUNK,

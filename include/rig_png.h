@@ -7,7 +7,7 @@
  * At GPU render rates that is the end-to-end bottleneck twice over: host zlib, and before it the PCIe copy of 786 KB of
  * raw pixels per image.  These entry points encode the images where they are rendered: filter (Sub), LZ77 restricted to
  * zero runs, fixed-Huffman deflate, Adler-32 and CRC-32 all run in CUDA kernels, and only the finished PNG byte streams
- * (typically 5-20 KB per 512 x 512 image of this data set) cross PCIe.  The streams are standard PNG (8-bit RGB, one IDAT
+ * (typically 5-20 KB per 512 x 512 image of this data set) cross PCIe.  The streams are standard PNG (8-bit RGB or RGBA, one IDAT
  * chunk, zlib stream of byte-aligned fixed-Huffman blocks): any decoder reads them; they are NOT byte-identical to what
  * libpng would write, and the parity criterion is that they decode to exactly the rendered pixels.
  * Plain C types only; every function returns 0 or a negative RIG_E_* code (include/rig.h).
@@ -26,8 +26,11 @@ extern "C" {
 
 typedef struct rig_png_ctx rig_png_ctx;
 
-/* Context on CUDA device `device` for W x H x 3 images (W a multiple of 16), at most max_images per call. */
-int rig_png_create(int device, int W, int H, int max_images, rig_png_ctx **out);
+/* Context on CUDA device `device` for W x H x 3 images (W a multiple of 16), at most max_images per call.
+ * channels = 3: RGB files (8-bit colour type 2, what cv2.imwrite writes for a 3-channel array);
+ * channels = 4: RGBA files (colour type 6) with alpha 255 everywhere -- the format fig.savefig writes, Agg's canvas being RGBA and
+ *               opaque (multigraph_generation/generator.py:256).  The input images are 3 bytes per pixel either way.           */
+int rig_png_create(int device, int W, int H, int max_images, int channels, rig_png_ctx **out);
 void rig_png_destroy(rig_png_ctx *ctx);
 const char *rig_png_last_error(const rig_png_ctx *ctx);
 

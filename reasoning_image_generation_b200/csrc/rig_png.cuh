@@ -21,7 +21,7 @@ namespace rig {
 #define PNG_PIECE_ROWS 2
 #endif
 constexpr int PNG_ROWS = PNG_PIECE_ROWS;
-constexpr int PNG_CHUNK = 48;                 // bytes per lane per pass = 16 pixels
+constexpr int PNG_CHUNK_PX = 16;              // pixels per lane per pass: 48 filtered bytes (RGB files) or 64 (RGBA files)
 constexpr uint32_t PNG_SLOT = 512;            // bytes reserved per piece; larger pieces go to the overflow arena
 constexpr uint32_t PNG_FILE_OVERHEAD = 65;    // signature 8 + IHDR 25 + IDAT 12 + zlib header 2 + final block 2 + Adler 4 + IEND 12
 constexpr uint32_t ADLER_MOD = 65521u;
@@ -39,9 +39,9 @@ struct PngTables {
     uint8_t header[33];  // signature + IHDR chunk of this context's W x H
 };
 
-__host__ __device__ inline size_t png_piece_buf_bytes(int W)   // worst case of one piece, + tail, rounded to 16
+__host__ __device__ inline size_t png_piece_buf_bytes(int W, int ch)   // worst case of one piece, + tail, rounded to 16
 {
-    const size_t bits = (size_t)PNG_ROWS * (1 + 3 * (size_t)W) * 9 + 64;
+    const size_t bits = (size_t)PNG_ROWS * (1 + (size_t)ch * W) * 9 + 64;
     return ((bits + 7) / 8 + 8 + 15) & ~(size_t)15;
 }
 
@@ -75,7 +75,7 @@ __device__ __forceinline__ void png_match(uint32_t len, uint32_t &code, int &nbi
 
 // single-walk sink: the lane's bits go to its own staging words; they are moved to the piece buffer once the warp scan has
 // placed them
-constexpr int PNG_STAGE_WORDS = 20;      // >= (48 * 9 + 8 + 8 * 13 + 18 + 31) / 32 bits a chunk can need
+constexpr int PNG_STAGE_WORDS = 24;      // >= (64 * 9 + 8 + 8 * 13 + 18 + 31) / 32 bits a chunk can need
 struct PngStage {
     uint32_t *stage;
     unsigned long long acc = 0;
@@ -139,20 +139,20 @@ __device__ __forceinline__ void png_zero_matches(Sink &s, uint32_t r, const PngL
 // The tokens of one lane's chunk.  nz: bit i set = filtered byte i is non-zero; fb: the chunk's filtered bytes (shared memory);
 // skip: leading zeros that belong to a run an earlier lane emits; tail_extra: zeros after this chunk that continue its trailing
 // run (all-zero lanes that follow, plus the leading zeros of the lane after them).
-template <class Sink>
+template <int CHUNK, class Sink>
 __device__ __forceinline__ void png_chunk_tokens(Sink &s, unsigned long long nz, const uint8_t *fb, int skip, uint32_t tail_extra, bool filter_byte,
                                                  const PngLut &T)
 {
     if (filter_byte) s.put(T.lit[1] & 0xffffffu, 8);          // filter type 1 (Sub) opens the row
     int pos = skip;
-    while (pos < PNG_CHUNK) {
+    while (pos < CHUNK) {
         const unsigned long long rem = nz >> pos;
         if (rem & 1ull) {
             const uint32_t t = T.lit[fb[pos]];
             s.put(t & 0xffffffu, (int)(t >> 24));
             pos++;
         } else {
-            const int gap = rem ? (__ffsll((long long)rem) - 1) : (PNG_CHUNK - pos);
+            const int gap = rem ? (__ffsll((long long)rem) - 1) : (CHUNK - pos);
             uint32_t r = (uint32_t)gap;
             if (!rem) r += tail_extra;
             s.put(T.lit[0] & 0xffffffu, 8);                    // the run's first zero is a literal
@@ -164,7 +164,7 @@ __device__ __forceinline__ void png_chunk_tokens(Sink &s, unsigned long long nz,
 
 struct PngParams {
     const uint8_t *imgs;
-    int n, W, H, bgr;
+    int n, W, H, bgr;               // bgr: channel order of the input images
     uint32_t pieces_per_image;
     PngPiece *pieces;
     uint8_t *scratch;               // [n * pieces_per_image * PNG_SLOT][overflow arena]
@@ -172,8 +172,8 @@ struct PngParams {
     unsigned long long *counters;   // [0] overflow arena cursor, [1] error flag
 };
 
-// shared memory per warp: bit buffer + 32 x 48 filtered bytes + the bits of an all-white row
-__host__ __device__ inline size_t png_warp_smem(int W) { return png_piece_buf_bytes(W) + 32 * PNG_CHUNK + 32 * 4 * PNG_STAGE_WORDS + 32; }
+// shared memory per warp: bit buffer + 32 chunks of filtered bytes + staging words + the bits of an all-white row
+__host__ __device__ inline size_t png_warp_smem(int W, int ch) { return png_piece_buf_bytes(W, ch) + 32 * PNG_CHUNK_PX * ch + 32 * 4 * PNG_STAGE_WORDS + 32; }
 
 // ORs the nbits bits that start at bit src_start of src into dst at bit dst_pos (dst is zero there); lanes share the words
 __device__ __forceinline__ void png_copy_bits(uint32_t *dst, uint32_t dst_pos, const uint32_t *src, uint32_t src_start, uint32_t nbits, int lane)
@@ -189,21 +189,25 @@ __device__ __forceinline__ void png_copy_bits(uint32_t *dst, uint32_t dst_pos, c
     }
 }
 
+// CH = 3: RGB files (what cv2.imwrite writes for the panels); CH = 4: RGBA files with alpha 255 (what fig.savefig writes: Agg's
+// canvas is RGBA and opaque).  The input images are 3 bytes per pixel either way.
+template <int CH>
 __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
 {
+    constexpr int CHUNK = PNG_CHUNK_PX * CH, FW = CHUNK / 4;      // filtered bytes / words per lane chunk
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ PngLut lut;
     png_fill_lut(lut);
     __syncthreads();
     const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t per_warp = png_warp_smem(P.W);
+    const size_t per_warp = png_warp_smem(P.W, CH), bufb = png_piece_buf_bytes(P.W, CH);
     uint32_t *buf = (uint32_t *)(smem + (size_t)warp * per_warp);
-    uint8_t *fbytes = (uint8_t *)buf + png_piece_buf_bytes(P.W) + lane * PNG_CHUNK;
-    uint32_t *stage = (uint32_t *)((uint8_t *)buf + png_piece_buf_bytes(P.W) + 32 * PNG_CHUNK) + lane * PNG_STAGE_WORDS;
-    uint32_t *wrow = (uint32_t *)((uint8_t *)buf + png_piece_buf_bytes(P.W) + 32 * PNG_CHUNK + 32 * 4 * PNG_STAGE_WORDS);
-    const int row_bytes = 3 * P.W, chunks = P.W / 16;
-    const uint32_t RL = 1u + (uint32_t)row_bytes;
-    const uint32_t buf_words = (uint32_t)(png_piece_buf_bytes(P.W) / 4);
+    uint8_t *fbytes = (uint8_t *)buf + bufb + lane * CHUNK;
+    uint32_t *stage = (uint32_t *)((uint8_t *)buf + bufb + 32 * CHUNK) + lane * PNG_STAGE_WORDS;
+    uint32_t *wrow = (uint32_t *)((uint8_t *)buf + bufb + 32 * CHUNK + 32 * 4 * PNG_STAGE_WORDS);
+    const int row_bytes = 3 * P.W, chunks = P.W / 16;            // input rows: packed RGB
+    const uint32_t RL = 1u + (uint32_t)(CH * P.W);                // filtered bytes per row of the file
+    const uint32_t buf_words = (uint32_t)(bufb / 4);
     const bool one_pass = chunks <= 32;        // rows of up to 512 pixels: a row that repeats the row above copies its bits
     // the bits of an all-white row (what most rows of this data set are): the virtual "row above" of every piece
     uint32_t white_bits = 0;
@@ -219,9 +223,9 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
             int nb;
             em.put(png_rev(0x30u + 1u, 8), 8);
             png_literal(255u, code, nb);
-            em.put(code, nb); em.put(code, nb); em.put(code, nb);
+            for (int q = 0; q < CH; q++) em.put(code, nb);
             em.put(png_rev(0x30u, 8), 8);
-            png_zero_matches(em, (uint32_t)row_bytes - 4u, lut);
+            png_zero_matches(em, RL - 1u - (uint32_t)CH - 1u, lut);
             white_bits = em.pos;
         }
         white_bits = __shfl_sync(0xffffffffu, white_bits, 0);
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
         uint32_t pw[12];
 #pragma unroll
         for (int i = 0; i < 12; i++) pw[i] = 0xffffffffu;
-        uint32_t p_s0 = lane == 0 ? 765u : 0u, p_s1 = lane == 0 ? 765u : 0u;
+        uint32_t p_s0 = lane == 0 ? 255u * CH : 0u, p_s1 = lane == 0 ? 255u * (CH * (CH - 1) / 2) : 0u;
         const uint32_t *p_src = wrow;
         uint32_t p_start = 0, p_bits = white_bits;
         for (int y = y0; y < y1; y++) {
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
 #pragma unroll
                 for (int i = 0; i < 12; i++) w[i] = 0xffffffffu;
                 if (live) {
-                    const uint4 *src = (const uint4 *)(img + (size_t)y * row_bytes + (size_t)c * PNG_CHUNK);
+                    const uint4 *src = (const uint4 *)(img + (size_t)y * row_bytes + (size_t)c * 48);
                     const uint4 a = __ldg(src), b = __ldg(src + 1), d = __ldg(src + 2);
                     w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
                     w[8] = d.x; w[9] = d.y; w[10] = d.z; w[11] = d.w;
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
                         }
                     }
                 }
-                const uint32_t base = row_pos + 1u + (uint32_t)c * PNG_CHUNK;
+                const uint32_t base = row_pos + 1u + (uint32_t)c * CHUNK;
                 if (one_pass) {
                     uint32_t diff = 0u;
 #pragma unroll
@@ -302,20 +306,39 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
                     f[i] = __vsub4(w[i], left);
                     any |= f[i];
                 }
+                // the file's filtered bytes: the RGB deltas, for RGBA files with a zero alpha delta per pixel (255 for the row's
+                // first pixel, whose left neighbour counts as 0)
+                uint32_t g[FW];
+                if (CH == 3) {
+#pragma unroll
+                    for (int i = 0; i < 12; i++) g[i] = f[i];
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t f0 = f[3 * q], f1 = f[3 * q + 1], f2 = f[3 * q + 2];
+                        g[(4 * q) % FW] = f0 & 0x00ffffffu;
+                        g[(4 * q + 1) % FW] = __byte_perm(f0, f1, 0x0543) & 0x00ffffffu;
+                        g[(4 * q + 2) % FW] = __byte_perm(f1, f2, 0x0432) & 0x00ffffffu;
+                        g[(4 * q + 3) % FW] = f2 >> 8;
+                    }
+                    if (lane == 0 && c0 == 0) g[0] |= 0xff000000u;
+                    any = 0u;
+#pragma unroll
+                    for (int i = 0; i < FW; i++) any |= g[i];
+                }
                 // zero structure of the chunk
                 unsigned long long nz = 0ull;
                 uint32_t s0 = 0, s1 = 0;
                 if (any && live) {                                  // (a dead lane's chunk is all zeros but its left neighbour is not)
 #pragma unroll
-                    for (int i = 0; i < 12; i++) {
-                        const uint32_t m = __vsetne4(f[i], 0u);       // 1 per non-zero byte
+                    for (int i = 0; i < FW; i++) {
+                        const uint32_t m = __vsetne4(g[i], 0u);       // 1 per non-zero byte
                         const uint32_t nib = (m & 1u) | ((m >> 7) & 2u) | ((m >> 14) & 4u) | ((m >> 21) & 8u);
                         nz |= (unsigned long long)nib << (4 * i);
                     }
                     uint4 *dst = (uint4 *)fbytes;
-                    dst[0] = make_uint4(f[0], f[1], f[2], f[3]);
-                    dst[1] = make_uint4(f[4], f[5], f[6], f[7]);
-                    dst[2] = make_uint4(f[8], f[9], f[10], f[11]);
+#pragma unroll
+                    for (int i = 0; i < FW / 4; i++) dst[i] = make_uint4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
                     // Adler partial sums of this chunk
                     unsigned long long m = nz;
                     while (m) {
@@ -329,9 +352,9 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
                     ad_b += (unsigned long long)(L - base) * s0 - s1;
                 }
                 p_s0 = s0; p_s1 = s1;
-                const int lead = live ? (nz ? (__ffsll((long long)nz) - 1) : PNG_CHUNK) : 0;      // leading zeros
+                const int lead = live ? (nz ? (__ffsll((long long)nz) - 1) : CHUNK) : 0;      // leading zeros
                 const bool all_zero = live && nz == 0ull;
-                const bool last_zero = live && !((nz >> (PNG_CHUNK - 1)) & 1ull);
+                const bool last_zero = live && !((nz >> (CHUNK - 1)) & 1ull);
                 const uint32_t zmask = __ballot_sync(0xffffffffu, all_zero);
                 const uint32_t prev_last_zero = __shfl_up_sync(0xffffffffu, (uint32_t)last_zero, 1);
                 const int skip = (lane > 0 && prev_last_zero) ? lead : 0;
@@ -342,17 +365,17 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
                     const int run = lane == 31 ? 0 : (__ffs((int)~after) - 1);          // consecutive all-zero lanes that follow
                     const int nxt = lane + 1 + run;
                     const int nxt_lead = __shfl_sync(0xffffffffu, lead, nxt & 31);
-                    tail_extra = (uint32_t)run * PNG_CHUNK + ((nxt < 32) ? (uint32_t)nxt_lead : 0u);
+                    tail_extra = (uint32_t)run * CHUNK + ((nxt < 32) ? (uint32_t)nxt_lead : 0u);
                 }
                 __syncwarp();
-                const bool mine = live && skip < PNG_CHUNK;          // a fully skipped chunk emits nothing
+                const bool mine = live && skip < CHUNK;          // a fully skipped chunk emits nothing
                 const bool fbyte = lane == 0 && c0 == 0;
                 // one walk: tokens into the lane's staging words, a warp scan of the bit counts, then a shifted move
                 uint32_t nbits_mine = 0;
                 if (mine || fbyte) {
                     PngStage sg;
                     sg.stage = stage;
-                    png_chunk_tokens(sg, nz, fbytes, mine ? skip : PNG_CHUNK, tail_extra, fbyte, lut);
+                    png_chunk_tokens<CHUNK>(sg, nz, fbytes, mine ? skip : CHUNK, tail_extra, fbyte, lut);
                     nbits_mine = sg.finish();
                 }
                 uint32_t incl = nbits_mine;
@@ -497,7 +520,7 @@ struct PngAssembleParams {
     const unsigned long long *offsets;
     const PngTables *tables;
     uint8_t *out;
-    int n, W, H;
+    int n, W, H, ch;
     uint32_t pieces_per_image;
 };
 
@@ -520,7 +543,7 @@ __global__ void __launch_bounds__(256) k_png_assemble(const PngAssembleParams P)
     uint8_t *file = P.out + P.offsets[img];
     const unsigned long long total = P.offsets[img + 1] - P.offsets[img];
     const uint32_t data_len = (uint32_t)(total - PNG_FILE_OVERHEAD) + 8u;       // zlib header + pieces + final block + Adler
-    const uint32_t RL = 1u + 3u * (uint32_t)P.W;
+    const uint32_t RL = 1u + (uint32_t)(P.ch * P.W);
     const unsigned long long ulen = (unsigned long long)P.H * RL;               // uncompressed (filtered) bytes
     // lane l owns pieces [l * ppl, (l + 1) * ppl): a contiguous segment of the file
     const uint32_t ppl = (ppi + 31u) / 32u;

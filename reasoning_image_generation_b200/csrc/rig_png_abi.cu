@@ -28,7 +28,7 @@ uint32_t host_multmodp(uint32_t a, uint32_t b)
 }  // namespace
 
 struct rig_png_ctx {
-    int device = 0, W = 0, H = 0, max_images = 0;
+    int device = 0, W = 0, H = 0, max_images = 0, ch = 3;
     uint32_t ppi = 0;
     int wpc = 4, sm_count = 1, ctas_per_sm = 1;
     size_t smem = 0;
@@ -70,17 +70,18 @@ size_t rig_png_bound(const rig_png_ctx *c, int n)
 {
     if (!c || n <= 0) return 0;
     // literal-only worst case: 9 bits per filtered byte, plus per-piece and per-file framing
-    const size_t per_piece = ((size_t)PNG_ROWS * (1 + 3 * (size_t)c->W) * 9 + 7) / 8 + 8;
+    const size_t per_piece = ((size_t)PNG_ROWS * (1 + (size_t)c->ch * c->W) * 9 + 7) / 8 + 8;
     return (size_t)n * ((size_t)c->ppi * per_piece + PNG_FILE_OVERHEAD);
 }
 
-int rig_png_create(int device, int W, int H, int max_images, rig_png_ctx **out)
+int rig_png_create(int device, int W, int H, int max_images, int channels, rig_png_ctx **out)
 {
     if (!out) return pfail(nullptr, RIG_E_INVALID, "out is NULL");
     *out = nullptr;
     if (W <= 0 || H <= 0 || W % 16 || W > 4096 || H > 4096)
         return pfail(nullptr, RIG_E_INVALID, "unsupported image %dx%d (W %% 16 == 0, <= 4096)", W, H);
     if (max_images <= 0) return pfail(nullptr, RIG_E_INVALID, "max_images must be positive");
+    if (channels != 3 && channels != 4) return pfail(nullptr, RIG_E_INVALID, "channels must be 3 (RGB files) or 4 (RGBA files)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -88,7 +89,7 @@ int rig_png_create(int device, int W, int H, int max_images, rig_png_ctx **out)
                      e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return pfail(nullptr, RIG_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
     rig_png_ctx *c = new rig_png_ctx();
-    c->device = device; c->W = W; c->H = H; c->max_images = max_images;
+    c->device = device; c->W = W; c->H = H; c->max_images = max_images; c->ch = channels;
     c->ppi = (uint32_t)((H + PNG_ROWS - 1) / PNG_ROWS);
     auto bail = [&](int code) {
         snprintf(g_png_create_err, sizeof g_png_create_err, "%s", c->err);
@@ -106,16 +107,28 @@ int rig_png_create(int device, int W, int H, int max_images, rig_png_ctx **out)
     PCKC(cudaSetDevice(device));
     cudaDeviceProp prop;
     PCKC(cudaGetDeviceProperties(&prop, device));
-    c->wpc = 8;
-    while (c->wpc > 1 && c->wpc * png_warp_smem(W) > 96 * 1024) c->wpc--;
-    c->smem = c->wpc * png_warp_smem(W);
+    // warps per CTA: the largest CTA of which three still fit an SM (measured, profiles/r1_notes.md: fewer, larger CTAs lose
+    // occupancy to the register file; many small ones pay the per-CTA token tables more often), else two, else one
+    {
+        const size_t per_warp = png_warp_smem(W, channels), sm_bytes = prop.sharedMemPerMultiprocessor;
+        int best = 1;
+        for (int want = 3; want >= 1 && best == 1; want--)
+            for (int w = 8; w >= 1; w--) {
+                const size_t cta = (size_t)w * per_warp + 3072 + 1024;      // + the static token tables + the per-CTA reservation
+                if (cta <= prop.sharedMemPerBlockOptin && sm_bytes / cta >= (size_t)want) { best = w; break; }
+            }
+        c->wpc = best;
+        if (const char *ev = getenv("RIG_PNG_WPC")) { const int w = atoi(ev); if (w >= 1 && w <= 8) c->wpc = w; }
+    }
+    c->smem = c->wpc * png_warp_smem(W, channels);
     c->sm_count = prop.multiProcessorCount;
-    c->ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (c->wpc * 32), (prop.sharedMemPerMultiprocessor - 2048) / (c->smem + 1024)));
+    c->ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (c->wpc * 32), prop.sharedMemPerMultiprocessor / (c->smem + 3072 + 1024)));
     if (c->smem > prop.sharedMemPerBlockOptin) {
         pfail(c, RIG_E_UNSUPPORTED, "image width %d needs %zu B of shared memory per piece", W, c->smem);
         return bail(RIG_E_UNSUPPORTED);
     }
-    PCKC(cudaFuncSetAttribute(k_png_pieces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+    if (channels == 3) PCKC(cudaFuncSetAttribute(k_png_pieces<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+    else PCKC(cudaFuncSetAttribute(k_png_pieces<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
     PCKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     PCKC(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
     PCKC(cudaEventCreate(&c->ev0));
@@ -136,7 +149,7 @@ int rig_png_create(int device, int W, int H, int max_images, rig_png_ctx **out)
         memcpy(h + 4, "IHDR", 4);
         h[8] = (uint8_t)(W >> 24); h[9] = (uint8_t)(W >> 16); h[10] = (uint8_t)(W >> 8); h[11] = (uint8_t)W;
         h[12] = (uint8_t)(H >> 24); h[13] = (uint8_t)(H >> 16); h[14] = (uint8_t)(H >> 8); h[15] = (uint8_t)H;
-        h[16] = 8; h[17] = 2; h[18] = 0; h[19] = 0; h[20] = 0;      // 8-bit RGB, deflate, adaptive filtering, no interlace
+        h[16] = 8; h[17] = channels == 4 ? 6 : 2; h[18] = 0; h[19] = 0; h[20] = 0;      // 8-bit RGB / RGBA, deflate, adaptive filtering, no interlace
         uint32_t crc = 0xffffffffu;
         for (int i = 4; i < 21; i++) crc = T.crc[(crc ^ h[i]) & 0xff] ^ (crc >> 8);
         crc ^= 0xffffffffu;
@@ -199,7 +212,8 @@ int rig_png_encode(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, u
         // persistent warps: every warp prepares the bits of a white row once, then walks pieces with a grid stride
         const unsigned long long want = (npieces + c->wpc - 1) / c->wpc;
         const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)c->sm_count * c->ctas_per_sm);
-        k_png_pieces<<<grid, c->wpc * 32, c->smem, st>>>(P);
+        if (c->ch == 3) k_png_pieces<3><<<grid, c->wpc * 32, c->smem, st>>>(P);
+        else k_png_pieces<4><<<grid, c->wpc * 32, c->smem, st>>>(P);
     }
     k_png_sizes<<<(n + 7) / 8, 256, 0, st>>>(c->d_pieces, n, c->ppi, c->d_sizes);
     k_png_scan<<<1, 1024, 0, st>>>(c->d_sizes, n, c->d_offsets);
@@ -225,7 +239,7 @@ int rig_png_encode(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, u
     }
     PngAssembleParams A;
     A.pieces = c->d_pieces; A.scratch = c->d_scratch; A.offsets = c->d_offsets; A.tables = c->d_tables; A.out = dev_out;
-    A.n = n; A.W = c->W; A.H = c->H; A.pieces_per_image = c->ppi;
+    A.n = n; A.W = c->W; A.H = c->H; A.ch = c->ch; A.pieces_per_image = c->ppi;
     k_png_assemble<<<(n + 7) / 8, 256, 0, st>>>(A);
     c->stats.kernel_launches++;
     PCK(c, cudaGetLastError());

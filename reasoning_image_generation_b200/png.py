@@ -37,7 +37,7 @@ def _lib():
     lib = _abi.load()
     if not _bound:
         vp = ctypes.c_void_p
-        lib.rig_png_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+        lib.rig_png_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
         lib.rig_png_create.restype = ctypes.c_int
         lib.rig_png_destroy.argtypes = [vp]
         lib.rig_png_destroy.restype = None
@@ -68,11 +68,14 @@ class PngError(RuntimeError):
 class PngEncoder:
     """One CUDA context-bound PNG writer for W x H x 3 images (one per process per GPU)."""
 
-    def __init__(self, W: int = 512, H: int = 512, device: int = 0, max_images: int = 4096, host_capacity: Optional[int] = None):
+    def __init__(self, W: int = 512, H: int = 512, device: int = 0, max_images: int = 4096, host_capacity: Optional[int] = None,
+                 channels: int = 3):
+        """channels=3: RGB files (cv2.imwrite of a 3-channel array); channels=4: RGBA files with alpha 255, the format
+        fig.savefig writes.  The device images are 3 bytes per pixel either way."""
         self._lib = _lib()
-        self.W, self.H, self.device, self.max_images = int(W), int(H), int(device), int(max_images)
+        self.W, self.H, self.device, self.max_images, self.channels = int(W), int(H), int(device), int(max_images), int(channels)
         h = ctypes.c_void_p()
-        rc = self._lib.rig_png_create(self.device, self.W, self.H, self.max_images, ctypes.byref(h))
+        rc = self._lib.rig_png_create(self.device, self.W, self.H, self.max_images, self.channels, ctypes.byref(h))
         if rc:
             raise PngError(rc, (self._lib.rig_png_last_error(None) or b'').decode())
         self._h = h
@@ -154,12 +157,12 @@ def write_files(buf: np.ndarray, offsets: np.ndarray, paths: Sequence[str]):
 
 def decode_png_strict(data: bytes) -> np.ndarray:
     """A small, strict PNG reader used by the tests (not a product path): checks the signature, every chunk CRC, the zlib
-    Adler-32 (via zlib) and undoes the row filters; returns uint8[H, W, 3]."""
+    Adler-32 (via zlib) and undoes the row filters; returns uint8[H, W, 3] (RGB files) or uint8[H, W, 4] (RGBA files)."""
     import struct
     import zlib
     assert data[:8] == b'\x89PNG\r\n\x1a\n', 'bad signature'
     pos, idat, W = 8, b'', None
-    H = 0
+    H, ch = 0, 3
     while pos < len(data):
         (ln,), typ = struct.unpack('>I', data[pos:pos + 4]), data[pos + 4:pos + 8]
         body = data[pos + 8:pos + 8 + ln]
@@ -167,25 +170,26 @@ def decode_png_strict(data: bytes) -> np.ndarray:
         assert zlib.crc32(typ + body) & 0xffffffff == crc, f'bad CRC in {typ!r}'
         if typ == b'IHDR':
             W, H, depth, ctype, comp, flt, inter = struct.unpack('>IIBBBBB', body)
-            assert (depth, ctype, comp, flt, inter) == (8, 2, 0, 0, 0)
+            assert (depth, comp, flt, inter) == (8, 0, 0, 0) and ctype in (2, 6)
+            ch = 3 if ctype == 2 else 4
         elif typ == b'IDAT':
             idat += body
         elif typ == b'IEND':
             assert pos + 12 + ln == len(data), 'bytes after IEND'
         pos += 12 + ln
     raw = zlib.decompress(idat)
-    stride = 1 + 3 * W
+    stride = 1 + ch * W
     assert len(raw) == H * stride
     rows = np.frombuffer(raw, np.uint8).reshape(H, stride)
-    out = np.zeros((H, W * 3), np.uint8)
+    out = np.zeros((H, W * ch), np.uint8)
     for y in range(H):
         ft, line = rows[y, 0], rows[y, 1:].astype(np.int64)
         if ft == 0:
             out[y] = line
         elif ft == 1:
-            out[y] = (np.cumsum(line.reshape(W, 3), axis=0) % 256).reshape(-1)
+            out[y] = (np.cumsum(line.reshape(W, ch), axis=0) % 256).reshape(-1)
         elif ft == 2:
             out[y] = (line + (out[y - 1] if y else 0)) % 256
         else:
             raise AssertionError(f'filter type {ft} not written by this encoder')
-    return out.reshape(H, W, 3)
+    return out.reshape(H, W, ch)

@@ -9,12 +9,12 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _encode(imgs, layout='rgb'):
+def _encode(imgs, layout='rgb', channels=3):
     import torch
     from reasoning_image_generation_b200.png import PngEncoder, split_files
     n, H, W, _ = imgs.shape
     t = torch.from_numpy(np.ascontiguousarray(imgs)).cuda()
-    enc = PngEncoder(W, H, max_images=max(n, 1))
+    enc = PngEncoder(W, H, max_images=max(n, 1), channels=channels)
     buf, off = enc.encode(t.data_ptr(), n, layout)
     files = split_files(buf, off)
     st = enc.stats()
@@ -28,9 +28,13 @@ def _check(files, imgs_rgb):
     assert len(files) == len(imgs_rgb)
     for f, ref in zip(files, imgs_rgb):
         got = decode_png_strict(f)
-        assert got.shape == ref.shape and (got == ref).all()
         cv = cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_UNCHANGED)
-        assert cv is not None and cv.shape == ref.shape and (cv[:, :, ::-1] == ref).all()
+        assert cv is not None
+        if got.shape[2] == 4:                      # RGBA files: the colour is the image, alpha is 255 everywhere
+            assert (got[:, :, 3] == 255).all() and (cv[:, :, 3] == 255).all()
+            got, cv = got[:, :, :3], cv[:, :, :3]
+        assert got.shape == ref.shape and (got == ref).all()
+        assert cv.shape == ref.shape and (cv[:, :, ::-1] == ref).all()
 
 
 def test_rendered_figures_roundtrip(built):
@@ -41,6 +45,8 @@ def test_rendered_figures_roundtrip(built):
     r = FigureRenderer(512, 512, max_images=64)
     imgs = r.render(sc, 'rgb')
     r.close()
+    files4, _ = _encode(imgs, channels=4)
+    _check(files4, imgs)
     files, st = _encode(imgs)
     _check(files, imgs)
     sizes = np.array([len(f) for f in files])
@@ -82,6 +88,9 @@ def test_noise_gradients_and_flat_images(built):
     files, _ = _encode(imgs)
     _check(files, imgs)
     assert len(files[2]) < 2048 and len(files[0]) > H * W * 3
+    files4, _ = _encode(imgs, channels=4)      # the same as RGBA files (what fig.savefig writes)
+    _check(files4, imgs)
+    assert files4[2][25] == 6 and files[2][25] == 2          # IHDR colour type
 
 
 @pytest.mark.parametrize('size', [(256, 256), (640, 480), (1600, 1600), (16, 3)])
@@ -95,6 +104,8 @@ def test_other_sizes(built, size):
             imgs[k, y:y + rng.randint(1, 9), x:x + rng.randint(1, 40)] = rng.randint(0, 256, 3)
     files, _ = _encode(imgs)
     _check(files, imgs)
+    files4, _ = _encode(imgs, channels=4)
+    _check(files4, imgs)
 
 
 def test_empty_batch_and_capacity(built):
@@ -121,12 +132,13 @@ def test_iter_png_is_savefig_for_a_batch(built):
     sc = synthetic_figure_scene(50, 256, 256, seed=12, kind='multi')
     ref = AggOracle().render(sc, 256, 256)
     r = FigureRenderer(256, 256, max_images=16)
-    enc = PngEncoder(256, 256, max_images=16)
+    enc = PngEncoder(256, 256, max_images=16, channels=4)      # RGBA files, as fig.savefig writes them
     seen = 0
     for i0, buf, off in r.iter_png(sc, enc, chunk=16):
         for k in range(len(off) - 1):
             img = cv2.imdecode(np.asarray(buf[int(off[k]):int(off[k + 1])]), cv2.IMREAD_UNCHANGED)
-            assert (img[:, :, ::-1] == ref[i0 + k]).all()
+            assert img.shape == (256, 256, 4) and (img[:, :, 3] == 255).all()
+            assert (img[:, :, 2::-1] == ref[i0 + k]).all()
             seen += 1
     assert seen == 50
     r.close()

@@ -35,7 +35,7 @@ def main():
     t1 = time.time()
     chunk = min(a.chunk, a.n)
     r = FigureRenderer(a.size, a.size, device=a.device, max_images=chunk)
-    enc = PngEncoder(a.size, a.size, device=a.device, max_images=chunk)
+    enc = PngEncoder(a.size, a.size, device=a.device, max_images=chunk, channels=4)      # RGBA, as fig.savefig writes
     total = 0
     for i0, buf, off in r.iter_png(scene, enc, chunk):
         n = len(off) - 1

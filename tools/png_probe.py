@@ -14,15 +14,15 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 chunk = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 sc = synthetic_figure_scene(n, 512, 512, seed=1, kind='single')
 r = FigureRenderer(512, 512, max_images=chunk)
-enc = PngEncoder(512, 512, max_images=chunk)
+enc = PngEncoder(512, 512, max_images=chunk, channels=4 if len(sys.argv) > 4 else 3)
 for _ in range(2):
-    for i0, buf, off in r.iter_png(sc, enc, chunk, overlap=(len(sys.argv) <= 3)):
+    for i0, buf, off in r.iter_png(sc, enc, chunk, overlap=True):
         pass
 enc.set_profiling(True)
 t = time.perf_counter()
 reps, total = 4, 0
 for _ in range(reps):
-    for i0, buf, off in r.iter_png(sc, enc, chunk, overlap=(len(sys.argv) <= 3)):
+    for i0, buf, off in r.iter_png(sc, enc, chunk, overlap=True):
         total += int(off[-1])
 dt = time.perf_counter() - t
 st = enc.stats()
