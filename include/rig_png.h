@@ -48,6 +48,14 @@ size_t rig_png_bound(const rig_png_ctx *ctx, int n);
 int rig_png_encode(rig_png_ctx *ctx, const uint8_t *imgs_dev, int n, int layout, uint8_t *out, size_t out_capacity,
                    uint64_t *offsets_host, int out_is_device, void *stream);
 
+/* The same in two steps, for pipelines: rig_png_encode_begin runs the kernels (it returns once the file sizes are known and the
+ * source images have been read) and starts the copy of the files to out_host on a second stream; rig_png_encode_end waits for
+ * that copy and hands out the offsets.  Two batches may be in flight (begin, begin, end, end, ...), so the copy of one batch
+ * overlaps the kernels of the next.  begin returns the slot (0 or 1) to pass to end, or a negative RIG_E_* code.             */
+int rig_png_encode_begin(rig_png_ctx *ctx, const uint8_t *imgs_dev, int n, int layout, uint8_t *out_host, size_t out_capacity,
+                         void *stream);
+int rig_png_encode_end(rig_png_ctx *ctx, int slot, uint64_t *offsets_host);
+
 /* Makes the encoder's stream wait for `event` (a cudaEvent_t, e.g. from rig_figure_fence) before the next rig_png_encode runs. */
 int rig_png_wait_event(rig_png_ctx *ctx, void *event);
 

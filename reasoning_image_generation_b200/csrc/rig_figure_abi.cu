@@ -10,7 +10,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -21,6 +25,123 @@ using namespace rig;
 
 namespace {
 thread_local char g_fig_create_err[512] = "";
+
+// Growable host array that is page-locked when a CUDA context owns it (so the H2D copy is one asynchronous DMA) and plain
+// malloc memory for the GPU-less debug entry point.  Contents are NOT kept across a grow.
+template <class T>
+struct HostBuf {
+    T *p = nullptr;
+    size_t n = 0, cap = 0;
+    bool pinned = false;
+    ~HostBuf() { release(); }
+    void release()
+    {
+        if (p) { if (pinned) cudaFreeHost(p); else free(p); }
+        p = nullptr; cap = 0; n = 0;
+    }
+    bool resize_discard(size_t want)
+    {
+        if (want > cap) {
+            const bool pin = pinned;
+            release();
+            pinned = pin;
+            const size_t c2 = std::max<size_t>(want + want / 4, 1024);
+            if (pinned) { if (cudaMallocHost((void **)&p, c2 * sizeof(T)) != cudaSuccess) { p = nullptr; return false; } }
+            else if (!(p = (T *)malloc(c2 * sizeof(T)))) return false;
+            cap = c2;
+        }
+        n = want;
+        return true;
+    }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+};
+
+// what k_figure reads, all images of a batch back to back
+struct FigureMerged {
+    HostBuf<FLayer> layers;
+    HostBuf<uint32_t> image_layer_begin;      // [n_images + 1]
+    HostBuf<FEdge> edges;
+    HostBuf<uint32_t> dir;
+    void set_pinned(bool on) { layers.pinned = image_layer_begin.pinned = edges.pinned = dir.pinned = on; }
+};
+
+// A few host threads that stay alive between calls (spawning 16 threads per 4096-image chunk costs a visible part of the chunk's
+// host time).  run(n, f) calls f(0..n-1) on the workers and returns when all are done; one run at a time.
+class HostPool {
+public:
+    explicit HostPool(int nthreads)
+    {
+        for (int t = 0; t < nthreads; t++) th_.emplace_back([this, t] { loop(t); });
+    }
+    ~HostPool()
+    {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            quit_ = true;
+            gen_++;
+        }
+        cv_.notify_all();
+        for (auto &x : th_) x.join();
+    }
+    int size() const { return (int)th_.size(); }
+    void run(int n, const std::function<void(int)> &f)
+    {
+        std::unique_lock<std::mutex> g(m_);
+        f_ = &f; n_ = n; left_ = (int)th_.size(); gen_++;
+        cv_.notify_all();
+        done_.wait(g, [this] { return left_ == 0; });
+        f_ = nullptr;
+    }
+private:
+    void loop(int t)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            const std::function<void(int)> *f;
+            int n;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (quit_) return;
+                f = f_; n = n_;
+            }
+            for (int i = t; i < n; i += (int)th_.size()) (*f)(i);
+            {
+                std::lock_guard<std::mutex> g(m_);
+                if (--left_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)> *f_ = nullptr;
+    int n_ = 0, left_ = 0;
+    unsigned long long gen_ = 0;
+    bool quit_ = false;
+};
+
+int host_thread_count()
+{
+    int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    if (const char *e = getenv("RIG_HOST_THREADS")) nt = std::max(1, atoi(e));
+    return nt;
+}
+
+// per-context scratch of the host path pipeline: the workers and their per-thread outputs, kept so their memory stays mapped
+struct HostPrep {
+    HostPool pool;
+    std::vector<FigurePrepared> parts;
+    std::vector<int> rcs;
+    std::vector<std::vector<char>> errs;
+    HostPrep() : pool(host_thread_count()) {}
+};
 }
 
 struct rig_figure_ctx {
@@ -32,7 +153,11 @@ struct rig_figure_ctx {
     cudaEvent_t ev_fence[8] = {};
     unsigned fence_next = 0;
     // resident scene
-    FigurePrepared prep;
+    // two merged host copies: the H2D copy of one batch is still running while the next batch is prepared into the other
+    FigureMerged prep[2];
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+    unsigned prep_next = 0;
+    HostPrep *host = nullptr;
     std::vector<uint32_t> order;
     std::vector<double> cost;
     int n_images = 0, layout = RIG_LAYOUT_RGB;
@@ -100,49 +225,61 @@ int validate(rig_figure_ctx *c, const rig_figure_scene *s, char *err, int errlen
     return RIG_OK;
 }
 
-// host path pipeline over all images, on up to 16 threads; results merged in image order
-int prepare_all(const rig_figure_scene *s, int W, int H, bool bgr, FigurePrepared &out, char *err, int errlen)
+// host path pipeline over all images, on up to 16 threads.  Phase 1: every worker runs the pipeline over its range of images into
+// its own arrays; phase 2 (after the sizes are known): every worker copies its arrays to their place in the merged buffers,
+// rebasing the layers' edge / directory offsets.
+int prepare_all(const rig_figure_scene *s, int W, int H, bool bgr, HostPrep &hp, FigureMerged &out, char *err, int errlen)
 {
-    out.layers.clear(); out.edges.clear(); out.dir.clear(); out.image_layer_begin.clear();
     const int n = s->n_images;
-    int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
-    if (const char *e = getenv("RIG_HOST_THREADS")) nt = std::max(1, atoi(e));
-    nt = std::max(1, std::min(nt, (n + 255) / 256));
-    std::vector<FigurePrepared> parts(nt);
-    std::vector<int> rcs(nt, 0);
-    std::vector<std::vector<char>> errs(nt, std::vector<char>(256, 0));
-    auto work = [&](int t) {
-        const int i0 = (int)((long long)n * t / nt), i1 = (int)((long long)n * (t + 1) / nt);
-        rcs[t] = figure_prepare(*s, W, H, bgr, i0, i1, parts[t], errs[t].data(), 256);
+    const int nt = std::max(1, std::min(hp.pool.size(), (n + 255) / 256));
+    if ((int)hp.parts.size() < nt) { hp.parts.resize(nt); hp.rcs.resize(nt); hp.errs.resize(nt, std::vector<char>(256, 0)); }
+    auto range = [&](int t, int &i0, int &i1) { i0 = (int)((long long)n * t / nt); i1 = (int)((long long)n * (t + 1) / nt); };
+    const std::function<void(int)> phase1 = [&](int t) {
+        FigurePrepared &p = hp.parts[t];
+        p.layers.clear(); p.edges.clear(); p.dir.clear(); p.image_layer_begin.clear();
+        int i0, i1;
+        range(t, i0, i1);
+        hp.rcs[t] = figure_prepare(*s, W, H, bgr, i0, i1, p, hp.errs[t].data(), 256);
     };
-    if (nt == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (int t = 0; t < nt; t++) th.emplace_back(work, t);
-        for (auto &x : th) x.join();
-    }
+    if (nt == 1) phase1(0); else hp.pool.run(nt, phase1);
     for (int t = 0; t < nt; t++)
-        if (rcs[t]) {
-            snprintf(err, errlen, "%s", errs[t].data());
-            return rcs[t];
+        if (hp.rcs[t]) {
+            snprintf(err, errlen, "%s", hp.errs[t].data());
+            return hp.rcs[t];
         }
+    std::vector<uint64_t> lbase(nt + 1, 0), ebase(nt + 1, 0), dbase(nt + 1, 0);
     for (int t = 0; t < nt; t++) {
-        const FigurePrepared &p = parts[t];
-        const uint32_t lbase = (uint32_t)out.layers.size(), ebase = (uint32_t)out.edges.size(), dbase = (uint32_t)out.dir.size();
-        if ((uint64_t)ebase + p.edges.size() > 0xfffffff0ull) {
-            snprintf(err, errlen, "more than 2^32 edges in one batch");
-            return RIG_E_CAPACITY;
-        }
-        for (size_t i = 0; i + 1 < p.image_layer_begin.size(); i++) out.image_layer_begin.push_back(lbase + p.image_layer_begin[i]);
-        for (FLayer L : p.layers) {
-            L.edge_begin += ebase;
-            L.dir_begin += dbase;
-            out.layers.push_back(L);
-        }
-        out.edges.insert(out.edges.end(), p.edges.begin(), p.edges.end());
-        out.dir.insert(out.dir.end(), p.dir.begin(), p.dir.end());
+        lbase[t + 1] = lbase[t] + hp.parts[t].layers.size();
+        ebase[t + 1] = ebase[t] + hp.parts[t].edges.size();
+        dbase[t + 1] = dbase[t] + hp.parts[t].dir.size();
     }
-    out.image_layer_begin.push_back((uint32_t)out.layers.size());
+    if (ebase[nt] > 0xfffffff0ull || lbase[nt] > 0xfffffff0ull || dbase[nt] > 0xfffffff0ull) {
+        snprintf(err, errlen, "more than 2^32 edges in one batch");
+        return RIG_E_CAPACITY;
+    }
+    if (!out.layers.resize_discard(lbase[nt]) || !out.edges.resize_discard(ebase[nt]) || !out.dir.resize_discard(dbase[nt]) ||
+        !out.image_layer_begin.resize_discard((size_t)n + 1)) {
+        snprintf(err, errlen, "out of host memory for %llu edges", (unsigned long long)ebase[nt]);
+        return RIG_E_CUDA;
+    }
+    const std::function<void(int)> phase2 = [&](int t) {
+        const FigurePrepared &p = hp.parts[t];
+        int i0, i1;
+        range(t, i0, i1);
+        const uint32_t lb = (uint32_t)lbase[t], eb = (uint32_t)ebase[t], db = (uint32_t)dbase[t];
+        for (int i = i0; i < i1; i++) out.image_layer_begin[i] = lb + p.image_layer_begin[i - i0];
+        FLayer *dst = out.layers.data() + lb;
+        for (size_t l = 0; l < p.layers.size(); l++) {
+            FLayer L = p.layers[l];
+            L.edge_begin += eb;
+            L.dir_begin += db;
+            dst[l] = L;
+        }
+        if (!p.edges.empty()) memcpy(out.edges.data() + eb, p.edges.data(), sizeof(FEdge) * p.edges.size());
+        if (!p.dir.empty()) memcpy(out.dir.data() + db, p.dir.data(), sizeof(uint32_t) * p.dir.size());
+    };
+    if (nt == 1) phase2(0); else hp.pool.run(nt, phase2);
+    out.image_layer_begin[n] = (uint32_t)lbase[nt];
     return RIG_OK;
 }
 
@@ -169,16 +306,24 @@ void order_range(rig_figure_ctx *c, uint32_t i0, uint32_t i1)
 int upload(rig_figure_ctx *c, const rig_figure_scene *s, int layout, cudaStream_t st)
 {
     char msg[256] = "";
+    static const bool trace = getenv("RIG_PREP_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto tv0 = now();
     int rc = validate(c, s, msg, sizeof msg);
     if (rc) return ffail(c, rc, "%s", msg);
     if (layout != RIG_LAYOUT_RGB && layout != RIG_LAYOUT_BGR) return ffail(c, RIG_E_INVALID, "bad out_layout %d", layout);
+    const auto tv1 = now();
+    const unsigned slot = c->prep_next++ & 1u;
+    FCK(c, cudaEventSynchronize(c->ev_h2d[slot]));      // the copy that last read this host buffer (two uploads ago)
+    FigureMerged &p = c->prep[slot];
     const auto t0 = std::chrono::steady_clock::now();
-    rc = prepare_all(s, c->W, c->H, layout == RIG_LAYOUT_BGR, c->prep, msg, sizeof msg);
+    rc = prepare_all(s, c->W, c->H, layout == RIG_LAYOUT_BGR, *c->host, p, msg, sizeof msg);
     if (rc) return ffail(c, rc, "%s", msg);
     c->stats.prepare_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    const auto tv2 = now();
     c->n_images = s->n_images;
     c->layout = layout;
-    const FigurePrepared &p = c->prep;
     c->cost.assign(c->n_images, 0.0);
     for (int i = 0; i < c->n_images; i++)
         for (uint32_t l = p.image_layer_begin[i]; l < p.image_layer_begin[i + 1]; l++)
@@ -187,6 +332,7 @@ int upload(rig_figure_ctx *c, const rig_figure_scene *s, int layout, cudaStream_
     order_range(c, 0, (uint32_t)c->n_images);
     c->stats.edges = p.edges.size();
     c->stats.layers = p.layers.size();
+    const auto tv3 = now();
     if ((rc = ensure(c, c->d_layers, c->cap_layers, p.layers.size()))) return rc;
     if ((rc = ensure(c, c->d_edges, c->cap_edges, p.edges.size()))) return rc;
     if ((rc = ensure(c, c->d_dir, c->cap_dir, p.dir.size()))) return rc;
@@ -195,7 +341,8 @@ int upload(rig_figure_ctx *c, const rig_figure_scene *s, int layout, cudaStream_
     if (!p.dir.empty()) FCK(c, cudaMemcpyAsync(c->d_dir, p.dir.data(), sizeof(uint32_t) * p.dir.size(), cudaMemcpyHostToDevice, st));
     FCK(c, cudaMemcpyAsync(c->d_begin, p.image_layer_begin.data(), sizeof(uint32_t) * (c->n_images + 1), cudaMemcpyHostToDevice, st));
     if (c->n_images) FCK(c, cudaMemcpyAsync(c->d_order, c->order.data(), sizeof(uint32_t) * c->n_images, cudaMemcpyHostToDevice, st));
-    FCK(c, cudaStreamSynchronize(st));
+    FCK(c, cudaEventRecord(c->ev_h2d[slot], st));
+    if (trace) fprintf(stderr, "upload: validate %.3f  wait %.3f  prepare %.3f  order %.3f  h2d-enqueue %.3f ms\n", ms(tv0, tv1), ms(tv1, t0), ms(t0, tv2), ms(tv2, tv3), ms(tv3, now()));
     return RIG_OK;
 }
 
@@ -308,7 +455,10 @@ int rig_figure_create(int device, int W, int H, int max_images, int max_artists,
     for (int i = 0; i < 2; i++) {
         FCKC(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
         FCKC(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+        FCKC(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+        c->prep[i].set_pinned(true);
     }
+    c->host = new HostPrep();
     FCKC(cudaMalloc(&c->d_begin, sizeof(uint32_t) * ((size_t)max_images + 1)));
     FCKC(cudaMalloc(&c->d_order, sizeof(uint32_t) * (size_t)max_images));
     FCKC(cudaMalloc(&c->d_work, sizeof(uint32_t) * 4));
@@ -330,7 +480,9 @@ void rig_figure_destroy(rig_figure_ctx *c)
     for (int i = 0; i < 2; i++) {
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+        if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
     }
+    delete c->host;
     for (cudaEvent_t e : c->ev_fence) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -452,8 +604,11 @@ int64_t rig_figure_debug_edges(const rig_figure_scene *scene, int W, int H, uint
     char msg[256] = "";
     int rc = validate(nullptr, scene, msg, sizeof msg);
     if (rc) return rc;
-    FigurePrepared p;
-    rc = prepare_all(scene, W, H, false, p, msg, sizeof msg);
+    FigureMerged p;                       // plain host memory: this entry point needs no GPU
+    {
+        HostPrep hp;
+        rc = prepare_all(scene, W, H, false, hp, p, msg, sizeof msg);
+    }
     if (rc) return rc;
     if ((int64_t)p.edges.size() > edge_cap) return RIG_E_CAPACITY;
     size_t img = 0;

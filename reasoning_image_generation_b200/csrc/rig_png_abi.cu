@@ -32,14 +32,21 @@ struct rig_png_ctx {
     uint32_t ppi = 0;
     int wpc = 4, sm_count = 1, ctas_per_sm = 1;
     size_t smem = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev_in = nullptr, ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_asm = nullptr;
+    // two output slots: the copy of one batch's files to the host overlaps the kernels of the next batch
+    cudaEvent_t ev0[2] = {nullptr, nullptr}, ev1[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    uint8_t *d_outs[2] = {nullptr, nullptr};
+    size_t out_caps[2] = {0, 0};
+    unsigned long long *h_offs[2] = {nullptr, nullptr};   // pinned
+    int slot_n[2] = {0, 0};
+    bool slot_busy[2] = {false, false};
+    unsigned next_slot = 0;
     PngTables *d_tables = nullptr;
     PngPiece *d_pieces = nullptr;
-    uint8_t *d_scratch = nullptr, *d_out = nullptr, *d_stage = nullptr;
-    size_t scratch_bytes = 0, over_begin = 0, out_cap = 0, stage_cap = 0;
+    uint8_t *d_scratch = nullptr, *d_stage = nullptr;
+    size_t scratch_bytes = 0, over_begin = 0, stage_cap = 0;
     unsigned long long *d_sizes = nullptr, *d_offsets = nullptr, *d_counters = nullptr;
-    unsigned long long *h_offsets = nullptr;     // pinned
     rig_png_stats stats = {};
     bool profiling = false;
     char err[512] = "";
@@ -130,9 +137,15 @@ int rig_png_create(int device, int W, int H, int max_images, int channels, rig_p
     if (channels == 3) PCKC(cudaFuncSetAttribute(k_png_pieces<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
     else PCKC(cudaFuncSetAttribute(k_png_pieces<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
     PCKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PCKC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     PCKC(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
-    PCKC(cudaEventCreate(&c->ev0));
-    PCKC(cudaEventCreate(&c->ev1));
+    PCKC(cudaEventCreateWithFlags(&c->ev_asm, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) {
+        PCKC(cudaEventCreate(&c->ev0[i]));
+        PCKC(cudaEventCreate(&c->ev1[i]));
+        PCKC(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
+        PCKC(cudaMallocHost(&c->h_offs[i], sizeof(unsigned long long) * ((size_t)max_images + 1)));
+    }
     PngTables T;
     for (uint32_t i = 0; i < 256; i++) {
         uint32_t v = i;
@@ -165,7 +178,6 @@ int rig_png_create(int device, int W, int H, int max_images, int channels, rig_p
     PCKC(cudaMalloc(&c->d_sizes, sizeof(unsigned long long) * ((size_t)max_images + 1)));
     PCKC(cudaMalloc(&c->d_offsets, sizeof(unsigned long long) * ((size_t)max_images + 1)));
     PCKC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 2));
-    PCKC(cudaMallocHost(&c->h_offsets, sizeof(unsigned long long) * ((size_t)max_images + 1)));
 #undef PCKC
     *out = c;
     return RIG_OK;
@@ -176,33 +188,32 @@ void rig_png_destroy(rig_png_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_tables); cudaFree(c->d_pieces); cudaFree(c->d_scratch); cudaFree(c->d_out); cudaFree(c->d_sizes); cudaFree(c->d_offsets);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    cudaFree(c->d_tables); cudaFree(c->d_pieces); cudaFree(c->d_scratch); cudaFree(c->d_sizes); cudaFree(c->d_offsets);
     cudaFree(c->d_counters); cudaFree(c->d_stage);
-    cudaFreeHost(c->h_offsets);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(c->d_outs[i]);
+        cudaFreeHost(c->h_offs[i]);
+        if (c->ev0[i]) cudaEventDestroy(c->ev0[i]);
+        if (c->ev1[i]) cudaEventDestroy(c->ev1[i]);
+        if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
+    }
     if (c->ev_in) cudaEventDestroy(c->ev_in);
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_asm) cudaEventDestroy(c->ev_asm);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
 
-int rig_png_encode(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, uint8_t *out, size_t out_capacity, uint64_t *offsets_host,
-                   int out_is_device, void *stream)
+// kernels of one batch up to the file offsets; returns the total number of bytes in *total (the host waits for the sizes)
+static int png_run_pieces(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, void *stream, int slot, unsigned long long *total)
 {
-    if (!c) return RIG_E_INVALID;
-    if (n < 0 || !offsets_host || (n && (!imgs_dev || !out))) return pfail(c, RIG_E_INVALID, "bad arguments to rig_png_encode");
-    if (n > c->max_images) return pfail(c, RIG_E_CAPACITY, "%d images > max_images %d", n, c->max_images);
-    if (layout != RIG_LAYOUT_RGB && layout != RIG_LAYOUT_BGR) return pfail(c, RIG_E_INVALID, "bad layout %d", layout);
-    if (((uintptr_t)imgs_dev) % 16) return pfail(c, RIG_E_INVALID, "imgs_dev must be 16-byte aligned");
-    offsets_host[0] = 0;
-    if (n == 0) return RIG_OK;
-    PCK(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     // order the encoder after the stream the images were rendered on
     PCK(c, cudaEventRecord(c->ev_in, (cudaStream_t)stream));
     PCK(c, cudaStreamWaitEvent(st, c->ev_in, 0));
     PCK(c, cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), st));
-    if (c->profiling) PCK(c, cudaEventRecord(c->ev0, st));
+    if (c->profiling) PCK(c, cudaEventRecord(c->ev0[slot], st));
     PngParams P;
     P.imgs = imgs_dev; P.n = n; P.W = c->W; P.H = c->H; P.bgr = layout == RIG_LAYOUT_BGR;
     P.pieces_per_image = c->ppi; P.pieces = c->d_pieces; P.scratch = c->d_scratch;
@@ -219,41 +230,124 @@ int rig_png_encode(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, u
     k_png_scan<<<1, 1024, 0, st>>>(c->d_sizes, n, c->d_offsets);
     c->stats.kernel_launches += 3;
     PCK(c, cudaGetLastError());
-    PCK(c, cudaMemcpyAsync(c->h_offsets, c->d_offsets, sizeof(unsigned long long) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
+    PCK(c, cudaMemcpyAsync(c->h_offs[slot], c->d_offsets, sizeof(unsigned long long) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
     unsigned long long h_counters[2] = {0, 0};
     PCK(c, cudaMemcpyAsync(h_counters, c->d_counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
     PCK(c, cudaStreamSynchronize(st));
     if (h_counters[1]) return pfail(c, RIG_E_CAPACITY, "the images are too incompressible for the piece scratch area (%d images); encode fewer per call", n);
-    const unsigned long long total = c->h_offsets[n];
-    if (total > out_capacity) return pfail(c, RIG_E_CAPACITY, "the PNG files need %llu bytes, out_capacity is %zu", total, out_capacity);
-    uint8_t *dev_out = out;
-    if (!out_is_device) {
-        if (c->out_cap < total) {
-            if (c->d_out) PCK(c, cudaFree(c->d_out));
-            c->d_out = nullptr;
-            const size_t want = (size_t)(total + total / 2 + (1u << 20));
-            PCK(c, cudaMalloc(&c->d_out, want));
-            c->out_cap = want;
-        }
-        dev_out = c->d_out;
-    }
+    *total = c->h_offs[slot][n];
+    return RIG_OK;
+}
+
+static int png_run_assemble(rig_png_ctx *c, int n, uint8_t *dev_out, int slot)
+{
     PngAssembleParams A;
     A.pieces = c->d_pieces; A.scratch = c->d_scratch; A.offsets = c->d_offsets; A.tables = c->d_tables; A.out = dev_out;
     A.n = n; A.W = c->W; A.H = c->H; A.ch = c->ch; A.pieces_per_image = c->ppi;
-    k_png_assemble<<<(n + 7) / 8, 256, 0, st>>>(A);
+    k_png_assemble<<<(n + 7) / 8, 256, 0, c->stream>>>(A);
     c->stats.kernel_launches++;
     PCK(c, cudaGetLastError());
-    if (c->profiling) PCK(c, cudaEventRecord(c->ev1, st));
-    if (!out_is_device) PCK(c, cudaMemcpyAsync(out, dev_out, total, cudaMemcpyDeviceToHost, st));
-    PCK(c, cudaStreamSynchronize(st));
+    if (c->profiling) PCK(c, cudaEventRecord(c->ev1[slot], c->stream));
+    return RIG_OK;
+}
+
+static int png_check_args(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, const void *out)
+{
+    if (n < 0 || (n && (!imgs_dev || !out))) return pfail(c, RIG_E_INVALID, "bad arguments to rig_png_encode");
+    if (n > c->max_images) return pfail(c, RIG_E_CAPACITY, "%d images > max_images %d", n, c->max_images);
+    if (layout != RIG_LAYOUT_RGB && layout != RIG_LAYOUT_BGR) return pfail(c, RIG_E_INVALID, "bad layout %d", layout);
+    if (((uintptr_t)imgs_dev) % 16) return pfail(c, RIG_E_INVALID, "imgs_dev must be 16-byte aligned");
+    return RIG_OK;
+}
+
+int rig_png_encode_begin(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, uint8_t *out_host, size_t out_capacity, void *stream)
+{
+    if (!c) return RIG_E_INVALID;
+    int rc = png_check_args(c, imgs_dev, n, layout, out_host);
+    if (rc) return rc;
+    PCK(c, cudaSetDevice(c->device));
+    const int slot = (int)(c->next_slot & 1u);
+    if (c->slot_busy[slot]) return pfail(c, RIG_E_INVALID, "both output slots are in flight: call rig_png_encode_end first");
+    c->slot_n[slot] = n;
+    if (n == 0) { c->h_offs[slot][0] = 0; c->slot_busy[slot] = true; c->next_slot++; return slot; }
+    unsigned long long total = 0;
+    rc = png_run_pieces(c, imgs_dev, n, layout, stream, slot, &total);
+    if (rc) return rc;
+    if (total > out_capacity) return pfail(c, RIG_E_CAPACITY, "the PNG files need %llu bytes, out_capacity is %zu", total, out_capacity);
+    if (c->out_caps[slot] < total) {
+        if (c->d_outs[slot]) PCK(c, cudaFree(c->d_outs[slot]));
+        c->d_outs[slot] = nullptr;
+        const size_t want = (size_t)(total + total / 2 + (1u << 20));
+        PCK(c, cudaMalloc(&c->d_outs[slot], want));
+        c->out_caps[slot] = want;
+    }
+    rc = png_run_assemble(c, n, c->d_outs[slot], slot);
+    if (rc) return rc;
+    // the copy runs on its own stream: the next batch's kernels start right behind k_png_assemble
+    PCK(c, cudaEventRecord(c->ev_asm, c->stream));
+    PCK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_asm, 0));
+    PCK(c, cudaMemcpyAsync(out_host, c->d_outs[slot], total, cudaMemcpyDeviceToHost, c->copy_stream));
+    PCK(c, cudaEventRecord(c->ev_copy[slot], c->copy_stream));
+    c->slot_busy[slot] = true;
+    c->next_slot++;
+    return slot;
+}
+
+int rig_png_encode_end(rig_png_ctx *c, int slot, uint64_t *offsets_host)
+{
+    if (!c || slot < 0 || slot > 1 || !offsets_host) return RIG_E_INVALID;
+    if (!c->slot_busy[slot]) return pfail(c, RIG_E_INVALID, "slot %d has no batch in flight", slot);
+    PCK(c, cudaSetDevice(c->device));
+    const int n = c->slot_n[slot];
+    if (n) {
+        PCK(c, cudaEventSynchronize(c->ev_copy[slot]));
+        if (c->profiling) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, c->ev0[slot], c->ev1[slot]) == cudaSuccess) {
+                c->stats.encode_ms += ms;
+                c->stats.timed_images += (uint64_t)n;
+            }
+        }
+    }
+    for (int i = 0; i <= n; i++) offsets_host[i] = c->h_offs[slot][i];
+    c->stats.images += (uint64_t)n;
+    c->stats.png_bytes += c->h_offs[slot][n];
+    c->slot_busy[slot] = false;
+    return RIG_OK;
+}
+
+int rig_png_encode(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, uint8_t *out, size_t out_capacity, uint64_t *offsets_host,
+                   int out_is_device, void *stream)
+{
+    if (!c) return RIG_E_INVALID;
+    if (!offsets_host) return pfail(c, RIG_E_INVALID, "offsets_host is NULL");
+    if (!out_is_device) {
+        const int slot = rig_png_encode_begin(c, imgs_dev, n, layout, out, out_capacity, stream);
+        if (slot < 0) return slot;
+        return rig_png_encode_end(c, slot, offsets_host);
+    }
+    int rc = png_check_args(c, imgs_dev, n, layout, out);
+    if (rc) return rc;
+    offsets_host[0] = 0;
+    if (n == 0) return RIG_OK;
+    PCK(c, cudaSetDevice(c->device));
+    const int slot = (int)(c->next_slot & 1u);
+    if (c->slot_busy[slot]) return pfail(c, RIG_E_INVALID, "both output slots are in flight: call rig_png_encode_end first");
+    unsigned long long total = 0;
+    rc = png_run_pieces(c, imgs_dev, n, layout, stream, slot, &total);
+    if (rc) return rc;
+    if (total > out_capacity) return pfail(c, RIG_E_CAPACITY, "the PNG files need %llu bytes, out_capacity is %zu", total, out_capacity);
+    rc = png_run_assemble(c, n, out, slot);
+    if (rc) return rc;
+    PCK(c, cudaStreamSynchronize(c->stream));
     if (c->profiling) {
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) {
+        if (cudaEventElapsedTime(&ms, c->ev0[slot], c->ev1[slot]) == cudaSuccess) {
             c->stats.encode_ms += ms;
             c->stats.timed_images += (uint64_t)n;
         }
     }
-    for (int i = 0; i <= n; i++) offsets_host[i] = c->h_offsets[i];
+    for (int i = 0; i <= n; i++) offsets_host[i] = c->h_offs[slot][i];
     c->stats.images += (uint64_t)n;
     c->stats.png_bytes += total;
     return RIG_OK;

@@ -311,7 +311,7 @@ class FigureRenderer:
         """``fig.savefig`` for a whole batch (multigraph_generation/generator.py:256): renders `chunk` figures at a time into
         the encoder's device staging buffer and encodes them there, so only PNG bytes cross PCIe.  Yields
         (first_image_index, buffer, offsets): file i of the chunk is buffer[offsets[i]:offsets[i + 1]] (pinned host memory,
-        valid until the next iteration).  With `overlap` a worker thread runs the host path pipeline and launches k_figure
+        valid until the next iteration; the copy of one chunk's files overlaps the encode kernels of the next).  With `overlap` a worker thread runs the host path pipeline and launches k_figure
         for the chunks ahead (two halves of the staging buffer) while this thread encodes and copies; the encoder is ordered
         after each render on the GPU (an event recorded right behind it), not by a host synchronisation."""
         import queue
@@ -354,6 +354,7 @@ class FigureRenderer:
 
         t = threading.Thread(target=worker, daemon=True)
         t.start()
+        pending = None                                               # (first image, encoder slot) whose copy is in flight
         try:
             for _ in starts:
                 item = ready.get()
@@ -361,11 +362,25 @@ class FigureRenderer:
                     raise item
                 i0, n_img, ptr, ev = item
                 encoder.wait_event(ev)                               # exactly this chunk's render, not what the worker enqueues next
-                buf, off = encoder.encode(ptr, n_img, 'rgb', 0)
+                slot = encoder.encode_begin(ptr, n_img, 'rgb', 0)    # kernels run while the previous chunk's files are copied
                 free.release()                                       # the encoder has read this half
-                yield i0, buf, off
+                if pending is not None:
+                    p0, pslot = pending
+                    pending = None
+                    buf, off = encoder.encode_end(pslot)
+                    pending = (i0, slot)
+                    yield p0, buf, off
+                else:
+                    pending = (i0, slot)
+            if pending is not None:
+                p0, pslot = pending
+                pending = None
+                buf, off = encoder.encode_end(pslot)
+                yield p0, buf, off
         finally:
             stop.set()
+            if pending is not None:                                  # closed early: retire the slot in flight
+                encoder.encode_end(pending[1])
             free.release()
             free.release()
             t.join()

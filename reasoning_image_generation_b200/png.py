@@ -26,7 +26,7 @@ class RigPngStats(ctypes.Structure):
 
 
 PNG_EXPORTS = ('rig_png_create', 'rig_png_destroy', 'rig_png_last_error', 'rig_png_bound', 'rig_png_encode', 'rig_png_get_stats',
-               'rig_png_set_profiling', 'rig_png_staging', 'rig_png_wait_event')
+               'rig_png_set_profiling', 'rig_png_staging', 'rig_png_wait_event', 'rig_png_encode_begin', 'rig_png_encode_end')
 
 _bound = False
 _LAYOUTS = {'rgb': _abi.RIG_LAYOUT_RGB, 'bgr': _abi.RIG_LAYOUT_BGR}
@@ -47,6 +47,10 @@ def _lib():
         lib.rig_png_bound.restype = ctypes.c_size_t
         lib.rig_png_encode.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_size_t, vp, ctypes.c_int, vp]
         lib.rig_png_encode.restype = ctypes.c_int
+        lib.rig_png_encode_begin.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_size_t, vp]
+        lib.rig_png_encode_begin.restype = ctypes.c_int
+        lib.rig_png_encode_end.argtypes = [vp, ctypes.c_int, vp]
+        lib.rig_png_encode_end.restype = ctypes.c_int
         lib.rig_png_wait_event.argtypes = [vp, vp]
         lib.rig_png_wait_event.restype = ctypes.c_int
         lib.rig_png_staging.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp)]
@@ -81,8 +85,12 @@ class PngEncoder:
         self._h = h
         self._lock = threading.Lock()
         # pinned destination: sized for typical puzzle images (64 KB each), grown on RIG_E_CAPACITY
-        self._pin = PinnedBuffer(int(host_capacity if host_capacity else max(1 << 20, self.max_images * 65536)))
-        self._offsets = np.zeros(self.max_images + 1, dtype=np.uint64)
+        # (one per output slot of the library: the copy of one batch overlaps the kernels of the next)
+        cap = int(host_capacity if host_capacity else max(1 << 20, self.max_images * 65536))
+        self._pins = [PinnedBuffer(cap), PinnedBuffer(cap)]
+        self._offs = [np.zeros(self.max_images + 1, dtype=np.uint64) for _ in range(2)]
+        self._slot_n = [0, 0]
+        self._begun = 0
 
     def _check(self, rc: int):
         if rc:
@@ -92,9 +100,9 @@ class PngEncoder:
         if getattr(self, '_h', None):
             self._lib.rig_png_destroy(self._h)
             self._h = None
-        if getattr(self, '_pin', None) is not None:
-            self._pin.close()
-            self._pin = None
+        for pin in getattr(self, '_pins', None) or ():
+            pin.close()
+        self._pins = None
 
     def __del__(self):
         try:
@@ -105,23 +113,40 @@ class PngEncoder:
     def bound(self, n: int) -> int:
         return int(self._lib.rig_png_bound(self._h, int(n)))
 
-    def encode(self, imgs_ptr: int, n: int, layout: str = 'rgb', stream: int = 0) -> Tuple[np.ndarray, np.ndarray]:
-        """n images at device pointer `imgs_ptr` -> (uint8 buffer view in pinned host memory, uint64 offsets[n + 1]).
-        File i is buffer[offsets[i]:offsets[i + 1]].  The views are valid until the next call."""
+    def encode_begin(self, imgs_ptr: int, n: int, layout: str = 'rgb', stream: int = 0) -> int:
+        """First half of `encode` (rig_png_encode_begin): runs the kernels and starts the copy of the files to pinned host memory.
+        Returns the slot to hand to `encode_end`.  At most two batches may be in flight."""
         if n > self.max_images:
             raise ValueError(f'{n} images > max_images {self.max_images}')
         with self._lock:
+            s = self._begun & 1
             for _ in range(2):
-                rc = self._lib.rig_png_encode(self._h, imgs_ptr, n, _LAYOUTS[layout], self._pin.ptr, self._pin.nbytes,
-                                              self._offsets.ctypes.data, 0, stream or None)
+                pin = self._pins[s]
+                rc = self._lib.rig_png_encode_begin(self._h, imgs_ptr, n, _LAYOUTS[layout], pin.ptr, pin.nbytes, stream or None)
                 if rc == _abi.RIG_E_CAPACITY and b'out_capacity' in (self._lib.rig_png_last_error(self._h) or b''):
-                    self._pin.close()
-                    self._pin = PinnedBuffer(min(self.bound(n), 2 * self._pin.nbytes + (1 << 24)))
+                    pin.close()
+                    self._pins[s] = PinnedBuffer(min(self.bound(n), 2 * pin.nbytes + (1 << 24)))
                     continue
                 break
-            self._check(rc)
-        off = self._offsets[:n + 1]
-        return self._pin.array[:int(off[n])], off
+            if rc < 0:
+                self._check(rc)
+            assert rc == s, (rc, s)
+            self._slot_n[s] = n
+            self._begun += 1
+        return s
+
+    def encode_end(self, slot: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Second half of `encode`: waits for the copy of `slot`; the views are valid until that slot is begun again (two
+        `encode_begin` calls later)."""
+        with self._lock:
+            self._check(self._lib.rig_png_encode_end(self._h, slot, self._offs[slot].ctypes.data))
+        off = self._offs[slot][:self._slot_n[slot] + 1]
+        return self._pins[slot].array[:int(off[-1])], off
+
+    def encode(self, imgs_ptr: int, n: int, layout: str = 'rgb', stream: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+        """n images at device pointer `imgs_ptr` -> (uint8 buffer view in pinned host memory, uint64 offsets[n + 1]).
+        File i is buffer[offsets[i]:offsets[i + 1]].  The views are valid until the next call."""
+        return self.encode_end(self.encode_begin(imgs_ptr, n, layout, stream))
 
     def wait_event(self, event: int):
         """The next `encode` starts only after `event` (a cudaEvent_t handle, e.g. FigureRenderer.fence()) has completed on the GPU."""

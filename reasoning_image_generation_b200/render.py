@@ -128,16 +128,38 @@ class Renderer:
         a time into the encoder's device staging buffer and encodes them there, so only PNG bytes cross PCIe.  `layout` is the
         channel order the panels are rendered in ('bgr' = what the reference hands to cv2.imwrite; the files hold RGB either
         way).  Yields (first_panel_index, buffer, offsets); file i of the chunk is buffer[offsets[i]:offsets[i + 1]] (pinned
-        host memory, valid until the next iteration)."""
+        host memory, valid until the next iteration).  The copy of one chunk's files overlaps the render and encode of the next."""
         self._check_scene(scene)
         chunk = max(1, min(int(chunk), encoder.max_images, self.max_panels))
-        for p0 in range(0, scene.n_panels, chunk):
-            sub = scene if (p0 == 0 and scene.n_panels <= chunk) else scene.slice(p0, min(scene.n_panels, p0 + chunk))
-            ptr = encoder.staging(sub.n_panels)
-            self.render_to_device(sub, ptr, layout, 0)
-            self.sync()                  # rendered on the context's own stream: finish before the encoder reads
-            buf, off = encoder.encode(ptr, sub.n_panels, layout, 0)
-            yield p0, buf, off
+        starts = list(range(0, scene.n_panels, chunk))
+        if not starts:
+            return
+        img_bytes = self.W * self.H * 3
+        base = encoder.staging(min(2, len(starts)) * chunk)
+        pending = None                   # (first panel, encoder slot) whose copy to the host is in flight
+        try:
+            for k, p0 in enumerate(starts):
+                sub = scene if (p0 == 0 and scene.n_panels <= chunk) else scene.slice(p0, min(scene.n_panels, p0 + chunk))
+                ptr = base + (k & 1) * chunk * img_bytes
+                self.render_to_device(sub, ptr, layout, 0)
+                self.sync()              # rendered on the context's own stream: finish before the encoder reads
+                slot = encoder.encode_begin(ptr, sub.n_panels, layout, 0)
+                if pending is not None:
+                    q0, qslot = pending
+                    pending = None
+                    buf, off = encoder.encode_end(qslot)
+                    pending = (p0, slot)
+                    yield q0, buf, off
+                else:
+                    pending = (p0, slot)
+            if pending is not None:
+                q0, qslot = pending
+                pending = None
+                buf, off = encoder.encode_end(qslot)
+                yield q0, buf, off
+        finally:
+            if pending is not None:
+                encoder.encode_end(pending[1])
 
     def upload(self, scene: Scene, layout: str = 'bgr', stream: int = 0):
         self._check_scene(scene)

@@ -168,3 +168,39 @@ def test_sequence_iter_png_is_imwrite_for_a_batch(built):
     assert seen == 40
     r.close()
     enc.close()
+
+
+def test_two_batches_in_flight(built):
+    """rig_png_encode_begin / rig_png_encode_end: begin, begin, end, end gives the same files as two synchronous encodes; a third
+    begin without an end is refused; closing a pipelined iterator early leaves the encoder usable."""
+    import torch
+    from reasoning_image_generation_b200.figure import FigureRenderer
+    from reasoning_image_generation_b200.png import PngEncoder, PngError, split_files
+    from reasoning_image_generation_b200.synth_figure import synthetic_figure_scene
+    sc = synthetic_figure_scene(24, 256, 256, seed=3, kind='multi')
+    r = FigureRenderer(256, 256, max_images=32)
+    imgs = r.render(sc, 'rgb')
+    a = torch.from_numpy(imgs[:12].copy()).cuda()
+    b = torch.from_numpy(imgs[12:].copy()).cuda()
+    enc = PngEncoder(256, 256, max_images=16)
+    ref_a = split_files(*enc.encode(a.data_ptr(), 12))
+    ref_b = split_files(*enc.encode(b.data_ptr(), 12))
+    for _ in range(3):                                    # odd number of rounds: the slots alternate roles
+        sa = enc.encode_begin(a.data_ptr(), 12)
+        sb = enc.encode_begin(b.data_ptr(), 12)
+        assert {sa, sb} == {0, 1}
+        with pytest.raises(PngError):
+            enc.encode_begin(a.data_ptr(), 12)
+        assert split_files(*enc.encode_end(sa)) == ref_a
+        assert split_files(*enc.encode_end(sb)) == ref_b
+        sa = enc.encode_begin(a.data_ptr(), 12)           # and a lone begin/end in between
+        assert split_files(*enc.encode_end(sa)) == ref_a
+    with pytest.raises(PngError):
+        enc.encode_end(0)                                 # nothing in flight
+    _check(ref_a + ref_b, imgs)
+    it = r.iter_png(sc, enc, chunk=4)
+    next(it); next(it)
+    it.close()                                            # retires the slot whose copy is in flight
+    assert split_files(*enc.encode(b.data_ptr(), 12)) == ref_b
+    r.close()
+    enc.close()

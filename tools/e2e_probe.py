@@ -56,3 +56,15 @@ dt = time.perf_counter() - t0
 print('overlapped: render %.2f ms  encode %.2f ms  per-chunk wall %.2f ms -> %.0f k img/s' % (1e3 * sum(trs) / 16, 1e3 * sum(tes) / 16, 1e3 * dt / 16, 16 * chunk / dt / 1e3))
 st = r.stats()
 print('host prepare %.2f ms' % st['prepare_ms'])
+
+# the product loop itself (iter_png: worker thread + two encoder slots)
+for ch in (3, 4):
+    e2 = PngEncoder(512, 512, max_images=chunk, channels=ch)
+    for rep in range(3):
+        t0 = time.perf_counter()
+        tot = 0
+        for i0, buf, off in r.iter_png(sc, e2, chunk=chunk):
+            tot += int(off[-1])
+        dt = time.perf_counter() - t0
+    print('iter_png channels=%d: %.0f k img/s (%.1f KB/file)' % (ch, n / dt / 1e3, tot / n / 1e3))
+    e2.close()
