@@ -22,6 +22,10 @@ namespace rig {
 #endif
 constexpr int PNG_ROWS = PNG_PIECE_ROWS;
 constexpr int PNG_CHUNK_PX = 16;              // pixels per lane per pass: 48 filtered bytes (RGB files) or 64 (RGBA files)
+#ifndef PNG_CLAIM_PIECES
+#define PNG_CLAIM_PIECES 4
+#endif
+constexpr uint32_t PNG_CLAIM = PNG_CLAIM_PIECES;   // consecutive pieces a warp claims at a time
 constexpr uint32_t PNG_SLOT = 512;            // bytes reserved per piece; larger pieces go to the overflow arena
 constexpr uint32_t PNG_FILE_OVERHEAD = 65;    // signature 8 + IHDR 25 + IDAT 12 + zlib header 2 + final block 2 + Adler 4 + IEND 12
 constexpr uint32_t ADLER_MOD = 65521u;
@@ -169,7 +173,7 @@ struct PngParams {
     PngPiece *pieces;
     uint8_t *scratch;               // [n * pieces_per_image * PNG_SLOT][overflow arena]
     unsigned long long over_begin, over_cap;
-    unsigned long long *counters;   // [0] overflow arena cursor, [1] error flag
+    unsigned long long *counters;   // [0] overflow arena cursor, [1] error flag, [2] next unclaimed piece
 };
 
 // shared memory per warp: bit buffer + 32 chunks of filtered bytes + staging words + the bits of an all-white row
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
     __shared__ PngLut lut;
     png_fill_lut(lut);
     __syncthreads();
-    const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = png_warp_smem(P.W, CH), bufb = png_piece_buf_bytes(P.W, CH);
     uint32_t *buf = (uint32_t *)(smem + (size_t)warp * per_warp);
     uint8_t *fbytes = (uint8_t *)buf + bufb + lane * CHUNK;
@@ -233,16 +237,43 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
     __syncwarp();
     const unsigned long long total_pieces = (unsigned long long)P.n * P.pieces_per_image;
     uint32_t used_words = 0;                   // words of buf the previous piece dirtied
-    for (unsigned long long gp = (unsigned long long)blockIdx.x * wpc + warp; gp < total_pieces; gp += (unsigned long long)gridDim.x * wpc) {
+    PngPiece canned;                           // this warp's first blank piece (nbytes 0: none yet)
+    canned.nbytes = 0u; canned.where = 0u; canned.a = 0u; canned.b = 0u;
+    // pieces are claimed a few at a time from a global cursor: blank pieces cost a fraction of drawn ones, and CTAs that become
+    // resident late (behind a k_figure launch on another stream) must not be left with a full static share
+    for (;;) {
+      unsigned long long gp0 = 0;
+      if (lane == 0) gp0 = atomicAdd(P.counters + 2, (unsigned long long)PNG_CLAIM);
+      gp0 = __shfl_sync(0xffffffffu, gp0, 0);
+      if (gp0 >= total_pieces) break;
+      const unsigned long long gp1 = gp0 + PNG_CLAIM < total_pieces ? gp0 + PNG_CLAIM : total_pieces;
+      for (unsigned long long gp = gp0; gp < gp1; gp++) {
         const uint32_t image = (uint32_t)(gp / P.pieces_per_image), piece = (uint32_t)(gp % P.pieces_per_image);
         const int y0 = (int)piece * PNG_ROWS, y1 = min(P.H, y0 + PNG_ROWS);
         const uint32_t L = (uint32_t)(y1 - y0) * RL;              // uncompressed bytes in this piece
+        const uint8_t *img = P.imgs + (size_t)image * P.H * row_bytes;
+        // Blank pieces (every pixel white: three quarters of this data set) all have the same bytes and Adler sums: the first one
+        // this warp meets is encoded the long way, the others just point at its bytes in the scratch area.
+        bool blank = false;
+        if (y1 - y0 == PNG_ROWS) {
+            uint32_t acc = 0xffffffffu;
+            for (int y = y0; y < y1; y++)
+                for (int c = lane; c < chunks; c += 32) {
+                    const uint4 *src = (const uint4 *)(img + (size_t)y * row_bytes + (size_t)c * 48);
+                    const uint4 a = __ldg(src), b = __ldg(src + 1), d = __ldg(src + 2);
+                    acc &= a.x & a.y & a.z & a.w & b.x & b.y & b.z & b.w & d.x & d.y & d.z & d.w;
+                }
+            blank = __all_sync(0xffffffffu, acc == 0xffffffffu);
+            if (blank && canned.nbytes) {
+                if (lane == 0) P.pieces[gp] = canned;
+                continue;
+            }
+        }
         for (uint32_t i = lane; i < used_words; i += 32) buf[i] = 0u;
         __syncwarp();
         uint32_t bitpos = 3;
         if (lane == 0) buf[0] = 2u;          // BFINAL = 0, BTYPE = 01 (fixed Huffman), LSB first
         unsigned long long ad_a = 0, ad_b = 0;
-        const uint8_t *img = P.imgs + (size_t)image * P.H * row_bytes;
         // the row above, as this lane saw it: raw words, Adler sums of its filtered chunk, where its bits are
         uint32_t pw[12];
 #pragma unroll
@@ -450,7 +481,14 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
             pc.b = (uint32_t)(ad_b % ADLER_MOD);
             P.pieces[gp] = pc;
         }
+        if (blank && !failed && nbytes <= PNG_SLOT) {
+            canned.nbytes = nbytes;
+            canned.where = (uint32_t)(where / 16);
+            canned.a = (uint32_t)(ad_a % ADLER_MOD);
+            canned.b = (uint32_t)(ad_b % ADLER_MOD);
+        }
         __syncwarp();
+      }
     }
 }
 

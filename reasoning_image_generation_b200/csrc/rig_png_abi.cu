@@ -177,7 +177,7 @@ int rig_png_create(int device, int W, int H, int max_images, int channels, rig_p
     PCKC(cudaMalloc(&c->d_scratch, c->scratch_bytes));
     PCKC(cudaMalloc(&c->d_sizes, sizeof(unsigned long long) * ((size_t)max_images + 1)));
     PCKC(cudaMalloc(&c->d_offsets, sizeof(unsigned long long) * ((size_t)max_images + 1)));
-    PCKC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 2));
+    PCKC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 4));
 #undef PCKC
     *out = c;
     return RIG_OK;
@@ -212,7 +212,7 @@ static int png_run_pieces(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int la
     // order the encoder after the stream the images were rendered on
     PCK(c, cudaEventRecord(c->ev_in, (cudaStream_t)stream));
     PCK(c, cudaStreamWaitEvent(st, c->ev_in, 0));
-    PCK(c, cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), st));
+    PCK(c, cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), st));
     if (c->profiling) PCK(c, cudaEventRecord(c->ev0[slot], st));
     PngParams P;
     P.imgs = imgs_dev; P.n = n; P.W = c->W; P.H = c->H; P.bgr = layout == RIG_LAYOUT_BGR;
