@@ -59,6 +59,11 @@ int rig_png_encode_end(rig_png_ctx *ctx, int slot, uint64_t *offsets_host);
 /* Makes the encoder's stream wait for `event` (a cudaEvent_t, e.g. from rig_figure_fence) before the next rig_png_encode runs. */
 int rig_png_wait_event(rig_png_ctx *ctx, void *event);
 
+/* Optional hint for the NEXT rig_png_encode / rig_png_encode_begin only: flags_dev[n][ceil(H / rows_per_band)] bytes in device
+ * memory, 1 = every pixel of those rows is white (255, 255, 255), as rig_figure_blank_bands reports.  Rows so marked are encoded
+ * without being read.  A flag of 0 promises nothing; a wrong 1 gives a file in which those rows may be white.  NULL clears the hint.           */
+int rig_png_set_blank_hint(rig_png_ctx *ctx, const uint8_t *flags_dev, int rows_per_band);
+
 /* A device buffer of at least n * H * W * 3 bytes owned by the context (grown on demand, 16-byte aligned, valid until the
  * next rig_png_staging call or rig_png_destroy): a place to render into before encoding, for callers that have no device
  * allocator of their own.                                                                                             */

@@ -44,6 +44,7 @@ struct FigureParams {
     int W, H;
     uint32_t bg;                         // c0 | c1 << 8 | c2 << 16
     uint32_t max_claim;
+    uint8_t *blank;                      // [n_images * bands per image] or NULL: 1 = the band holds only background pixels
 };
 
 // bytes of shared memory one warp needs: band pixels, cover + area accumulators, per-row touched-group mask and carry-in
@@ -177,9 +178,13 @@ __global__ void __launch_bounds__(FIG_MAX_WARPS * 32, 1) k_figure(const FigurePa
             const uint32_t lmask = __ballot_sync(0xffffffffu, (int)(int16_t)(myh.yy & 0xffffu) <= r1 && (int)(int16_t)(myh.yy >> 16) >= r0);
             const bool any_more = __any_sync(0xffffffffu, more);
             if (lmask == 0u && !any_more) {
-                if (lane == 0) bulk_store(gdst, tmpl, out_bytes);
+                if (lane == 0) {
+                    bulk_store(gdst, tmpl, out_bytes);
+                    if (P.blank) P.blank[(size_t)image * bands_per_image + band] = 1;
+                }
                 continue;
             }
+            if (P.blank && lane == 0) P.blank[(size_t)image * bands_per_image + band] = 0;
             if (dirty) {
                 if (lane == 0) bulk_wait_read();
                 __syncwarp();

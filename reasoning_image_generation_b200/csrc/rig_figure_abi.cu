@@ -167,6 +167,11 @@ struct rig_figure_ctx {
     size_t cap_layers = 0, cap_edges = 0, cap_dir = 0, cap_images = 0;
     uint8_t *d_stage[2] = {nullptr, nullptr};
     size_t stage_images = 0;
+    // blank-band flags of the last two device-destination renders (a consumer reads one while the next render writes the other)
+    uint8_t *d_blank[2] = {nullptr, nullptr};
+    unsigned blank_next = 0;
+    bool want_blank = false;
+    const uint8_t *last_blank = nullptr;
     uint32_t max_claim = 32;
     rig_figure_stats stats = {};
     bool profiling = false;
@@ -228,7 +233,7 @@ int validate(rig_figure_ctx *c, const rig_figure_scene *s, char *err, int errlen
 // host path pipeline over all images, on up to 16 threads.  Phase 1: every worker runs the pipeline over its range of images into
 // its own arrays; phase 2 (after the sizes are known): every worker copies its arrays to their place in the merged buffers,
 // rebasing the layers' edge / directory offsets.
-int prepare_all(const rig_figure_scene *s, int W, int H, bool bgr, HostPrep &hp, FigureMerged &out, char *err, int errlen)
+int prepare_all(const rig_figure_scene *s, int W, int H, bool bgr, HostPrep &hp, FigureMerged &out, std::vector<double> *cost, char *err, int errlen)
 {
     const int n = s->n_images;
     const int nt = std::max(1, std::min(hp.pool.size(), (n + 255) / 256));
@@ -257,6 +262,7 @@ int prepare_all(const rig_figure_scene *s, int W, int H, bool bgr, HostPrep &hp,
         snprintf(err, errlen, "more than 2^32 edges in one batch");
         return RIG_E_CAPACITY;
     }
+    if (cost) cost->resize((size_t)n);
     if (!out.layers.resize_discard(lbase[nt]) || !out.edges.resize_discard(ebase[nt]) || !out.dir.resize_discard(dbase[nt]) ||
         !out.image_layer_begin.resize_discard((size_t)n + 1)) {
         snprintf(err, errlen, "out of host memory for %llu edges", (unsigned long long)ebase[nt]);
@@ -268,6 +274,13 @@ int prepare_all(const rig_figure_scene *s, int W, int H, bool bgr, HostPrep &hp,
         range(t, i0, i1);
         const uint32_t lb = (uint32_t)lbase[t], eb = (uint32_t)ebase[t], db = (uint32_t)dbase[t];
         for (int i = i0; i < i1; i++) out.image_layer_begin[i] = lb + p.image_layer_begin[i - i0];
+        if (cost)                            // scheduling weight of an image: its edges + the rows its layers resolve
+            for (int i = i0; i < i1; i++) {
+                const size_t l0 = p.image_layer_begin[i - i0], l1 = i + 1 < i1 ? p.image_layer_begin[i + 1 - i0] : p.layers.size();
+                double w = 0.0;
+                for (size_t l = l0; l < l1; l++) w += (double)p.layers[l].n_edges + 8.0 * std::max(0, p.layers[l].ymax - p.layers[l].ymin + 1);
+                (*cost)[i] = w;
+            }
         FLayer *dst = out.layers.data() + lb;
         for (size_t l = 0; l < p.layers.size(); l++) {
             FLayer L = p.layers[l];
@@ -297,10 +310,19 @@ int ensure(rig_figure_ctx *c, T *&p, size_t &cap, size_t need)
     return RIG_OK;
 }
 
+// images [i0, i1) costliest first (ties and near-ties in index order): a counting sort over 256 cost classes -- the order only
+// steers the band queue, so it need not be exact
 void order_range(rig_figure_ctx *c, uint32_t i0, uint32_t i1)
 {
-    for (uint32_t i = i0; i < i1; i++) c->order[i] = i;
-    std::stable_sort(c->order.begin() + i0, c->order.begin() + i1, [&](uint32_t a, uint32_t b) { return c->cost[a] > c->cost[b]; });
+    if (i1 <= i0) return;
+    double mx = 0.0;
+    for (uint32_t i = i0; i < i1; i++) mx = std::max(mx, c->cost[i]);
+    const double scale = mx > 0.0 ? 255.0 / mx : 0.0;
+    uint32_t count[257] = {0};
+    auto cls = [&](uint32_t i) { return 255u - (uint32_t)(c->cost[i] * scale); };
+    for (uint32_t i = i0; i < i1; i++) count[cls(i) + 1]++;
+    for (int k = 0; k < 256; k++) count[k + 1] += count[k];
+    for (uint32_t i = i0; i < i1; i++) c->order[i0 + count[cls(i)]++] = i;
 }
 
 int upload(rig_figure_ctx *c, const rig_figure_scene *s, int layout, cudaStream_t st)
@@ -318,16 +340,12 @@ int upload(rig_figure_ctx *c, const rig_figure_scene *s, int layout, cudaStream_
     FCK(c, cudaEventSynchronize(c->ev_h2d[slot]));      // the copy that last read this host buffer (two uploads ago)
     FigureMerged &p = c->prep[slot];
     const auto t0 = std::chrono::steady_clock::now();
-    rc = prepare_all(s, c->W, c->H, layout == RIG_LAYOUT_BGR, *c->host, p, msg, sizeof msg);
+    rc = prepare_all(s, c->W, c->H, layout == RIG_LAYOUT_BGR, *c->host, p, &c->cost, msg, sizeof msg);
     if (rc) return ffail(c, rc, "%s", msg);
     c->stats.prepare_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     const auto tv2 = now();
     c->n_images = s->n_images;
     c->layout = layout;
-    c->cost.assign(c->n_images, 0.0);
-    for (int i = 0; i < c->n_images; i++)
-        for (uint32_t l = p.image_layer_begin[i]; l < p.image_layer_begin[i + 1]; l++)
-            c->cost[i] += (double)p.layers[l].n_edges + 8.0 * std::max(0, p.layers[l].ymax - p.layers[l].ymin + 1);
     c->order.resize(c->n_images);
     order_range(c, 0, (uint32_t)c->n_images);
     c->stats.edges = p.edges.size();
@@ -385,6 +403,12 @@ int launch(rig_figure_ctx *c, uint32_t i0, uint32_t i1, uint8_t *out_dev, uint32
     P.W = c->W; P.H = c->H;
     P.bg = 0x00ffffffu;
     P.max_claim = c->max_claim;
+    P.blank = nullptr;
+    c->last_blank = nullptr;
+    if (c->want_blank && img_base == 0 && i0 == 0) {      // whole-batch launches into the caller's device buffer
+        P.blank = c->d_blank[c->blank_next++ & 1u];
+        c->last_blank = P.blank;
+    }
     const uint32_t bands = P.n_images * (uint32_t)((c->H + FIG_ROWS - 1) / FIG_ROWS);
     const uint32_t want = (bands + c->warps - 1) / c->warps;
     const uint32_t grid = std::max(1u, std::min((uint32_t)c->sm_count, want));
@@ -462,6 +486,7 @@ int rig_figure_create(int device, int W, int H, int max_images, int max_artists,
     FCKC(cudaMalloc(&c->d_begin, sizeof(uint32_t) * ((size_t)max_images + 1)));
     FCKC(cudaMalloc(&c->d_order, sizeof(uint32_t) * (size_t)max_images));
     FCKC(cudaMalloc(&c->d_work, sizeof(uint32_t) * 4));
+    for (int i = 0; i < 2; i++) FCKC(cudaMalloc(&c->d_blank[i], (size_t)max_images * (size_t)((H + FIG_ROWS - 1) / FIG_ROWS)));
 #undef FCKC
     *out = c;
     return RIG_OK;
@@ -475,6 +500,7 @@ void rig_figure_destroy(rig_figure_ctx *c)
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     cudaFree(c->d_layers); cudaFree(c->d_edges); cudaFree(c->d_dir); cudaFree(c->d_begin); cudaFree(c->d_order); cudaFree(c->d_work);
     cudaFree(c->d_stage[0]); cudaFree(c->d_stage[1]);
+    cudaFree(c->d_blank[0]); cudaFree(c->d_blank[1]);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_used) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
@@ -515,6 +541,21 @@ int rig_figure_fence(rig_figure_ctx *c, void **event_out)
     if (!e) FCK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     FCK(c, cudaEventRecord(e, c->stream));
     *event_out = (void *)e;
+    return RIG_OK;
+}
+
+int rig_figure_set_blank_flags(rig_figure_ctx *c, int on)
+{
+    if (!c) return RIG_E_INVALID;
+    c->want_blank = on != 0;
+    return RIG_OK;
+}
+
+int rig_figure_blank_bands(rig_figure_ctx *c, const uint8_t **flags_dev_out, int *rows_per_band_out)
+{
+    if (!c || !flags_dev_out || !rows_per_band_out) return RIG_E_INVALID;
+    *flags_dev_out = c->last_blank;
+    *rows_per_band_out = FIG_ROWS;
     return RIG_OK;
 }
 
@@ -607,7 +648,7 @@ int64_t rig_figure_debug_edges(const rig_figure_scene *scene, int W, int H, uint
     FigureMerged p;                       // plain host memory: this entry point needs no GPU
     {
         HostPrep hp;
-        rc = prepare_all(scene, W, H, false, hp, p, msg, sizeof msg);
+        rc = prepare_all(scene, W, H, false, hp, p, nullptr, msg, sizeof msg);
     }
     if (rc) return rc;
     if ((int64_t)p.edges.size() > edge_cap) return RIG_E_CAPACITY;

@@ -174,6 +174,9 @@ struct PngParams {
     uint8_t *scratch;               // [n * pieces_per_image * PNG_SLOT][overflow arena]
     unsigned long long over_begin, over_cap;
     unsigned long long *counters;   // [0] overflow arena cursor, [1] error flag, [2] next unclaimed piece
+    const uint8_t *blank;           // optional hint, [n][blank_bands]: 1 = rows [b * blank_rows, (b + 1) * blank_rows) are all white
+    int blank_rows;
+    uint32_t blank_bands;
 };
 
 // shared memory per warp: bit buffer + 32 chunks of filtered bytes + staging words + the bits of an all-white row
@@ -257,6 +260,12 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
         bool blank = false;
         if (y1 - y0 == PNG_ROWS) {
             uint32_t acc = 0xffffffffu;
+            bool hinted = false;
+            if (P.blank) {                       // the renderer's word for it: no need to read the pixels
+                const uint8_t *fl = P.blank + (size_t)image * P.blank_bands;
+                hinted = (__ldg(fl + y0 / P.blank_rows) & __ldg(fl + (y1 - 1) / P.blank_rows)) != 0;
+            }
+            if (!hinted || !canned.nbytes)       // (the copy every other blank piece will point at is made from pixels that were read)
             for (int y = y0; y < y1; y++)
                 for (int c = lane; c < chunks; c += 32) {
                     const uint4 *src = (const uint4 *)(img + (size_t)y * row_bytes + (size_t)c * 48);

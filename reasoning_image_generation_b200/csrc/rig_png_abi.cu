@@ -42,6 +42,8 @@ struct rig_png_ctx {
     int slot_n[2] = {0, 0};
     bool slot_busy[2] = {false, false};
     unsigned next_slot = 0;
+    const uint8_t *hint = nullptr;     // blank-band flags for the next encode only
+    int hint_rows = 0;
     PngTables *d_tables = nullptr;
     PngPiece *d_pieces = nullptr;
     uint8_t *d_scratch = nullptr, *d_stage = nullptr;
@@ -206,7 +208,8 @@ void rig_png_destroy(rig_png_ctx *c)
 }
 
 // kernels of one batch up to the file offsets; returns the total number of bytes in *total (the host waits for the sizes)
-static int png_run_pieces(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, void *stream, int slot, unsigned long long *total)
+static int png_run_pieces(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, void *stream, int slot, unsigned long long *total,
+                          const uint8_t *hint, int hint_rows)
 {
     cudaStream_t st = c->stream;
     // order the encoder after the stream the images were rendered on
@@ -218,6 +221,7 @@ static int png_run_pieces(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int la
     P.imgs = imgs_dev; P.n = n; P.W = c->W; P.H = c->H; P.bgr = layout == RIG_LAYOUT_BGR;
     P.pieces_per_image = c->ppi; P.pieces = c->d_pieces; P.scratch = c->d_scratch;
     P.over_begin = c->over_begin; P.over_cap = c->scratch_bytes - c->over_begin; P.counters = c->d_counters;
+    P.blank = hint; P.blank_rows = hint_rows; P.blank_bands = hint ? (uint32_t)((c->H + hint_rows - 1) / hint_rows) : 0u;
     const unsigned long long npieces = (unsigned long long)n * c->ppi;
     {
         // persistent warps: every warp prepares the bits of a white row once, then walks pieces with a grid stride
@@ -263,6 +267,9 @@ static int png_check_args(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int la
 int rig_png_encode_begin(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, uint8_t *out_host, size_t out_capacity, void *stream)
 {
     if (!c) return RIG_E_INVALID;
+    const uint8_t *hint = c->hint;          // for this call only, whatever its outcome
+    const int hint_rows = c->hint_rows;
+    c->hint = nullptr;
     int rc = png_check_args(c, imgs_dev, n, layout, out_host);
     if (rc) return rc;
     PCK(c, cudaSetDevice(c->device));
@@ -271,7 +278,7 @@ int rig_png_encode_begin(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int lay
     c->slot_n[slot] = n;
     if (n == 0) { c->h_offs[slot][0] = 0; c->slot_busy[slot] = true; c->next_slot++; return slot; }
     unsigned long long total = 0;
-    rc = png_run_pieces(c, imgs_dev, n, layout, stream, slot, &total);
+    rc = png_run_pieces(c, imgs_dev, n, layout, stream, slot, &total, hint, hint_rows);
     if (rc) return rc;
     if (total > out_capacity) return pfail(c, RIG_E_CAPACITY, "the PNG files need %llu bytes, out_capacity is %zu", total, out_capacity);
     if (c->out_caps[slot] < total) {
@@ -326,6 +333,9 @@ int rig_png_encode(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, u
         if (slot < 0) return slot;
         return rig_png_encode_end(c, slot, offsets_host);
     }
+    const uint8_t *hint = c->hint;
+    const int hint_rows = c->hint_rows;
+    c->hint = nullptr;
     int rc = png_check_args(c, imgs_dev, n, layout, out);
     if (rc) return rc;
     offsets_host[0] = 0;
@@ -334,7 +344,7 @@ int rig_png_encode(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, u
     const int slot = (int)(c->next_slot & 1u);
     if (c->slot_busy[slot]) return pfail(c, RIG_E_INVALID, "both output slots are in flight: call rig_png_encode_end first");
     unsigned long long total = 0;
-    rc = png_run_pieces(c, imgs_dev, n, layout, stream, slot, &total);
+    rc = png_run_pieces(c, imgs_dev, n, layout, stream, slot, &total, hint, hint_rows);
     if (rc) return rc;
     if (total > out_capacity) return pfail(c, RIG_E_CAPACITY, "the PNG files need %llu bytes, out_capacity is %zu", total, out_capacity);
     rc = png_run_assemble(c, n, out, slot);
@@ -350,6 +360,15 @@ int rig_png_encode(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int layout, u
     for (int i = 0; i <= n; i++) offsets_host[i] = c->h_offs[slot][i];
     c->stats.images += (uint64_t)n;
     c->stats.png_bytes += total;
+    return RIG_OK;
+}
+
+int rig_png_set_blank_hint(rig_png_ctx *c, const uint8_t *flags_dev, int rows_per_band)
+{
+    if (!c) return RIG_E_INVALID;
+    if (flags_dev && rows_per_band <= 0) return pfail(c, RIG_E_INVALID, "rows_per_band must be positive");
+    c->hint = flags_dev;
+    c->hint_rows = rows_per_band;
     return RIG_OK;
 }
 

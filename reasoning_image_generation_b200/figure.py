@@ -182,7 +182,8 @@ class RigFigureStats(ctypes.Structure):
 
 FIGURE_EXPORTS = ('rig_figure_create', 'rig_figure_destroy', 'rig_figure_last_error', 'rig_figure_render_batch',
                   'rig_figure_upload', 'rig_figure_render_resident', 'rig_figure_sync', 'rig_figure_get_stats',
-                  'rig_figure_set_profiling', 'rig_figure_debug_edges', 'rig_figure_stream', 'rig_figure_fence')
+                  'rig_figure_set_profiling', 'rig_figure_debug_edges', 'rig_figure_stream', 'rig_figure_fence',
+                  'rig_figure_blank_bands', 'rig_figure_set_blank_flags')
 
 _bound = False
 
@@ -210,6 +211,10 @@ def _lib():
         lib.rig_figure_stream.restype = vp
         lib.rig_figure_fence.argtypes = [vp, ctypes.POINTER(vp)]
         lib.rig_figure_fence.restype = ctypes.c_int
+        lib.rig_figure_blank_bands.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int)]
+        lib.rig_figure_blank_bands.restype = ctypes.c_int
+        lib.rig_figure_set_blank_flags.argtypes = [vp, ctypes.c_int]
+        lib.rig_figure_set_blank_flags.restype = ctypes.c_int
         lib.rig_figure_get_stats.argtypes = [vp, ctypes.POINTER(RigFigureStats)]
         lib.rig_figure_get_stats.restype = ctypes.c_int
         lib.rig_figure_set_profiling.argtypes = [vp, ctypes.c_int]
@@ -307,83 +312,40 @@ class FigureRenderer:
         self._check(self._lib.rig_figure_fence(self._h, ctypes.byref(e)))
         return int(e.value)
 
+    def set_blank_flags(self, on: bool):
+        """Makes renders into device memory also write one flag per band of rows (see `blank_bands`)."""
+        self._check(self._lib.rig_figure_set_blank_flags(self._h, 1 if on else 0))
+
+    def blank_bands(self):
+        """(device pointer, rows per band) of the blank-band flags k_figure wrote during the last render into device memory: one byte
+        per band and image, 1 = only background pixels (rig_figure_blank_bands).  Valid until the second next render; (0, rows)
+        unless `set_blank_flags(True)` was in force."""
+        p, rows = ctypes.c_void_p(), ctypes.c_int()
+        self._check(self._lib.rig_figure_blank_bands(self._h, ctypes.byref(p), ctypes.byref(rows)))
+        return int(p.value or 0), int(rows.value)
+
     def iter_png(self, scene: FigureScene, encoder, chunk: int = 4096, overlap: bool = True):
         """``fig.savefig`` for a whole batch (multigraph_generation/generator.py:256): renders `chunk` figures at a time into
         the encoder's device staging buffer and encodes them there, so only PNG bytes cross PCIe.  Yields
         (first_image_index, buffer, offsets): file i of the chunk is buffer[offsets[i]:offsets[i + 1]] (pinned host memory,
-        valid until the next iteration; the copy of one chunk's files overlaps the encode kernels of the next).  With `overlap` a worker thread runs the host path pipeline and launches k_figure
+        valid until the next iteration; the copy of one chunk's files overlaps the encode kernels of the next).  With `overlap` a
+        worker thread runs the host path pipeline and launches k_figure
         for the chunks ahead (two halves of the staging buffer) while this thread encodes and copies; the encoder is ordered
         after each render on the GPU (an event recorded right behind it), not by a host synchronisation."""
-        import queue
+        from .png import pipelined_png
         self._check_scene(scene)
         chunk = max(1, min(int(chunk), encoder.max_images, self.max_images))
-        starts = list(range(0, scene.n_images, chunk))
-        if not starts:
-            return
-        img_bytes = self.W * self.H * 3
-        two = overlap and len(starts) > 1
-        base = encoder.staging(2 * chunk if two else chunk)
 
-        def sub_scene(i0):
-            return scene if (i0 == 0 and scene.n_images <= chunk) else scene.slice(i0, min(scene.n_images, i0 + chunk))
+        def render_chunk(i0, ptr):
+            sub = scene if (i0 == 0 and scene.n_images <= chunk) else scene.slice(i0, min(scene.n_images, i0 + chunk))
+            self.render_to_device(sub, ptr, 'rgb', 0)            # asynchronous: returns once k_figure is enqueued
+            return sub.n_images, self.fence(), self.blank_bands()
 
-        if not two:
-            for i0 in starts:
-                sub = sub_scene(i0)
-                self.render_to_device(sub, base, 'rgb', 0)
-                encoder.wait_event(self.fence())
-                buf, off = encoder.encode(base, sub.n_images, 'rgb', 0)
-                yield i0, buf, off
-            return
-        free = threading.Semaphore(2)            # staging halves the worker may render into
-        ready: 'queue.Queue' = queue.Queue()
-        stop = threading.Event()
-
-        def worker():
-            try:
-                for k, i0 in enumerate(starts):
-                    free.acquire()
-                    if stop.is_set():
-                        return
-                    sub = sub_scene(i0)
-                    ptr = base + (k & 1) * chunk * img_bytes
-                    self.render_to_device(sub, ptr, 'rgb', 0)        # asynchronous: returns once k_figure is enqueued
-                    ready.put((i0, sub.n_images, ptr, self.fence()))
-            except BaseException as e:                               # re-raised on the consumer's thread
-                ready.put(e)
-
-        t = threading.Thread(target=worker, daemon=True)
-        t.start()
-        pending = None                                               # (first image, encoder slot) whose copy is in flight
+        self.set_blank_flags(True)                               # the encoder skips the bands k_figure left blank
         try:
-            for _ in starts:
-                item = ready.get()
-                if isinstance(item, BaseException):
-                    raise item
-                i0, n_img, ptr, ev = item
-                encoder.wait_event(ev)                               # exactly this chunk's render, not what the worker enqueues next
-                slot = encoder.encode_begin(ptr, n_img, 'rgb', 0)    # kernels run while the previous chunk's files are copied
-                free.release()                                       # the encoder has read this half
-                if pending is not None:
-                    p0, pslot = pending
-                    pending = None
-                    buf, off = encoder.encode_end(pslot)
-                    pending = (i0, slot)
-                    yield p0, buf, off
-                else:
-                    pending = (i0, slot)
-            if pending is not None:
-                p0, pslot = pending
-                pending = None
-                buf, off = encoder.encode_end(pslot)
-                yield p0, buf, off
+            yield from pipelined_png(encoder, range(0, scene.n_images, chunk), chunk, self.W * self.H * 3, render_chunk, 'rgb', overlap)
         finally:
-            stop.set()
-            if pending is not None:                                  # closed early: retire the slot in flight
-                encoder.encode_end(pending[1])
-            free.release()
-            free.release()
-            t.join()
+            self.set_blank_flags(False)
 
     def upload(self, scene: FigureScene, layout: str = 'rgb', stream: int = 0):
         self._check_scene(scene)

@@ -26,7 +26,8 @@ class RigPngStats(ctypes.Structure):
 
 
 PNG_EXPORTS = ('rig_png_create', 'rig_png_destroy', 'rig_png_last_error', 'rig_png_bound', 'rig_png_encode', 'rig_png_get_stats',
-               'rig_png_set_profiling', 'rig_png_staging', 'rig_png_wait_event', 'rig_png_encode_begin', 'rig_png_encode_end')
+               'rig_png_set_profiling', 'rig_png_staging', 'rig_png_wait_event', 'rig_png_encode_begin', 'rig_png_encode_end',
+               'rig_png_set_blank_hint')
 
 _bound = False
 _LAYOUTS = {'rgb': _abi.RIG_LAYOUT_RGB, 'bgr': _abi.RIG_LAYOUT_BGR}
@@ -51,6 +52,8 @@ def _lib():
         lib.rig_png_encode_begin.restype = ctypes.c_int
         lib.rig_png_encode_end.argtypes = [vp, ctypes.c_int, vp]
         lib.rig_png_encode_end.restype = ctypes.c_int
+        lib.rig_png_set_blank_hint.argtypes = [vp, vp, ctypes.c_int]
+        lib.rig_png_set_blank_hint.restype = ctypes.c_int
         lib.rig_png_wait_event.argtypes = [vp, vp]
         lib.rig_png_wait_event.restype = ctypes.c_int
         lib.rig_png_staging.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp)]
@@ -148,6 +151,11 @@ class PngEncoder:
         File i is buffer[offsets[i]:offsets[i + 1]].  The views are valid until the next call."""
         return self.encode_end(self.encode_begin(imgs_ptr, n, layout, stream))
 
+    def set_blank_hint(self, flags_ptr: int, rows_per_band: int):
+        """Blank-band flags (device pointer, e.g. FigureRenderer.blank_bands()) for the next encode / encode_begin only: rows marked 1
+        are white and are encoded without being read."""
+        self._check(self._lib.rig_png_set_blank_hint(self._h, flags_ptr or None, int(rows_per_band)))
+
     def wait_event(self, event: int):
         """The next `encode` starts only after `event` (a cudaEvent_t handle, e.g. FigureRenderer.fence()) has completed on the GPU."""
         self._check(self._lib.rig_png_wait_event(self._h, event))
@@ -166,6 +174,83 @@ class PngEncoder:
         self._check(self._lib.rig_png_get_stats(self._h, ctypes.byref(st)))
         return dict(kernel_launches=int(st.kernel_launches), images=int(st.images), png_bytes=int(st.png_bytes),
                     encode_ms=float(st.encode_ms), timed_images=int(st.timed_images))
+
+
+def pipelined_png(encoder: 'PngEncoder', starts: Sequence[int], chunk: int, img_bytes: int, render_chunk, layout: str = 'rgb',
+                  overlap: bool = True):
+    """The loop behind FigureRenderer.iter_png and Renderer.iter_png.  render_chunk(i0, device_ptr) renders the chunk that starts
+    at item i0 into device_ptr and returns (n_images, event[, (flags_ptr, rows_per_band)]): `event` is a cudaEvent_t handle recorded behind the render, or
+    0 when the render has already finished; the optional third item is the renderer's blank-band flags for that chunk
+    (PngEncoder.set_blank_hint).  With `overlap` a worker thread renders the chunks ahead into the two halves of the encoder's
+    staging buffer while the calling thread encodes; the copy of one chunk's files overlaps the kernels of the next (two encoder
+    slots).  Yields (i0, buffer, offsets)."""
+    import queue
+    starts = list(starts)
+    if not starts:
+        return
+    two = overlap and len(starts) > 1
+    base = encoder.staging(2 * chunk if two else chunk)
+    if not two:
+        for i0 in starts:
+            n_img, ev, *hint = render_chunk(i0, base)
+            if ev:
+                encoder.wait_event(ev)
+            if hint and hint[0][0]:
+                encoder.set_blank_hint(*hint[0])
+            buf, off = encoder.encode(base, n_img, layout, 0)
+            yield i0, buf, off
+        return
+    free = threading.Semaphore(2)            # staging halves the worker may render into
+    ready: 'queue.Queue' = queue.Queue()
+    stop = threading.Event()
+
+    def worker():
+        try:
+            for k, i0 in enumerate(starts):
+                free.acquire()
+                if stop.is_set():
+                    return
+                ptr = base + (k & 1) * chunk * img_bytes
+                n_img, ev, *hint = render_chunk(i0, ptr)
+                ready.put((i0, n_img, ptr, ev, hint[0] if hint else None))
+        except BaseException as e:                               # re-raised on the consumer's thread
+            ready.put(e)
+
+    t = threading.Thread(target=worker, daemon=True)
+    t.start()
+    pending = None                                               # (first item, encoder slot) whose copy is in flight
+    try:
+        for _ in starts:
+            item = ready.get()
+            if isinstance(item, BaseException):
+                raise item
+            i0, n_img, ptr, ev, hint = item
+            if ev:
+                encoder.wait_event(ev)                           # exactly this chunk's render, not what the worker enqueues next
+            if hint and hint[0]:
+                encoder.set_blank_hint(*hint)
+            slot = encoder.encode_begin(ptr, n_img, layout, 0)   # kernels run while the previous chunk's files are copied
+            free.release()                                       # the encoder has read this half
+            if pending is not None:
+                p0, pslot = pending
+                pending = None
+                buf, off = encoder.encode_end(pslot)
+                pending = (i0, slot)
+                yield p0, buf, off
+            else:
+                pending = (i0, slot)
+        if pending is not None:
+            p0, pslot = pending
+            pending = None
+            buf, off = encoder.encode_end(pslot)
+            yield p0, buf, off
+    finally:
+        stop.set()
+        if pending is not None:                                  # closed early: retire the slot in flight
+            encoder.encode_end(pending[1])
+        free.release()
+        free.release()
+        t.join()
 
 
 def split_files(buf: np.ndarray, offsets: np.ndarray) -> List[bytes]:

@@ -204,3 +204,80 @@ def test_two_batches_in_flight(built):
     assert split_files(*enc.encode(b.data_ptr(), 12)) == ref_b
     r.close()
     enc.close()
+
+
+def test_blank_band_hint(built):
+    """rig_figure_blank_bands -> rig_png_set_blank_hint: k_figure's flags are truthful (a flagged band is white in the rendered
+    pixels), the files encoded with the hint are byte-identical to the files encoded without it, the hint lasts for one call, and
+    it is really what the encoder goes by (an all-ones hint gives nearly white files)."""
+    import torch
+    from reasoning_image_generation_b200.figure import FigureRenderer
+    from reasoning_image_generation_b200.png import PngEncoder, split_files
+    from reasoning_image_generation_b200.synth_figure import synthetic_figure_scene
+    for (W, H) in ((512, 512), (256, 37)):
+        n = 40
+        sc = synthetic_figure_scene(n, W, H, seed=21, kind='multi')
+        r = FigureRenderer(W, H, max_images=64)
+        assert r.blank_bands()[0] == 0                       # nothing rendered yet
+        r.set_blank_flags(True)
+        dev = torch.empty(n * H * W * 3, dtype=torch.uint8, device='cuda')
+        r.render_to_device(sc, dev.data_ptr())
+        r.sync()
+        ptr, rows = r.blank_bands()
+        assert ptr and rows >= 1
+        bands = (H + rows - 1) // rows
+        flags = _dev_bytes(ptr, n * bands).reshape(n, bands)
+        imgs = dev.cpu().numpy().reshape(n, H, W, 3)
+        assert set(np.unique(flags)) <= {0, 1}
+        if H >= 128:
+            assert flags.mean() > 0.2                        # the synthetic figures leave blank margins
+        for i in range(n):
+            for b in np.nonzero(flags[i])[0]:
+                assert (imgs[i, b * rows:(b + 1) * rows] == 255).all(), (i, b)
+        enc = PngEncoder(W, H, max_images=64, channels=4)
+        plain = split_files(*enc.encode(dev.data_ptr(), n))
+        enc.set_blank_hint(ptr, rows)
+        hinted = split_files(*enc.encode(dev.data_ptr(), n))
+        assert hinted == plain
+        _check(plain, imgs)
+        if H == 512:
+            # all-ones hint: once a warp holds its copy of a blank piece (made from pixels it has read: the white images in front
+            # give every warp one), it takes the hint's word and the drawn rows of the last images come out white
+            from reasoning_image_generation_b200.png import decode_png_strict
+            nw = 120
+            both = torch.cat([torch.full((nw * H * W * 3,), 255, dtype=torch.uint8, device='cuda'), dev[:8 * H * W * 3]])
+            ones = torch.ones((nw + 8) * bands, dtype=torch.uint8, device='cuda')
+            enc2 = PngEncoder(W, H, max_images=nw + 8, channels=3)
+            enc2.set_blank_hint(ones.data_ptr(), rows)
+            files = split_files(*enc2.encode(both.data_ptr(), nw + 8))
+            drawn = sum(int((decode_png_strict(f) != 255).any(axis=2).sum()) for f in files[nw:])
+            assert drawn < 0.1 * int((imgs[:8] != 255).any(axis=3).sum())
+            enc2.close()
+        enc.set_blank_hint(ptr, rows)
+        enc.set_blank_hint(0, 0)                              # cleared again
+        assert split_files(*enc.encode(dev.data_ptr(), n)) == plain      # the hint was for one call
+        r.set_blank_flags(False)                              # off again: the next render writes no flags
+        r.render_to_device(sc, dev.data_ptr())
+        r.sync()
+        assert r.blank_bands()[0] == 0
+        r.close()
+        enc.close()
+
+
+def _dev_bytes(ptr, nbytes):
+    """Device memory at a raw pointer -> numpy (through cudaMemcpy of the runtime torch already loaded)."""
+    import ctypes
+    import torch
+    out = np.zeros(nbytes, np.uint8)
+    rt = ctypes.CDLL(None)
+    fn = getattr(rt, 'cudaMemcpy', None)
+    if fn is None:
+        import glob
+        import os
+        libs = glob.glob(os.path.join(os.path.dirname(torch.__file__), 'lib', 'libcudart*.so*')) + \
+            glob.glob(os.path.join(os.path.dirname(torch.__file__), '..', 'nvidia', 'cuda_runtime', 'lib', 'libcudart.so*'))
+        fn = ctypes.CDLL(libs[0]).cudaMemcpy
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    fn.restype = ctypes.c_int
+    assert fn(out.ctypes.data, ptr, nbytes, 2) == 0
+    return out

@@ -9,7 +9,7 @@ from reasoning_image_generation_b200.figure import FigureRenderer  # noqa: E402
 from reasoning_image_generation_b200.png import PngEncoder  # noqa: E402
 from reasoning_image_generation_b200.synth_figure import synthetic_figure_scene  # noqa: E402
 
-n, chunk = 16384, 4096
+n, chunk = 32768, 4096
 sc = synthetic_figure_scene(n, 512, 512, seed=1, kind='single')
 subs = [sc.slice(i, i + chunk) for i in range(0, n, chunk)]
 r = FigureRenderer(512, 512, max_images=chunk)
@@ -20,7 +20,7 @@ base = enc.staging(2 * chunk)
 
 def render(k):
     t = time.perf_counter()
-    r.render_to_device(subs[k % 4], base + (k & 1) * chunk * img, 'rgb', 0)
+    r.render_to_device(subs[k % len(subs)], base + (k & 1) * chunk * img, 'rgb', 0)
     r.sync()
     return time.perf_counter() - t
 
@@ -58,7 +58,9 @@ st = r.stats()
 print('host prepare %.2f ms' % st['prepare_ms'])
 
 # the product loop itself (iter_png: worker thread + two encoder slots)
-for ch in (3, 4):
+real_blank = r.blank_bands
+for ch, hint in ((3, True), (4, True), (4, False)):
+    r.blank_bands = real_blank if hint else (lambda: (0, 2))
     e2 = PngEncoder(512, 512, max_images=chunk, channels=ch)
     for rep in range(3):
         t0 = time.perf_counter()
@@ -66,5 +68,5 @@ for ch in (3, 4):
         for i0, buf, off in r.iter_png(sc, e2, chunk=chunk):
             tot += int(off[-1])
         dt = time.perf_counter() - t0
-    print('iter_png channels=%d: %.0f k img/s (%.1f KB/file)' % (ch, n / dt / 1e3, tot / n / 1e3))
+    print('iter_png channels=%d hint=%s: %.0f k img/s (%.1f KB/file)' % (ch, hint, n / dt / 1e3, tot / n / 1e3))
     e2.close()

@@ -9,7 +9,7 @@ from reasoning_image_generation_b200.figure import FigureRenderer  # noqa: E402
 from reasoning_image_generation_b200.png import PngEncoder  # noqa: E402
 from reasoning_image_generation_b200.synth_figure import synthetic_figure_scene  # noqa: E402
 
-n, chunk = 32768, 4096
+n, chunk = 32768, (int(sys.argv[2]) if len(sys.argv) > 2 else 4096)
 ch = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 sc = synthetic_figure_scene(n, 512, 512, seed=1, kind='single')
 r = FigureRenderer(512, 512, max_images=chunk)
