@@ -480,18 +480,20 @@ def sequence_leg(env, args, sampler, with_cpu):
     # ---- the same with the PNG files cv2.imwrite would produce as the deliverable (encoded on the device)
     from reasoning_image_generation_b200.png import PngEncoder
     enc = PngEncoder(512, 512, device=env.local, max_images=E2E_PANELS)
+    # (the whole step scene, E2E_PANELS at a time: a worker thread renders chunk k + 1 while chunk k is encoded and copied)
     for _ in range(2):
-        for p0, buf, off in r.iter_png(sub, enc, E2E_PANELS, 'rgb'):
+        for p0, buf, off in r.iter_png(scene, enc, E2E_PANELS, 'rgb'):
             pass
     barrier()
     t0 = time.perf_counter()
     seq_png_bytes = 0
     for _ in range(e2e_steps):
-        for p0, buf, off in r.iter_png(sub, enc, E2E_PANELS, 'rgb'):
+        for p0, buf, off in r.iter_png(scene, enc, E2E_PANELS, 'rgb'):
             seq_png_bytes += int(off[-1])
     torch.cuda.synchronize()
     (dt_png,) = env.max_over_ranks(time.perf_counter() - t0)
-    e2e_png_value = world * E2E_PANELS * e2e_steps / dt_png
+    e2e_png_value = world * n * e2e_steps / dt_png
+    h2d_png = 40 * scene.n_elements + 4 * (scene.n_panels + 1) + scene.n_panels
     enc.close()
 
     # ---- near-duplicate stage (reported beside `value`, not part of it)
@@ -585,10 +587,11 @@ def sequence_leg(env, args, sampler, with_cpu):
         'e2e_pixels': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                        'panels_per_step_per_gpu': E2E_PANELS, 'note': 'Renderer.render: host SoA scene in, every pixel copied to '
                        'pinned host memory (PCIe-bound); checksum %d' % checksum},
-        'e2e': {'value': e2e_png_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': seq_png_bytes // e2e_steps,
-                    'png_bytes_per_image': seq_png_bytes / (e2e_steps * E2E_PANELS), 'panels_per_step_per_gpu': E2E_PANELS,
+        'e2e': {'value': e2e_png_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d_png, 'd2h_bytes_per_step': seq_png_bytes // e2e_steps,
+                    'png_bytes_per_image': seq_png_bytes / (e2e_steps * n), 'panels_per_step_per_gpu': n, 'chunk': E2E_PANELS,
                     'note': 'Renderer.iter_png = save_image / cv2.imwrite for a batch: host SoA scene in, panels rendered and '
-                            'PNG-encoded on the device, finished files copied to pinned host memory'},
+                            'PNG-encoded on the device %d at a time, finished files copied to pinned host memory; the render of '
+                            'chunk k + 1 overlaps the encode and copy of chunk k' % E2E_PANELS},
         'gpu_launches': launches,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic, 'kernel': 'k_raster', 'peak_source': peak_src,
