@@ -387,7 +387,8 @@ def figure_leg(env, args, sampler):
     st2 = r2.stats()
     e2e_launches = st2['kernel_launches'] + enc.stats()['kernel_launches'] - l0
     e2e_value = env.world * FIG_E2E * e2e_steps / dt
-    h2d = int((16 * st2['edges'] + 32 * st2['layers']) * (FIG_E2E / FIG_E2E_CHUNK) + 8 * (FIG_E2E + 1))
+    # edges + layer headers of the step scene (the resident upload above holds the same scene) + per-image tables
+    h2d = int((16 * stats['edges'] + 32 * stats['layers']) * (FIG_E2E / n) + 8 * (FIG_E2E + 1))
     enc.close()
     r2.close()
     # ---- the same through the raw-pixel API: every pixel copied to pinned host memory (PCIe-bound)
@@ -409,7 +410,7 @@ def figure_leg(env, args, sampler):
         'value': value, 'ms_per_step': ms_max / args.steps, 'warmup': n_warm, 'clocks': clocks,
         'launches': stats['kernel_launches'] - launches0, 'stats': stats, 'n': n, 'multi_shape': multi_info,
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': png_bytes // e2e_steps,
-                'images_per_step_per_gpu': FIG_E2E, 'chunk': FIG_E2E_CHUNK, 'host_prepare_ms_per_chunk': st2['prepare_ms'],
+                'images_per_step_per_gpu': FIG_E2E, 'chunk': FIG_E2E_CHUNK,
                 'png_bytes_per_image': png_bytes / (e2e_steps * FIG_E2E), 'gpu_launches': e2e_launches,
                 'note': 'FigureRenderer.iter_png = fig.savefig for a batch: host artist arrays in (path pipeline on host threads, '
                         'edges uploaded), k_figure, device-side PNG encode (RGBA files), finished files copied to pinned host memory; host '

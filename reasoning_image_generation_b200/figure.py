@@ -332,18 +332,18 @@ class FigureRenderer:
         worker thread runs the host path pipeline and launches k_figure
         for the chunks ahead (two halves of the staging buffer) while this thread encodes and copies; the encoder is ordered
         after each render on the GPU (an event recorded right behind it), not by a host synchronisation."""
-        from .png import pipelined_png
+        from .png import chunk_plan, pipelined_png
         self._check_scene(scene)
         chunk = max(1, min(int(chunk), encoder.max_images, self.max_images))
 
-        def render_chunk(i0, ptr):
-            sub = scene if (i0 == 0 and scene.n_images <= chunk) else scene.slice(i0, min(scene.n_images, i0 + chunk))
+        def render_chunk(i0, i1, ptr):
+            sub = scene if (i0 == 0 and i1 == scene.n_images) else scene.slice(i0, i1)
             self.render_to_device(sub, ptr, 'rgb', 0)            # asynchronous: returns once k_figure is enqueued
             return sub.n_images, self.fence(), self.blank_bands()
 
         self.set_blank_flags(True)                               # the encoder skips the bands k_figure left blank
         try:
-            yield from pipelined_png(encoder, range(0, scene.n_images, chunk), chunk, self.W * self.H * 3, render_chunk, 'rgb', overlap)
+            yield from pipelined_png(encoder, chunk_plan(scene.n_images, chunk), chunk, self.W * self.H * 3, render_chunk, 'rgb', overlap)
         finally:
             self.set_blank_flags(False)
 

@@ -176,23 +176,31 @@ class PngEncoder:
                     encode_ms=float(st.encode_ms), timed_images=int(st.timed_images))
 
 
-def pipelined_png(encoder: 'PngEncoder', starts: Sequence[int], chunk: int, img_bytes: int, render_chunk, layout: str = 'rgb',
+def chunk_plan(n: int, chunk: int) -> List[Tuple[int, int]]:
+    """[i0, i1) ranges of `chunk` items (the last one shorter) covering n.  (Shorter first and last chunks, to shrink the two
+    pipeline stages nothing overlaps, measured no better: launches of 1-2 k images run at half the rate of 4 k ones.)"""
+    n, chunk = int(n), max(1, int(chunk))
+    return [(i, min(n, i + chunk)) for i in range(0, n, chunk)]
+
+
+def pipelined_png(encoder: 'PngEncoder', ranges: Sequence[Tuple[int, int]], chunk: int, img_bytes: int, render_chunk, layout: str = 'rgb',
                   overlap: bool = True):
-    """The loop behind FigureRenderer.iter_png and Renderer.iter_png.  render_chunk(i0, device_ptr) renders the chunk that starts
-    at item i0 into device_ptr and returns (n_images, event[, (flags_ptr, rows_per_band)]): `event` is a cudaEvent_t handle recorded behind the render, or
+    """The loop behind FigureRenderer.iter_png and Renderer.iter_png.  `ranges`: (i0, i1) item ranges of at most `chunk` items
+    (chunk_plan).  render_chunk(i0, i1, device_ptr) renders those items into device_ptr
+    and returns (n_images, event[, (flags_ptr, rows_per_band)]): `event` is a cudaEvent_t handle recorded behind the render, or
     0 when the render has already finished; the optional third item is the renderer's blank-band flags for that chunk
     (PngEncoder.set_blank_hint).  With `overlap` a worker thread renders the chunks ahead into the two halves of the encoder's
     staging buffer while the calling thread encodes; the copy of one chunk's files overlaps the kernels of the next (two encoder
     slots).  Yields (i0, buffer, offsets)."""
     import queue
-    starts = list(starts)
+    starts = list(ranges)
     if not starts:
         return
     two = overlap and len(starts) > 1
     base = encoder.staging(2 * chunk if two else chunk)
     if not two:
-        for i0 in starts:
-            n_img, ev, *hint = render_chunk(i0, base)
+        for i0, i1 in starts:
+            n_img, ev, *hint = render_chunk(i0, i1, base)
             if ev:
                 encoder.wait_event(ev)
             if hint and hint[0][0]:
@@ -206,12 +214,12 @@ def pipelined_png(encoder: 'PngEncoder', starts: Sequence[int], chunk: int, img_
 
     def worker():
         try:
-            for k, i0 in enumerate(starts):
+            for k, (i0, i1) in enumerate(starts):
                 free.acquire()
                 if stop.is_set():
                     return
                 ptr = base + (k & 1) * chunk * img_bytes
-                n_img, ev, *hint = render_chunk(i0, ptr)
+                n_img, ev, *hint = render_chunk(i0, i1, ptr)
                 ready.put((i0, n_img, ptr, ev, hint[0] if hint else None))
         except BaseException as e:                               # re-raised on the consumer's thread
             ready.put(e)

@@ -124,23 +124,23 @@ class Renderer:
             self._check(self._lib.rig_render_batch(self._h, ctypes.byref(s), out_ptr, 1, _LAYOUTS[layout], stream or None))
 
     def iter_png(self, scene: Scene, encoder, chunk: int = 4096, layout: str = 'bgr', overlap: bool = True):
-        """``save_image(path, img)`` = ``cv2.imwrite`` (src/utils.py:18-21) for a whole batch of panels: renders `chunk` panels at
+        """``save_image(path, img)`` = ``cv2.imwrite`` (src/utils.py:18-21) for a whole batch of panels: renders up to `chunk` panels at
         a time into the encoder's device staging buffer and encodes them there, so only PNG bytes cross PCIe.  `layout` is the
         channel order the panels are rendered in ('bgr' = what the reference hands to cv2.imwrite; the files hold RGB either
         way).  Yields (first_panel_index, buffer, offsets); file i of the chunk is buffer[offsets[i]:offsets[i + 1]] (pinned
         host memory, valid until the next iteration).  With `overlap` a worker thread renders the chunks ahead while this thread
         encodes, and the copy of one chunk's files overlaps the kernels of the next."""
-        from .png import pipelined_png
+        from .png import chunk_plan, pipelined_png
         self._check_scene(scene)
         chunk = max(1, min(int(chunk), encoder.max_images, self.max_panels))
 
-        def render_chunk(p0, ptr):
-            sub = scene if (p0 == 0 and scene.n_panels <= chunk) else scene.slice(p0, min(scene.n_panels, p0 + chunk))
+        def render_chunk(p0, p1, ptr):
+            sub = scene if (p0 == 0 and p1 == scene.n_panels) else scene.slice(p0, p1)
             self.render_to_device(sub, ptr, layout, 0)
             self.sync()                  # rendered on the context's own stream: finished before the encoder reads
             return sub.n_panels, 0
 
-        yield from pipelined_png(encoder, range(0, scene.n_panels, chunk), chunk, self.W * self.H * 3, render_chunk, layout, overlap)
+        yield from pipelined_png(encoder, chunk_plan(scene.n_panels, chunk), chunk, self.W * self.H * 3, render_chunk, layout, overlap)
 
     def upload(self, scene: Scene, layout: str = 'bgr', stream: int = 0):
         self._check_scene(scene)
