@@ -153,8 +153,19 @@ __device__ __forceinline__ void png_chunk_tokens(Sink &s, unsigned long long nz,
         const unsigned long long rem = nz >> pos;
         if (rem & 1ull) {
             const uint32_t t = T.lit[fb[pos]];
-            s.put(t & 0xffffffu, (int)(t >> 24));
-            pos++;
+            if ((rem & 2ull) && pos + 1 < CHUNK) {             // two literals in one go (at most 18 bits)
+                const uint32_t u = T.lit[fb[pos + 1]];
+                s.put((t & 0xffffffu) | ((u & 0xffffffu) << (t >> 24)), (int)((t >> 24) + (u >> 24)));
+                pos += 2;
+            } else {
+                s.put(t & 0xffffffu, (int)(t >> 24));
+                pos++;
+            }
+        } else if ((rem & 6ull) != 0ull) {                     // one or two zeros between literals (the alpha delta of an RGBA
+            const int gap = (rem & 2ull) ? 1 : 2;              // pixel): too short for a match, literal zeros
+            const uint32_t z = T.lit[0] & 0xffffffu;
+            s.put(gap == 2 ? (z | (z << 8)) : z, 8 * gap);
+            pos += gap;
         } else {
             const int gap = rem ? (__ffsll((long long)rem) - 1) : (CHUNK - pos);
             uint32_t r = (uint32_t)gap;
@@ -250,8 +261,9 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
       gp0 = __shfl_sync(0xffffffffu, gp0, 0);
       if (gp0 >= total_pieces) break;
       const unsigned long long gp1 = gp0 + PNG_CLAIM < total_pieces ? gp0 + PNG_CLAIM : total_pieces;
+      uint32_t image = (uint32_t)(gp0 / P.pieces_per_image), piece = (uint32_t)(gp0 % P.pieces_per_image) - 1u;
       for (unsigned long long gp = gp0; gp < gp1; gp++) {
-        const uint32_t image = (uint32_t)(gp / P.pieces_per_image), piece = (uint32_t)(gp % P.pieces_per_image);
+        if (++piece == P.pieces_per_image) { piece = 0u; image++; }
         const int y0 = (int)piece * PNG_ROWS, y1 = min(P.H, y0 + PNG_ROWS);
         const uint32_t L = (uint32_t)(y1 - y0) * RL;              // uncompressed bytes in this piece
         const uint8_t *img = P.imgs + (size_t)image * P.H * row_bytes;
@@ -263,7 +275,8 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
             bool hinted = false;
             if (P.blank) {                       // the renderer's word for it: no need to read the pixels
                 const uint8_t *fl = P.blank + (size_t)image * P.blank_bands;
-                hinted = (__ldg(fl + y0 / P.blank_rows) & __ldg(fl + (y1 - 1) / P.blank_rows)) != 0;
+                if (P.blank_rows == PNG_ROWS) hinted = __ldg(fl + piece) != 0;          // the renderer's bands are the pieces
+                else hinted = (__ldg(fl + y0 / P.blank_rows) & __ldg(fl + (y1 - 1) / P.blank_rows)) != 0;
             }
             if (!hinted || !canned.nbytes)       // (the copy every other blank piece will point at is made from pixels that were read)
             for (int y = y0; y < y1; y++)
@@ -372,21 +385,19 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
                 if (any && live) {                                  // (a dead lane's chunk is all zeros but its left neighbour is not)
 #pragma unroll
                     for (int i = 0; i < FW; i++) {
-                        const uint32_t m = __vsetne4(g[i], 0u);       // 1 per non-zero byte
-                        const uint32_t nib = (m & 1u) | ((m >> 7) & 2u) | ((m >> 14) & 4u) | ((m >> 21) & 8u);
+                        const uint32_t m = __vsetne4(g[i], 0u);       // 1 per non-zero byte, at bits 0, 8, 16, 24
+                        const uint32_t nib = (m * 0x01020408u) >> 24; // ... gathered into bits 0..3 (the partial products share no bit)
                         nz |= (unsigned long long)nib << (4 * i);
                     }
                     uint4 *dst = (uint4 *)fbytes;
 #pragma unroll
                     for (int i = 0; i < FW / 4; i++) dst[i] = make_uint4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
-                    // Adler partial sums of this chunk
-                    unsigned long long m = nz;
-                    while (m) {
-                        const int i = __ffsll((long long)m) - 1;
-                        m &= m - 1;
-                        const uint32_t v = fbytes[i];
-                        s0 += v;
-                        s1 += v * (uint32_t)i;
+                    // Adler partial sums of this chunk: sum of the bytes and sum of byte * index, four bytes per dot product
+#pragma unroll
+                    for (int i = 0; i < FW; i++) {
+                        const uint32_t t = __dp4a(g[i], 0x01010101u, 0u);
+                        s0 += t;
+                        s1 += __dp4a(g[i], 0x03020100u, 0u) + (uint32_t)(4 * i) * t;
                     }
                     ad_a += s0;
                     ad_b += (unsigned long long)(L - base) * s0 - s1;
