@@ -127,9 +127,16 @@ private:
     bool quit_ = false;
 };
 
+// Workers of one context: the box's cores, shared among the ranks torchrun started on it (LOCAL_WORLD_SIZE), at most 16.
+// (Measured on a 16-core box with one GPU: 4 / 8 / 16 / 32 / 64 threads -> 0.81 / 0.90 / 1.03 / 1.00 / 0.98 M figures/s end to end.)
 int host_thread_count()
 {
-    int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) {
+        const int ranks = atoi(e);
+        if (ranks > 1) hw = std::max(2u, hw / (unsigned)ranks);
+    }
+    int nt = (int)std::min(hw, 16u);
     if (const char *e = getenv("RIG_HOST_THREADS")) nt = std::max(1, atoi(e));
     return nt;
 }
