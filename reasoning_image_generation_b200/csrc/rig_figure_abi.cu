@@ -179,7 +179,7 @@ struct rig_figure_ctx {
     unsigned blank_next = 0;
     bool want_blank = false;
     const uint8_t *last_blank = nullptr;
-    uint32_t max_claim = 32;
+    uint32_t max_claim = 0;      // bands a warp claims at most per visit to the queue; 0: by launch size (RIG_FIG_MAX_CLAIM overrides)
     rig_figure_stats stats = {};
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool, ev_used;
@@ -409,7 +409,9 @@ int launch(rig_figure_ctx *c, uint32_t i0, uint32_t i1, uint8_t *out_dev, uint32
     P.n_images = i1 - i0;
     P.W = c->W; P.H = c->H;
     P.bg = 0x00ffffffu;
-    P.max_claim = c->max_claim;
+    // long claims keep a warp on one image (its layer headers stay in registers): best for big launches; short launches end
+    // with fewer stragglers on shorter claims (4 096 images: 0.93 ms with 8, 0.98 ms with 32; 32 768: 6.57 vs 6.38 ms)
+    P.max_claim = c->max_claim ? c->max_claim : (i1 - i0 <= 6144u ? 8u : (i1 - i0 <= 12288u ? 16u : 32u));
     P.blank = nullptr;
     c->last_blank = nullptr;
     if (c->want_blank && img_base == 0 && i0 == 0) {      // whole-batch launches into the caller's device buffer

@@ -8,7 +8,8 @@ big = synthetic_figure_scene(32768, 512, 512, seed=1, kind='single')
 out = torch.empty(32768 * 512 * 512 * 3, dtype=torch.uint8, device='cuda')
 r = FigureRenderer(512, 512, max_images=32768, max_artists=1 << 20)
 import os
-for n in ((32768,) if os.environ.get('ONLY_BIG') else (1024, 2048, 4096, 8192, 16384, 32768)):
+sizes = [int(x) for x in os.environ['SIZES'].split(',')] if os.environ.get('SIZES') else None
+for n in (sizes or ((32768,) if os.environ.get('ONLY_BIG') else (1024, 2048, 4096, 8192, 16384, 32768))):
     r.upload(big.slice(0, n) if n < 32768 else big)
     for _ in range(5):
         r.render_resident(out.data_ptr())
