@@ -160,6 +160,7 @@ private:
 // ---- stroker --------------------------------------------------------------------------------------
 struct SV {
     double x, y, d;   // d: distance to the next vertex of the sequence
+    double nx, ny;    // half-width offset of the segment to the next vertex: w (y' - y) / d, w (x' - x) / d (set by finish())
 };
 class StrokeGen {
 public:
@@ -184,24 +185,36 @@ public:
         const int n = (int)seq_.size();
         if (n < 3) closed = false;
         if (n < 2 + (closed ? 1 : 0)) return;
+        // math_stroke::calc_join derives both segments' offsets at every join, and every segment is visited by four joins (two per
+        // side); they are computed once here.  On the way back the segments run the other way: IEEE subtraction, multiplication
+        // and division are odd functions, so the offsets there are these negated (0.0 - v, which keeps a zero positive as the
+        // direct evaluation does).
+        const int nseg = closed ? n : n - 1;
+        for (int i = 0; i < nseg; i++) {
+            SV &c = seq_[i];
+            const SV &q = seq_[i + 1 < n ? i + 1 : 0];
+            c.nx = w_ * (q.y - c.y) / c.d;
+            c.ny = w_ * (q.x - c.x) / c.d;
+        }
         first_ = true;
         if (closed) {
             for (int i = 0; i < n; i++) {
-                const SV &p = seq_[(i + n - 1) % n], &c = seq_[i], &q = seq_[(i + 1) % n];
-                join(p, c, q, p.d, c.d);
+                const SV &p = seq_[i ? i - 1 : n - 1], &c = seq_[i], &q = seq_[i + 1 < n ? i + 1 : 0];
+                join(p, c, q, p.nx, p.ny, c.nx, c.ny, p.d, c.d);
             }
             sink_.close();
             first_ = true;
             for (int i = n - 1; i >= 0; i--) {
-                const SV &p = seq_[(i + n - 1) % n], &c = seq_[i], &q = seq_[(i + 1) % n];
-                join(q, c, p, c.d, p.d);
+                const SV &p = seq_[i ? i - 1 : n - 1], &c = seq_[i], &q = seq_[i + 1 < n ? i + 1 : 0];
+                join(q, c, p, 0.0 - c.nx, 0.0 - c.ny, 0.0 - p.nx, 0.0 - p.ny, c.d, p.d);
             }
             sink_.close();
         } else {
             cap(seq_[0], seq_[1], seq_[0].d);
-            for (int i = 1; i + 1 < n; i++) join(seq_[i - 1], seq_[i], seq_[i + 1], seq_[i - 1].d, seq_[i].d);
+            for (int i = 1; i + 1 < n; i++) join(seq_[i - 1], seq_[i], seq_[i + 1], seq_[i - 1].nx, seq_[i - 1].ny, seq_[i].nx, seq_[i].ny, seq_[i - 1].d, seq_[i].d);
             cap(seq_[n - 1], seq_[n - 2], seq_[n - 2].d);
-            for (int i = n - 2; i >= 1; i--) join(seq_[i + 1], seq_[i], seq_[i - 1], seq_[i].d, seq_[i - 1].d);
+            for (int i = n - 2; i >= 1; i--)
+                join(seq_[i + 1], seq_[i], seq_[i - 1], 0.0 - seq_[i].nx, 0.0 - seq_[i].ny, 0.0 - seq_[i - 1].nx, 0.0 - seq_[i - 1].ny, seq_[i].d, seq_[i - 1].d);
             sink_.close();
         }
     }
@@ -219,7 +232,7 @@ private:
     {
         const size_t n = seq_.size();
         if (n > 1 && !measure(seq_[n - 2], seq_[n - 1])) seq_.pop_back();
-        seq_.push_back(SV{x, y, 0.0});
+        seq_.push_back(SV{x, y, 0.0, 0.0, 0.0});
     }
     void settle(bool closed)
     {
@@ -304,10 +317,9 @@ private:
             out(v1.x + dx2, v1.y - dy2);
         }
     }
-    void join(const SV &v0, const SV &v1, const SV &v2, double len1, double len2)
+    // (dx1, dy1), (dx2, dy2): w (v1.y - v0.y) / len1, w (v1.x - v0.x) / len1 and the same for v1 -> v2
+    void join(const SV &v0, const SV &v1, const SV &v2, double dx1, double dy1, double dx2, double dy2, double len1, double len2)
     {
-        const double dx1 = w_ * (v1.y - v0.y) / len1, dy1 = w_ * (v1.x - v0.x) / len1;
-        const double dx2 = w_ * (v2.y - v1.y) / len2, dy2 = w_ * (v2.x - v1.x) / len2;
         const double cp = cross(v0.x, v0.y, v1.x, v1.y, v2.x, v2.y);
         if ((cp > kVertexDistEps && w_ > 0) || (cp < -kVertexDistEps && w_ < 0)) {
             double limit = ((len1 < len2) ? len1 : len2) / wabs_;
