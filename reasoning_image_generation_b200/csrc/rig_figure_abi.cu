@@ -4,6 +4,7 @@
 // threads, copy layers / edges / slab directories to HBM, launch k_figure (persistent, one CTA per SM).  With a host
 // destination the images go through two device staging buffers so the D2H copy of one chunk overlaps the next chunk.
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -127,11 +128,20 @@ private:
     bool quit_ = false;
 };
 
+// cores this process may run on (its affinity mask: what a container's cpuset or taskset leaves), else the machine's
+static unsigned usable_cores()
+{
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) return (unsigned)CPU_COUNT(&set);
+    return std::max(1u, std::thread::hardware_concurrency());
+}
+
 // Workers of one context: the box's cores, shared among the ranks torchrun started on it (LOCAL_WORLD_SIZE), at most 16.
 // (Measured on a 16-core box with one GPU: 4 / 8 / 16 / 32 / 64 threads -> 0.81 / 0.90 / 1.03 / 1.00 / 0.98 M figures/s end to end.)
 int host_thread_count()
 {
-    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    unsigned hw = usable_cores();
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) {
         const int ranks = atoi(e);
         if (ranks > 1) hw = std::max(2u, hw / (unsigned)ranks);

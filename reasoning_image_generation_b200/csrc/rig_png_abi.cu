@@ -1,5 +1,6 @@
 // rig_png_abi.cu -- the extern "C" boundary declared in include/rig_png.h.
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -87,6 +88,15 @@ size_t rig_png_bound(const rig_png_ctx *c, int n)
     return (size_t)n * ((size_t)c->ppi * per_piece + PNG_FILE_OVERHEAD);
 }
 
+// cores this process may run on (its affinity mask: what a container's cpuset or taskset leaves), else the machine's
+static unsigned usable_cores()
+{
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) return (unsigned)CPU_COUNT(&set);
+    return std::max(1u, std::thread::hardware_concurrency());
+}
+
 // How the host waits for the GPU: spinning in cudaStreamSynchronize keeps a core busy; sleeping on a blocking-sync event costs a
 // wake-up.  Measured end to end (figures, RGBA files): 16 cores per GPU: spin 1.04-1.05 M, sleep 0.87-0.97 M images/s; 4 cores per GPU
 // (where the spinning thread takes a quarter of what the renderer's host pipeline needs): spin 0.54-0.56 M, sleep 0.69-0.80 M.
@@ -94,10 +104,10 @@ size_t rig_png_bound(const rig_png_ctx *c, int n)
 static bool png_blocking_wait()
 {
     if (const char *e = getenv("RIG_PNG_BLOCKING_SYNC")) return atoi(e) != 0;
-    unsigned cores = std::max(1u, std::thread::hardware_concurrency());
+    unsigned cores = usable_cores();
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) {
         const int ranks = atoi(e);
-        if (ranks > 1) cores = std::max(1u, cores / (unsigned)ranks);
+        if (ranks > 1 && cores > (unsigned)ranks) cores = cores / (unsigned)ranks;
     }
     return cores < 8u;
 }
