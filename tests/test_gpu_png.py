@@ -281,3 +281,31 @@ def _dev_bytes(ptr, nbytes):
     fn.restype = ctypes.c_int
     assert fn(out.ctypes.data, ptr, nbytes, 2) == 0
     return out
+
+
+@pytest.mark.parametrize('rows', [1, 5, 64])
+def test_blank_hint_with_other_band_heights(built, rows):
+    """The hint's bands need not be the encoder's 2-row pieces (a renderer with 5-row bands, say): a piece is skipped only if
+    every band it touches is flagged.  Flags computed from the pixels on the host; files identical to the unhinted ones."""
+    import torch
+    from reasoning_image_generation_b200.figure import FigureRenderer
+    from reasoning_image_generation_b200.png import PngEncoder, split_files
+    from reasoning_image_generation_b200.synth_figure import synthetic_figure_scene
+    n, W, H = 200, 256, 131
+    sc = synthetic_figure_scene(n, W, H, seed=4, kind='single')
+    r = FigureRenderer(W, H, max_images=n)
+    imgs = r.render(sc, 'rgb')
+    r.close()
+    bands = (H + rows - 1) // rows
+    white_rows = (imgs == 255).all(axis=(2, 3))                              # [n, H]
+    flags = np.zeros((n, bands), np.uint8)
+    for b in range(bands):
+        flags[:, b] = white_rows[:, b * rows:(b + 1) * rows].all(axis=1)
+    dev = torch.from_numpy(imgs).cuda()
+    fl = torch.from_numpy(flags).cuda()
+    enc = PngEncoder(W, H, max_images=n)
+    plain = split_files(*enc.encode(dev.data_ptr(), n))
+    enc.set_blank_hint(fl.data_ptr(), rows)
+    assert split_files(*enc.encode(dev.data_ptr(), n)) == plain
+    _check(plain[:20], imgs[:20])
+    enc.close()
