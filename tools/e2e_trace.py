@@ -11,6 +11,7 @@ from reasoning_image_generation_b200.synth_figure import synthetic_figure_scene 
 
 n, chunk = 32768, (int(sys.argv[2]) if len(sys.argv) > 2 else 4096)
 ch = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+assert n % chunk == 0, 'chunk must divide n (a worker exception would leave the main loop waiting)'
 sc = synthetic_figure_scene(n, 512, 512, seed=1, kind='single')
 r = FigureRenderer(512, 512, max_images=chunk)
 enc = PngEncoder(512, 512, max_images=chunk, channels=ch)
