@@ -72,7 +72,8 @@ struct FigureMerged {
 };
 
 // A few host threads that stay alive between calls (spawning 16 threads per 4096-image chunk costs a visible part of the chunk's
-// host time).  run(n, f) calls f(0..n-1) on the workers and returns when all are done; one run at a time.
+// host time).  run(n, f) calls f(0..n-1) on the workers -- items are claimed one at a time from a shared counter, so a slow core
+// or a run of expensive items delays nobody else -- and returns when all are done; one run at a time.
 class HostPool {
 public:
     explicit HostPool(int nthreads)
@@ -93,7 +94,7 @@ public:
     void run(int n, const std::function<void(int)> &f)
     {
         std::unique_lock<std::mutex> g(m_);
-        f_ = &f; n_ = n; left_ = (int)th_.size(); gen_++;
+        f_ = &f; n_ = n; left_ = (int)th_.size(); next_.store(0, std::memory_order_relaxed); gen_++;
         cv_.notify_all();
         done_.wait(g, [this] { return left_ == 0; });
         f_ = nullptr;
@@ -112,7 +113,8 @@ private:
                 if (quit_) return;
                 f = f_; n = n_;
             }
-            for (int i = t; i < n; i += (int)th_.size()) (*f)(i);
+            (void)t;
+            for (int i; (i = next_.fetch_add(1, std::memory_order_relaxed)) < n;) (*f)(i);
             {
                 std::lock_guard<std::mutex> g(m_);
                 if (--left_ == 0) done_.notify_all();
@@ -124,6 +126,7 @@ private:
     std::condition_variable cv_, done_;
     const std::function<void(int)> *f_ = nullptr;
     int n_ = 0, left_ = 0;
+    std::atomic<int> next_{0};
     unsigned long long gen_ = 0;
     bool quit_ = false;
 };
@@ -247,15 +250,17 @@ int validate(rig_figure_ctx *c, const rig_figure_scene *s, char *err, int errlen
     return RIG_OK;
 }
 
-// host path pipeline over all images, on up to 16 threads.  Phase 1: every worker runs the pipeline over its range of images into
-// its own arrays; phase 2 (after the sizes are known): every worker copies its arrays to their place in the merged buffers,
+// host path pipeline over all images, on up to 16 threads.  Phase 1: the workers run the pipeline block by block of images, each
+// block into its own arrays; phase 2 (after the sizes are known): they copy the blocks to their place in the merged buffers,
 // rebasing the layers' edge / directory offsets.
 int prepare_all(const rig_figure_scene *s, int W, int H, bool bgr, HostPrep &hp, FigureMerged &out, std::vector<double> *cost, char *err, int errlen)
 {
     const int n = s->n_images;
-    const int nt = std::max(1, std::min(hp.pool.size(), (n + 255) / 256));
+    // work items: blocks of kBlock consecutive images (fewer, larger ones would leave the last worker's share to the slowest core)
+    constexpr int kBlock = 64;
+    const int nt = std::max(1, (n + kBlock - 1) / kBlock);
     if ((int)hp.parts.size() < nt) { hp.parts.resize(nt); hp.rcs.resize(nt); hp.errs.resize(nt, std::vector<char>(256, 0)); }
-    auto range = [&](int t, int &i0, int &i1) { i0 = (int)((long long)n * t / nt); i1 = (int)((long long)n * (t + 1) / nt); };
+    auto range = [&](int t, int &i0, int &i1) { i0 = t * kBlock; i1 = std::min(n, i0 + kBlock); };
     const std::function<void(int)> phase1 = [&](int t) {
         FigurePrepared &p = hp.parts[t];
         p.layers.clear(); p.edges.clear(); p.dir.clear(); p.image_layer_begin.clear();
@@ -263,7 +268,7 @@ int prepare_all(const rig_figure_scene *s, int W, int H, bool bgr, HostPrep &hp,
         range(t, i0, i1);
         hp.rcs[t] = figure_prepare(*s, W, H, bgr, i0, i1, p, hp.errs[t].data(), 256);
     };
-    if (nt == 1) phase1(0); else hp.pool.run(nt, phase1);
+    if (nt == 1 || hp.pool.size() == 1) { for (int t = 0; t < nt; t++) phase1(t); } else hp.pool.run(nt, phase1);
     for (int t = 0; t < nt; t++)
         if (hp.rcs[t]) {
             snprintf(err, errlen, "%s", hp.errs[t].data());
@@ -308,7 +313,7 @@ int prepare_all(const rig_figure_scene *s, int W, int H, bool bgr, HostPrep &hp,
         if (!p.edges.empty()) memcpy(out.edges.data() + eb, p.edges.data(), sizeof(FEdge) * p.edges.size());
         if (!p.dir.empty()) memcpy(out.dir.data() + db, p.dir.data(), sizeof(uint32_t) * p.dir.size());
     };
-    if (nt == 1) phase2(0); else hp.pool.run(nt, phase2);
+    if (nt == 1 || hp.pool.size() == 1) { for (int t = 0; t < nt; t++) phase2(t); } else hp.pool.run(nt, phase2);
     out.image_layer_begin[n] = (uint32_t)lbase[nt];
     return RIG_OK;
 }

@@ -562,10 +562,18 @@ void finish_layer(FigurePrepared &out, size_t e0, uint32_t rgba, int W, int H, s
 
 int figure_prepare(const rig_figure_scene &s, int W, int H, bool bgr, int i0, int i1, FigurePrepared &out, char *err, int errlen)
 {
-    std::vector<Node> path;
-    std::vector<SV> stroke_storage;
-    std::vector<FEdge> sort_tmp;
-    std::vector<uint32_t> sort_count;
+    // scratch that keeps its capacity from call to call (a call covers a block of a few dozen images)
+    struct Scratch {
+        std::vector<Node> path;
+        std::vector<SV> stroke_storage;
+        std::vector<FEdge> sort_tmp;
+        std::vector<uint32_t> sort_count;
+    };
+    thread_local Scratch scratch;
+    std::vector<Node> &path = scratch.path;
+    std::vector<SV> &stroke_storage = scratch.stroke_storage;
+    std::vector<FEdge> &sort_tmp = scratch.sort_tmp;
+    std::vector<uint32_t> &sort_count = scratch.sort_count;
     for (int img = i0; img < i1; img++) {
         out.image_layer_begin.push_back((uint32_t)out.layers.size());
         for (uint32_t a = s.image_artist_begin[img]; a < s.image_artist_begin[img + 1]; a++) {
