@@ -50,11 +50,21 @@ public:
         sy_ = py_ = y;
         pf_ = flags(x, y);
         open_ = false;
+        pi_ok_ = false;
     }
     void line_to(double x2, double y2)
     {
         open_ = true;
         const unsigned f2 = flags(x2, y2);
+        if ((pf_ | f2) == 0u) {                                  // both ends inside the box (nearly every segment): no clipping,
+            const int ix2 = iround(x2 * 256), iy2 = iround(y2 * 256);      // and the start was rounded as the previous end
+            const int ix1 = pi_ok_ ? ipx_ : iround(px_ * 256), iy1 = pi_ok_ ? ipy_ : iround(py_ * 256);
+            cells_line(ix1, iy1, ix2, iy2);
+            ipx_ = ix2; ipy_ = iy2; pi_ok_ = true;
+            px_ = x2; py_ = y2; pf_ = f2;
+            return;
+        }
+        pi_ok_ = false;
         if ((pf_ & 10u) == (f2 & 10u) && (pf_ & 10u) != 0u) {   // both above or both below the box
             px_ = x2; py_ = y2; pf_ = f2;
             return;
@@ -154,6 +164,8 @@ private:
     double cx1_, cy1_, cx2_, cy2_;
     double px_ = 0, py_ = 0, sx_ = 0, sy_ = 0;
     unsigned pf_ = 0;
+    int ipx_ = 0, ipy_ = 0;      // the previous point in 24.8 fixed point, valid if pi_ok_
+    bool pi_ok_ = false;
     bool open_ = false;
 };
 
