@@ -1,6 +1,6 @@
 """Development probe (GPU box): smoke + parity on a synthetic batch + first timings."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import __graft_entry__ as ge
 from reasoning_image_generation_b200 import Renderer

@@ -1,13 +1,13 @@
 """Soak test of the figure path on a GPU box: many synthetic and random scenes, k_figure (through the C ABI) against
 oracle/aggdraw.c, plus PNG round trips of a subset.  Prints one line per batch; exits non-zero on the first differing image.
-    python tools/soak_figure.py [images_per_kind]"""
+    python tests/tools/soak_figure.py [images_per_kind]"""
 import os
 import sys
 from multiprocessing import Pool
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from reasoning_image_generation_b200 import figure_paths as fp  # noqa: E402
 from reasoning_image_generation_b200.figure import FigureRenderer, FigureSceneBuilder  # noqa: E402
 from reasoning_image_generation_b200.synth_figure import synthetic_figure_scene  # noqa: E402
