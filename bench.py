@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 IMG_BYTES = 512 * 512 * 3
 PANELS_PER_STEP = 16384        # 12.9 GB of pixels per step per GPU: far larger than the 126 MB L2
 E2E_PANELS = 4096              # 3.2 GB pinned host destination per e2e step
-DEDUP_N = 1 << 20              # hashes in the all-pairs timing input (5.5e11 pairs)
+DEDUP_N = 10_000_000           # BASELINE configs[4]: hashes in the all-pairs timing input (5.0e13 pairs)
 FIG_PER_STEP = 32768           # 25.8 GB of pixels per step per GPU
 FIG_E2E = 32768               # images per e2e step (the whole step scene) ...
 FIG_E2E_CHUNK = 4096          # ... rendered + encoded 4096 at a time
@@ -543,6 +543,19 @@ def sequence_leg(env, args, sampler, with_cpu):
     dd_ms = e0.elapsed_time(e1)
     dd_ms, hash_ms = env.max_over_ranks(dd_ms, hash_ms)
     pairs = n_total * (n_total - 1) // 2
+    # roofline of the scan: integer pipes, against throughputs MEASURED on this device by the same library (k_int_pipe_peak).
+    # Per pair the filter issues 1 POPC and 2.5 ALU-pipe instructions (2 LOP3 + half a 3-input minimum); see rig_dedup.cuh.
+    popc_peak, alu_peak = r.int_pipe_peak('popc'), r.int_pipe_peak('lop3')
+    pairs_per_gpu_s = pairs / world / (dd_ms / 1e3)
+    t_popc, t_alu = 1.0 / popc_peak, 2.5 / alu_peak              # seconds per pair if that pipe alone were the limit
+    bound_pipe = 'popc' if t_popc >= t_alu else 'alu'
+    dd_roofline = {'bound': 'int_pipe', 'pipe': bound_pipe, 'achieved': pairs_per_gpu_s * (1.0 if bound_pipe == 'popc' else 2.5) / 1e12,
+                   'peak': (popc_peak if bound_pipe == 'popc' else alu_peak) / 1e12, 'unit': 'T lane-ops/s per GPU',
+                   'frac': pairs_per_gpu_s * max(t_popc, t_alu), 'popc_peak_ops_per_s': popc_peak, 'alu_peak_ops_per_s': alu_peak,
+                   'popc_per_pair': 1.0, 'alu_per_pair': 2.5, 'kernel': 'k_hamming',
+                   'peak_source': 'measured on this device: rig_int_pipe_peak (dependent POPC / LOP3 chains, 64 warps per SM)',
+                   'note': 'pairs counted algorithmically (N(N-1)/2); the kernel also evaluates the below-diagonal part of the diagonal '
+                           'tiles and the all_gather / all_reduce are inside the timed region'}
 
     # ---- overview compositor (layout.compose_grid): 7 consecutive panels of the rendered step per sample
     from reasoning_image_generation_b200.compose import GridCompositor, GridLayout
@@ -605,7 +618,7 @@ def sequence_leg(env, args, sampler, with_cpu):
                  'panel_read_gbs_per_gpu': n_samples * 7 * IMG_BYTES / (grid_ms / 1e3) / 1e9,
                  'note': 'k_grid: layout.compose_grid for a batch (INTER_AREA 512 -> 118 per cell + constant overlay), panels '
                          'already in HBM; bound: HBM read of the panels'},
-        'dedup': {'pairs_per_s': pairs / (dd_ms / 1e3), 'n_hashes': n_total, 'pairs': pairs, 'ms': dd_ms, 'threshold': 10,
+        'dedup': {'pairs_per_s': pairs / (dd_ms / 1e3), 'roofline': dd_roofline, 'n_hashes': n_total, 'pairs': pairs, 'ms': dd_ms, 'threshold': 10,
                   'hash_bits': 256, 'hit_pairs': int(hits.item()), 'dropped': int(drop.sum().item()),
                   'input': 'uniform random 256-bit hashes, seed 0, 1 % planted near-duplicates (SURVEY 8d)',
                   'exchange': 'nccl all_gather + max all_reduce' if dist is not None else 'none (1 rank)',

@@ -25,7 +25,7 @@ extern "C" {
 #define RIG_OK 0
 #define RIG_E_INVALID (-1)      /* bad argument */
 #define RIG_E_CUDA (-2)         /* CUDA runtime error; see rig_last_error */
-#define RIG_E_CAPACITY (-3)     /* batch larger than the context was created for */
+#define RIG_E_CAPACITY (-3)     /* batch larger than the context was created for, or (rig_sync) record arena overflow */
 #define RIG_E_UNSUPPORTED (-4)  /* valid for the reference but outside this build's limits */
 #define RIG_E_NODEVICE (-5)     /* no usable CUDA device */
 
@@ -93,6 +93,10 @@ int rig_render_resident(rig_ctx *ctx, uint8_t *out_device, void *stream);
  * rig_hash_batch(out_device), without re-reading the pixels from HBM.                                                  */
 int rig_render_resident_hashed(rig_ctx *ctx, uint8_t *out_device, uint64_t *hashes_device, void *stream);
 
+/* Waits for the context's streams.  Also the place where an asynchronous (device-destination / resident) render reports a
+ * draw-record arena overflow: RIG_E_CAPACITY, the pixels of that render are invalid, and the context's chunk budget has been
+ * halved for good (it is not reset by the next upload), so rendering the same scene again succeeds.  Chunks are sized from an
+ * upper bound that includes every wrap-around copy an element can have, so this is a defensive path, not an expected one.    */
 int rig_sync(rig_ctx *ctx);
 
 /* Counters of the last render on this context (for bench.py's gpu_launches / diagnostics). */
@@ -127,6 +131,11 @@ int rig_hash_batch(rig_ctx *ctx, const uint8_t *imgs_dev, int n, int layout, uin
  * NULL) accumulates the number of hit pairs found.                                                 */
 int rig_dedup(rig_ctx *ctx, const uint64_t *all_hashes_dev, uint64_t n_total, uint64_t row_begin, uint64_t row_end,
               int threshold, uint8_t *drop_flags_dev, uint64_t *hits_dev, void *stream);
+
+/* Measures the throughput of the integer pipe the scan is bound by, on this device: which = 0 POPC, 1 LOP3 (ALU pipe);
+ * lane-operations per second over all SMs (k_int_pipe_peak, dependent chains x 64 warps per SM, best of 3).  The denominator
+ * of the scan's roofline (SURVEY 8d asks for a measured, not an assumed, POPC peak).                                        */
+int rig_int_pipe_peak(rig_ctx *ctx, int which, double *ops_per_second);
 
 /* Page-locked host memory for scene / output buffers (plain cudaMallocHost / cudaFreeHost). */
 int rig_pinned_alloc(size_t bytes, void **out);

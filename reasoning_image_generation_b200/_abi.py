@@ -57,7 +57,7 @@ class RigStats(ctypes.Structure):
 EXPORTS = (
     'rig_create', 'rig_destroy', 'rig_last_error', 'rig_render_batch', 'rig_scene_upload',
     'rig_render_resident', 'rig_render_resident_hashed', 'rig_sync', 'rig_get_stats', 'rig_set_profiling', 'rig_debug_shape_tables',
-    'rig_hash_batch', 'rig_dedup', 'rig_hash_words', 'rig_pinned_alloc', 'rig_pinned_free',
+    'rig_hash_batch', 'rig_dedup', 'rig_hash_words', 'rig_int_pipe_peak', 'rig_pinned_alloc', 'rig_pinned_free',
 )
 
 _lib = None
@@ -103,6 +103,8 @@ def load() -> ctypes.CDLL:
     lib.rig_hash_batch.restype = ctypes.c_int
     lib.rig_dedup.argtypes = [vp, vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, vp, vp, vp]
     lib.rig_dedup.restype = ctypes.c_int
+    lib.rig_int_pipe_peak.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    lib.rig_int_pipe_peak.restype = ctypes.c_int
     lib.rig_pinned_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
     lib.rig_pinned_alloc.restype = ctypes.c_int
     lib.rig_pinned_free.argtypes = [vp]

@@ -61,7 +61,8 @@ struct rig_ctx {
     std::vector<uint32_t> h_begin;
     std::vector<uint32_t> nominal_recs, nominal_aux;   // per element, one copy
     std::vector<Chunk> chunks;
-    double budget_frac = 0.6;
+    double budget_frac = 0.6;                 // sticky: halved by every arena overflow, never reset by an upload
+    double nominal_scale = 1.0;               // RIG_NOMINAL_SCALE (tests: < 1 under-sizes the chunks to force the overflow path)
     uint32_t max_claim = 16, heavy_div = 4;   // RIG_MAX_CLAIM / RIG_HEAVY_DIV override (tuning)
     size_t chunk_panel_limit = 1u << 20;
     rig_stats stats = {};
@@ -105,6 +106,20 @@ void nominal_counts(int kind, int fill, int stroke, uint32_t &nrec, uint32_t &na
         nrec = l * ((fill ? n + 1 : 0) + n * stroke_recs(t));
         naux = l * (fill ? n : 0);
     }
+}
+
+// Upper bound of the wrap-around copies of an element (shapes.py:260-266 draws one copy per (+-W, +-H) offset whose shifted
+// bounding box meets the canvas): every outline vertex lies within `size` of the centre, so count the offsets whose
+// (centre +- size + stroke) box meets the canvas.  The device computes the exact mask; this only sizes the chunks.
+int wrap_copies_bound(int cx, int cy, int size, int stroke, int W, int H)
+{
+    const int r = size + stroke + 2;
+    int nx = 0, ny = 0;
+    for (int k = -1; k <= 1; k++) {
+        nx += (cx + k * W + r >= 0 && cx + k * W - r <= W);
+        ny += (cy + k * H + r >= 0 && cy + k * H - r <= H);
+    }
+    return std::max(1, nx) * std::max(1, ny);
 }
 
 void plan_chunks(rig_ctx *c, size_t panel_limit)
@@ -308,7 +323,15 @@ int upload_scene(rig_ctx *c, const rig_scene *s, int layout, cudaStream_t st)
     if (s->n_panels == 0) c->h_begin.assign(1, 0);
     c->nominal_recs.resize(s->n_elements);
     c->nominal_aux.resize(s->n_elements);
-    for (int i = 0; i < s->n_elements; i++) nominal_counts(s->kind[i], s->fill[i], s->stroke[i], c->nominal_recs[i], c->nominal_aux[i]);
+    for (int i = 0; i < s->n_elements; i++) {
+        nominal_counts(s->kind[i], s->fill[i], s->stroke[i], c->nominal_recs[i], c->nominal_aux[i]);
+        // x the wrap copies the element can have, so that a planned chunk cannot overflow the arena (the caller of the
+        // asynchronous device path may never call rig_sync and would otherwise not learn of missing elements)
+        const DElem &e = c->h_elems[i];
+        const double k = wrap_copies_bound(e.cx, e.cy, e.size, e.stroke, c->W, c->H) * c->nominal_scale;
+        c->nominal_recs[i] = (uint32_t)std::max(1.0, c->nominal_recs[i] * k);
+        c->nominal_aux[i] = (uint32_t)(c->nominal_aux[i] * k);
+    }
     if (s->n_elements) CK(c, cudaMemcpyAsync(c->d_elems, c->h_elems, sizeof(DElem) * s->n_elements, cudaMemcpyHostToDevice, st));
     CK(c, cudaMemcpyAsync(c->d_begin, c->h_begin.data(), sizeof(uint32_t) * (s->n_panels + 1), cudaMemcpyHostToDevice, st));
     if (s->n_panels) {
@@ -317,8 +340,7 @@ int upload_scene(rig_ctx *c, const rig_scene *s, int layout, cudaStream_t st)
     }
     // h_elems / h_begin are reused by the next upload: the copies above must have left the host
     CK(c, cudaStreamSynchronize(st));
-    c->budget_frac = 0.6;
-    plan_chunks(c, c->chunk_panel_limit);
+    plan_chunks(c, c->chunk_panel_limit);      // budget_frac is sticky: a scene that overflowed once is re-planned smaller
     return upload_order(c, st);
 }
 
@@ -417,6 +439,7 @@ int rig_create(int device, int W, int H, int max_panels, int max_elements, rig_c
     }
     c->raster_warps = warps;
     if (const char *e = getenv("RIG_MAX_CLAIM")) c->max_claim = (uint32_t)std::max(1, atoi(e));
+    if (const char *e = getenv("RIG_NOMINAL_SCALE")) { double v = atof(e); if (v > 0) c->nominal_scale = v; }
     if (const char *e = getenv("RIG_HEAVY_DIV")) c->heavy_div = (uint32_t)std::max(0, atoi(e));
     if (const char *e = getenv("RIG_WARPS")) { int w = atoi(e); if (w >= 1 && w <= warps) c->raster_warps = w; }
     c->raster_smem = raster_smem_bytes(W, c->raster_warps);
@@ -641,17 +664,55 @@ int rig_dedup(rig_ctx *c, const uint64_t *all_hashes_dev, uint64_t n_total, uint
     if (row_begin == row_end) return RIG_OK;
     CK(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    // macro tiles (row block I, column block J >= I + c0) that reach above the diagonal, enumerated row-major (rig_dedup.cuh)
     const uint64_t rows = row_end - row_begin;
-    const uint64_t gy_total = (rows + DD_TI - 1) / DD_TI, gx = (n_total + DD_TJ - 1) / DD_TJ;
-    // gridDim.y is limited to 65535: walk the row range in slabs
-    for (uint64_t y0 = 0; y0 < gy_total; y0 += 65535) {
-        const uint64_t gy = std::min<uint64_t>(65535, gy_total - y0);
-        dim3 grid((unsigned)gx, (unsigned)gy);
-        k_hamming<<<grid, DD_TI, 0, st>>>(all_hashes_dev, n_total, row_begin + y0 * DD_TI, row_end, threshold, drop_flags_dev,
-                                          (unsigned long long *)hits_dev);
+    const uint64_t n_row_blocks = (rows + DD_B - 1) / DD_B, gx = (n_total + DD_B - 1) / DD_B;
+    const uint64_t c0 = (row_begin + 1) / DD_B;
+    if (c0 >= gx) return RIG_OK;                        // the only row left is the last one: no column above it
+    const uint64_t per_row0 = gx - c0;
+    const uint64_t nI = std::min<uint64_t>(n_row_blocks, per_row0);
+    const uint64_t tiles = nI * per_row0 - nI * (nI - 1) / 2;
+    const uint64_t max_grid = 1u << 30;
+    for (uint64_t t0 = 0; t0 < tiles; t0 += max_grid) {
+        const unsigned g = (unsigned)std::min<uint64_t>(max_grid, tiles - t0);
+        k_hamming<<<g, DD_THREADS, 0, st>>>(all_hashes_dev, n_total, row_begin, row_end, threshold, (long long)per_row0, (unsigned)c0, t0,
+                                            drop_flags_dev, (unsigned long long *)hits_dev);
         c->stats.kernel_launches++;
     }
     CK(c, cudaGetLastError());
+    return RIG_OK;
+}
+
+int rig_int_pipe_peak(rig_ctx *c, int which, double *ops_per_second)
+{
+    if (!c || !ops_per_second) return RIG_E_INVALID;
+    if (which != 0 && which != 1) return fail(c, RIG_E_INVALID, "which must be 0 (POPC) or 1 (LOP3)");
+    CK(c, cudaSetDevice(c->device));
+    uint32_t *d_out = nullptr;
+    const int ctas = c->sm_count * 8, iters = 4096;
+    CK(c, cudaMalloc(&d_out, sizeof(uint32_t) * 256 * (size_t)ctas));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t err = cudaEventCreate(&e0);
+    if (err == cudaSuccess) err = cudaEventCreate(&e1);
+    float best = 0.f;
+    for (int rep = 0; rep < 4 && err == cudaSuccess; rep++) {          // rep 0 warms up
+        cudaEventRecord(e0, c->stream);
+        if (which == 0) k_int_pipe_peak<0><<<ctas, 256, 0, c->stream>>>(d_out, 0x2545f491u + rep, iters);
+        else k_int_pipe_peak<1><<<ctas, 256, 0, c->stream>>>(d_out, 0x2545f491u + rep, iters);
+        cudaEventRecord(e1, c->stream);
+        err = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && (best == 0.f || ms < best)) best = ms;
+    }
+    c->stats.kernel_launches += 4;
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(d_out);
+    CK(c, err);
+    // per thread and iteration: 64 chain steps, each 1 POPC (which = 0) or 2 LOP3 (which = 1)
+    const double ops = (double)ctas * 256.0 * iters * 64.0 * (which == 0 ? 1.0 : 2.0);
+    *ops_per_second = best > 0.f ? ops / (best * 1e-3) : 0.0;
     return RIG_OK;
 }
 

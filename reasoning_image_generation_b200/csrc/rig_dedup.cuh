@@ -110,41 +110,137 @@ __global__ void k_hash_bits_fused(const uint32_t *__restrict__ sums, const uint8
     }
 }
 
-// All-pairs scan.  CTA = 256 rows x one column tile of TJ hashes staged in shared memory; a thread
-// keeps its row hash in registers and walks the tile (every lane reads the same shared address:
-// broadcast).  The first 64 bits reject almost every pair with 2 POPCs; the remaining 192 bits are
-// only examined when some lane of the warp is still under the threshold.
-constexpr int DD_TI = 256;
-constexpr int DD_TJ = 1024;
+// All-pairs scan.
+//
+// Work unit: a macro tile = DD_B rows x DD_B columns of the pair matrix (only tiles that reach above the diagonal exist; the
+// 1-D grid enumerates them row-major).  The CTA stages the FIRST 64 BITS of the DD_B column hashes in shared memory (32 KB) and
+// walks them once per pass of DD_R x 256 rows; a thread keeps the first 64 bits of its DD_R rows in registers.
+//
+// Per pair the inner loop costs 1 POPC:   f = (a.lo ^ t.lo) | (a.hi ^ t.hi)      2 x LOP3
+//                                         p = popc(f)                            1 x POPC
+//                                         m = min(m, p, p')                      1/2 x VIMNMX3
+// popc(f) <= popc of the 64-bit xor <= the 256-bit distance, so `popc(f) > thr` rejects exactly (no false negatives); for
+// unrelated hashes f has ~24 of 32 bits set, so the filter passes ~1e-8 of the pairs at thr = 10.  Only when the minimum over
+// a group of 8 columns x DD_R rows is <= thr does the thread re-walk the group, fetch the full 256-bit hashes (L2) and apply
+// the definition `dist <= thr && i < j`.  The column word pair is one broadcast LDS.128 per 2 columns and DD_R rows.
+// Bound: the POPC pipe (a quarter-rate pipe: 16 lanes / clk / SM measured by k_int_pipe_peak<0>, see bench.py `dedup.roofline`).
+constexpr int DD_B = 4096;          // macro tile edge
+constexpr int DD_R = 4;             // rows per thread and pass
+constexpr int DD_THREADS = 256;
+constexpr int DD_G = 8;             // columns per group (one min-test per group)
 
-__global__ void __launch_bounds__(DD_TI)
-k_hamming(const uint64_t *__restrict__ h, unsigned long long n, unsigned long long row_begin, unsigned long long row_end,
-          int thr, uint8_t *__restrict__ drop, unsigned long long *__restrict__ hits)
+__device__ __forceinline__ int dd_pre(uint2 a, uint2 t) { return __popc((a.x ^ t.x) | (a.y ^ t.y)); }
+
+// The rare path: re-walk one group (operands re-read from shared memory / L2, so that nothing of the hot loop's registers has
+// its address taken) and apply the definition on the full 256 bits.  Returns the hits of this thread.
+__device__ __noinline__ unsigned dd_confirm(const uint64_t *__restrict__ h, unsigned long long n, unsigned long long i_end, int thr,
+                                            unsigned long long i_first, const uint2 *cols, unsigned long long j_first, uint8_t *__restrict__ drop)
 {
-    __shared__ uint64_t tile[DD_TJ * HASH_WORDS];
-    const unsigned long long i0 = row_begin + (unsigned long long)blockIdx.y * DD_TI;
-    const unsigned long long j0 = (unsigned long long)blockIdx.x * DD_TJ;
-    if (j0 + DD_TJ <= i0 + 1 || i0 >= row_end) return;   // tile entirely at or below the diagonal
-    const unsigned long long jn = (n - j0 < (unsigned long long)DD_TJ) ? n - j0 : DD_TJ;
-    for (unsigned long long k = threadIdx.x; k < jn * HASH_WORDS; k += blockDim.x) tile[k] = h[j0 * HASH_WORDS + k];
+    unsigned found = 0;
+#pragma unroll 1
+    for (int r = 0; r < DD_R; r++) {
+        const unsigned long long i = i_first + (unsigned long long)r * DD_THREADS;
+        if (i >= i_end) break;
+        const ulonglong2 *hi = (const ulonglong2 *)(h + i * HASH_WORDS);
+        const ulonglong2 x0 = __ldg(hi), x1 = __ldg(hi + 1);
+        const uint2 a = make_uint2((uint32_t)x0.x, (uint32_t)(x0.x >> 32));
+#pragma unroll 1
+        for (int c = 0; c < DD_G; c++) {
+            const unsigned long long j = j_first + c;
+            if (j >= n) break;
+            if (j <= i || dd_pre(a, cols[c]) > thr) continue;
+            const ulonglong2 *hj = (const ulonglong2 *)(h + j * HASH_WORDS);
+            const ulonglong2 y0 = __ldg(hj), y1 = __ldg(hj + 1);
+            const int d = __popcll(x0.x ^ y0.x) + __popcll(x0.y ^ y0.y) + __popcll(x1.x ^ y1.x) + __popcll(x1.y ^ y1.y);
+            if (d <= thr) { drop[j] = 1; found++; }
+        }
+    }
+    return found;
+}
+
+// tile id -> (row block I, column block J): row block I holds the column blocks J >= I + c0, `per_row0` of them for I = 0
+__device__ __forceinline__ void dd_tile(unsigned long long t, long long per_row0, unsigned &I, unsigned &J_off)
+{
+    // P(I) = I * per_row0 - I (I - 1) / 2 tiles precede row block I; largest I with P(I) <= t
+    const double b = 2.0 * (double)per_row0 + 1.0;
+    long long i = (long long)((b - sqrt(fmax(b * b - 8.0 * (double)t, 0.0))) * 0.5);
+    if (i < 0) i = 0;
+    while (i > 0 && (unsigned long long)(i * per_row0 - i * (i - 1) / 2) > t) i--;
+    while ((unsigned long long)((i + 1) * per_row0 - (i + 1) * i / 2) <= t) i++;
+    I = (unsigned)i;
+    J_off = (unsigned)(t - (unsigned long long)(i * per_row0 - i * (i - 1) / 2));
+}
+
+__global__ void __launch_bounds__(DD_THREADS)
+k_hamming(const uint64_t *__restrict__ h, unsigned long long n, unsigned long long row_begin, unsigned long long row_end,
+          int thr, long long per_row0, unsigned c0, unsigned long long tile0, uint8_t *__restrict__ drop, unsigned long long *__restrict__ hits)
+{
+    __shared__ __align__(16) uint2 tile[DD_B];
+    unsigned I, Joff;
+    dd_tile(tile0 + blockIdx.x, per_row0, I, Joff);
+    const unsigned long long i0 = row_begin + (unsigned long long)I * DD_B;
+    const unsigned long long j0 = ((unsigned long long)I + c0 + Joff) * DD_B;
+    const unsigned long long jn = (n - j0 < (unsigned long long)DD_B) ? n - j0 : DD_B;
+    for (unsigned k = threadIdx.x; k < DD_B; k += DD_THREADS)
+        tile[k] = k < jn ? *(const uint2 *)(h + (j0 + k) * HASH_WORDS) : make_uint2(0u, 0u);
     __syncthreads();
-    const unsigned long long i = i0 + threadIdx.x;
-    const bool live = i < row_end && i < n;
-    uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    if (live) { a0 = h[i * 4]; a1 = h[i * 4 + 1]; a2 = h[i * 4 + 2]; a3 = h[i * 4 + 3]; }
+    const unsigned long long i_end = (i0 + DD_B < row_end) ? i0 + DD_B : row_end;
+    const int ngroups = (int)((jn + DD_G - 1) / DD_G);
     unsigned long long found = 0;
-    for (unsigned long long jj = 0; jj < jn; jj++) {
-        const uint64_t *t = tile + jj * HASH_WORDS;
-        int d = __popcll(a0 ^ t[0]);
-        bool cand = live && d <= thr && (j0 + jj) > i;
-        if (__any_sync(0xffffffffu, cand)) {
-            if (cand) {
-                d += __popcll(a1 ^ t[1]) + __popcll(a2 ^ t[2]) + __popcll(a3 ^ t[3]);
-                if (d <= thr) { drop[j0 + jj] = 1; found++; }
+#pragma unroll 1
+    for (unsigned long long ip = i0; ip < i_end; ip += DD_R * DD_THREADS) {
+        // columns at or below this pass's first row cannot pair with it: start at the group holding column ip + 1
+        const int g_begin = (ip + 1 > j0) ? (int)((ip + 1 - j0) / DD_G) : 0;
+        if (g_begin >= ngroups) break;
+        uint2 a[DD_R];
+        const unsigned long long i_first = ip + threadIdx.x;
+#pragma unroll
+        for (int r = 0; r < DD_R; r++) {
+            const unsigned long long i = i_first + (unsigned long long)r * DD_THREADS;
+            // rows past the range keep the previous row's bits: the confirm step ignores them
+            a[r] = i < i_end ? *(const uint2 *)(h + i * HASH_WORDS) : (r ? a[r - 1] : make_uint2(0x55555555u, 0xaaaaaaaau));
+        }
+#pragma unroll 1
+        for (int g = g_begin; g < ngroups; g++) {
+            const uint4 *q = (const uint4 *)(tile + g * DD_G);
+            int m = 64;
+#pragma unroll
+            for (int k = 0; k < DD_G / 2; k++) {
+                const uint4 w = q[k];
+#pragma unroll
+                for (int r = 0; r < DD_R; r++) m = __vimin3_s32(m, dd_pre(a[r], make_uint2(w.x, w.y)), dd_pre(a[r], make_uint2(w.z, w.w)));
             }
+            if (m <= thr) found += dd_confirm(h, n, i_end, thr, i_first, tile + g * DD_G, j0 + (unsigned long long)g * DD_G, drop);
         }
     }
     if (hits && found) atomicAdd(hits, found);
+}
+
+// Integer-pipe peaks for the scan's roofline ("measure with a microbenchmark; do not assume").
+// WHICH = 0: POPC; 1: LOP3 (the ALU pipe the filter's xor/or and the 3-input minimum share).  8 independent chains per thread.
+template <int WHICH>
+__global__ void __launch_bounds__(256)
+k_int_pipe_peak(uint32_t *__restrict__ out, uint32_t seed, int iters)
+{
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = seed * (threadIdx.x + 1u) + 0x9e3779b9u * (k + blockIdx.x);
+    const uint32_t y = seed ^ 0x5bd1e995u, z = seed * 3u + 1u;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (WHICH == 0) x[k] = __popc(x[k]);                     // a pure dependent POPC chain (its timing does not depend on the data)
+                else x[k] = (x[k] ^ y) | (x[(k + 1) & 7] & z);            // two LOP3 (four runtime inputs)
+            }
+        }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= x[k];
+    if (s == 0x12345678u + y) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 }  // namespace rig

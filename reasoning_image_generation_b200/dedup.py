@@ -108,16 +108,24 @@ class DedupFilter:
         import torch.distributed as dist
         torch = self.torch
         world, rank = dist.get_world_size(), dist.get_rank()
-        counts = [torch.zeros(1, dtype=torch.int64, device=self.dev) for _ in range(world)]
-        dist.all_gather(counts, torch.tensor([local_hashes.shape[0]], dtype=torch.int64, device=self.dev))
-        counts = [int(c.item()) for c in counts]
-        parts = [torch.empty((c, HASH_WORDS), dtype=torch.int64, device=self.dev) for c in counts]
-        dist.all_gather(parts, local_hashes.contiguous())
-        allh = torch.cat(parts, dim=0)
-        b, e = row_blocks(allh.shape[0], world)[rank]
-        drop, hits = self.scan(allh, threshold, b, e)
-        torch.cuda.current_stream(self.dev).synchronize()
-        self.r.sync()
+        n_local = int(local_hashes.shape[0])
+        # one collective + one host read for the slice sizes; equal slices (the usual case) are gathered straight into place
+        counts_t = torch.empty(world, dtype=torch.int64, device=self.dev)
+        dist.all_gather_into_tensor(counts_t, torch.tensor([n_local], dtype=torch.int64, device=self.dev))
+        counts = counts_t.tolist()
+        n_total, n_max = sum(counts), max(counts)
+        local = local_hashes.contiguous()
+        if n_max * world == n_total:
+            allh = torch.empty((n_total, HASH_WORDS), dtype=torch.int64, device=self.dev)
+            dist.all_gather_into_tensor(allh, local)
+        else:
+            padded = torch.zeros((n_max, HASH_WORDS), dtype=torch.int64, device=self.dev)
+            padded[:n_local] = local
+            slab = torch.empty((world, n_max, HASH_WORDS), dtype=torch.int64, device=self.dev)
+            dist.all_gather_into_tensor(slab, padded)
+            allh = torch.cat([slab[g, :c] for g, c in enumerate(counts)], dim=0)
+        b, e = row_blocks(n_total, world)[rank]
+        drop, hits = self.scan(allh, threshold, b, e)           # on torch's current stream: the collectives below follow it
         dist.all_reduce(drop, op=dist.ReduceOp.MAX)
         dist.all_reduce(hits, op=dist.ReduceOp.SUM)
         return drop, hits, allh

@@ -363,8 +363,7 @@ class DatasetWriter:
         scene = concat_scenes([em.scene for em in ems])
         with torch.cuda.device(self.device):
             dev = torch.empty((scene.n_panels, self.H, self.W, 3), dtype=torch.uint8, device=f'cuda:{self.device}')
-            self.renderer.render_to_device(scene, dev.data_ptr(), layout='bgr')
-            self.renderer.sync()
+            self.renderer.render_to_device_checked(scene, dev.data_ptr(), layout='bgr')
             buf, off = self.panel_png.encode(dev.data_ptr(), scene.n_panels, layout='bgr')
             paths, which = [], []
             for em, b in zip(ems, base):

@@ -123,6 +123,18 @@ class Renderer:
         with self._lock:
             self._check(self._lib.rig_render_batch(self._h, ctypes.byref(s), out_ptr, 1, _LAYOUTS[layout], stream or None))
 
+    def render_to_device_checked(self, scene: Scene, out_ptr: int, layout: str = 'bgr', attempts: int = 6):
+        """render_to_device + sync; a draw-record arena overflow (RIG_E_CAPACITY from rig_sync, which also halves the context's
+        sticky chunk budget) is retried here instead of reaching the caller in the middle of a batch."""
+        for k in range(attempts):
+            self.render_to_device(scene, out_ptr, layout, 0)
+            try:
+                self.sync()
+                return
+            except RigError as e:
+                if e.code != _abi.RIG_E_CAPACITY or k == attempts - 1:
+                    raise
+
     def iter_png(self, scene: Scene, encoder, chunk: int = 4096, layout: str = 'bgr', overlap: bool = True):
         """``save_image(path, img)`` = ``cv2.imwrite`` (src/utils.py:18-21) for a whole batch of panels: renders up to `chunk` panels at
         a time into the encoder's device staging buffer and encodes them there, so only PNG bytes cross PCIe.  `layout` is the
@@ -136,8 +148,7 @@ class Renderer:
 
         def render_chunk(p0, p1, ptr):
             sub = scene if (p0 == 0 and p1 == scene.n_panels) else scene.slice(p0, p1)
-            self.render_to_device(sub, ptr, layout, 0)
-            self.sync()                  # rendered on the context's own stream: finished before the encoder reads
+            self.render_to_device_checked(sub, ptr, layout)   # context's own stream: finished before the encoder reads
             return sub.n_panels, 0
 
         yield from pipelined_png(encoder, chunk_plan(scene.n_panels, chunk), chunk, self.W * self.H * 3, render_chunk, layout, overlap)
@@ -181,6 +192,14 @@ class Renderer:
         with self._lock:
             self._check(self._lib.rig_dedup(self._h, hashes_ptr, n_total, row_begin, row_end, threshold, drop_ptr,
                                             hits_ptr or None, stream or None))
+
+
+    def int_pipe_peak(self, which: str = 'popc') -> float:
+        """Measured lane-operations per second of the POPC ('popc') or ALU ('lop3') pipe on this device (rig_int_pipe_peak)."""
+        v = ctypes.c_double()
+        with self._lock:
+            self._check(self._lib.rig_int_pipe_peak(self._h, {'popc': 0, 'lop3': 1}[which], ctypes.byref(v)))
+        return float(v.value)
 
 
 # ---- drop-in for the reference method ---------------------------------------------------------

@@ -51,6 +51,19 @@ def test_every_declared_png_symbol_is_exported(built):
     assert sorted(png.PNG_EXPORTS) == names
 
 
+def test_every_declared_grid_symbol_is_exported(built):
+    """include/rig_grid.h: the overview compositor of the same library."""
+    from reasoning_image_generation_b200 import compose
+    lib = _abi.load()
+    txt = open(os.path.join(ROOT, 'include', 'rig_grid.h')).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    names = sorted(set(re.findall(r'\b(rig_grid_[a-z_]+)\s*\(', txt)))
+    assert len(names) == 7
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(compose.GRID_EXPORTS) == names
+
+
 def test_strict_png_reader_agrees_with_libpng():
     """The tests' pure-zlib PNG reader decodes what cv2.imwrite (libpng) writes."""
     import cv2

@@ -42,7 +42,7 @@ def test_hash_kernel_on_noise(ctx):
     assert (h.cpu().numpy().view(np.uint64) == want).all()
 
 
-@pytest.mark.parametrize('n,thr', [(1, 10), (257, 10), (5000, 10), (5000, 0), (3001, 40)])
+@pytest.mark.parametrize('n,thr', [(1, 10), (257, 10), (5000, 10), (5000, 0), (3001, 40), (4096, 3), (4097, 3), (20011, 10)])
 def test_hamming_scan_matches_oracle(ctx, n, thr):
     r, f, torch = ctx
     rng = np.random.default_rng(n + thr)
@@ -55,6 +55,16 @@ def test_hamming_scan_matches_oracle(ctx, n, thr):
         flips = int(rng.integers(0, thr + 3))
         v = h[i].copy().view(np.uint64)
         for b in rng.choice(256, flips, replace=False):
+            v[b // 64] ^= np.uint64(1) << np.uint64(b % 64)
+        h[j] = v.view(np.int64)
+    # pairs that pass the 64-bit pre-filter of k_hamming (equal first words) but differ by thr + 1 bits further up, and
+    # pairs that differ only in the first words
+    for k in range(n // 200):
+        i, j = sorted(rng.integers(0, n, 2))
+        if i == j:
+            continue
+        v = h[i].copy().view(np.uint64)
+        for b in rng.choice(np.arange(64, 256), thr + 1 - (k & 1), replace=False):
             v[b // 64] ^= np.uint64(1) << np.uint64(b % 64)
         h[j] = v.view(np.int64)
     hu = h.view(np.uint64)

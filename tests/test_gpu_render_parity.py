@@ -187,6 +187,38 @@ def test_record_arena_overflow_is_retried_not_silently_wrong(built):
     small.close()
 
 
+def test_forced_arena_overflow_on_every_path(built, monkeypatch):
+    """Chunks are sized from an upper bound that includes wrap-around copies, so the arena does not overflow on its own any
+    more; RIG_NOMINAL_SCALE under-sizes them to exercise the defensive paths: the host destination retries internally, the
+    asynchronous device destination reports RIG_E_CAPACITY at rig_sync with a budget that stays halved, so that the retry of
+    the same scene succeeds (Renderer.render_to_device_checked, used by iter_png and the dataset driver)."""
+    import torch
+    from reasoning_image_generation_b200._abi import RIG_E_CAPACITY
+    els = [dict(kind='crescent', size=300, fill=True, stroke_width=3, center=(2, 2), angle=30, color=(9, 99, 199)),
+           dict(kind='heart', size=300, fill=True, stroke_width=3, center=(510, 509), angle=45, color=(9, 99, 199))]
+    sb = SceneBuilder(512, 512)
+    for _ in range(24):
+        sb.add_panel(els, False)
+    sc = sb.finish()
+    ref = ref_render.render_panel(512, 512, (255, 255, 255), els, False, 3, backend=ref_render.CBackend())
+    monkeypatch.setenv('RIG_NOMINAL_SCALE', '0.05')
+    small = Renderer(512, 512, device=0, max_panels=24, max_elements=48)     # arena = the 65 536-slot minimum
+    assert (small.render(sc, 'bgr') == ref[None]).all()                      # host destination: internal retry
+    small.close()
+    small = Renderer(512, 512, device=0, max_panels=24, max_elements=48)
+    dev = torch.zeros((24, 512, 512, 3), dtype=torch.uint8, device='cuda')
+    small.render_to_device(sc, dev.data_ptr(), 'bgr')
+    with pytest.raises(RigError) as ei:
+        small.sync()
+    assert ei.value.code == RIG_E_CAPACITY and small.stats()['overflow'] == 1
+    small.render_to_device_checked(sc, dev.data_ptr(), 'bgr')                # sticky budget: converges, then stays small
+    assert (dev.cpu().numpy() == ref[None]).all() and small.stats()['overflow'] == 0
+    small.render_to_device(sc, dev.data_ptr(), 'bgr')                        # a fresh upload of the same scene no longer overflows
+    small.sync()
+    assert (dev.cpu().numpy() == ref[None]).all()
+    small.close()
+
+
 @pytest.mark.parametrize('W,H', [(256, 192), (640, 361), (1024, 64)])
 def test_other_canvas_sizes(built, W, H):
     """Canvas sizes other than 512 x 512 (ragged last band, other band widths, fewer warps per CTA at W = 1024)."""
