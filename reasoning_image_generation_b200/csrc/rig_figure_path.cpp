@@ -1,533 +1,37 @@
-// rig_figure_path.cpp -- host half of the figure path: one draw_path argument list -> polygon edges in 24.8 fixed point.
+// rig_figure_path.cpp -- host instance of the figure path's geometry pipeline (rig_figure_geom.h): artists -> rasteriser layers.
 //
-// What matplotlib's Agg backend does between RendererAgg::draw_path and the cell rasteriser, restated as a push pipeline
-// (matplotlib and Agg are third-party dependencies of the reference that are absent from /root/reference; call sites:
-// multigraph_generation/generator.py:250-259):
-//
-//   PathFeed      trans *= scale(1, -1); trans *= translate(0, H); vertices through the affine; PathSnapper
-//   Flatten       agg::conv_curve (curve3_div / curve4_div, approximation_scale 1, angle_tolerance 0)
-//   StrokeGen     agg::conv_stroke: vertex_sequence de-duplication, vcgen_stroke contour order, math_stroke joins and caps
-//   ClipToCells   agg::rasterizer_sl_clip<ras_conv_dbl>::line_to and the auto-closing of rasterizer_scanline_aa; emits
-//                 the integer end points cells.line() would get (horizontal edges add nothing to any cell and are dropped)
-//
-// Everything is double precision with the host libm, compiled with -ffp-contract=off: the doubles are the ones the CPU
-// renderer computes, so the integer edges are the same, and the device only does integer work on them.
+// The pipeline itself (transform, PathSnapper, curve flattening, Agg's stroker, the rasteriser's clipper) lives in
+// rig_figure_geom.h and is shared with the device kernel k_figure_path; this file runs it on host threads with std::vector
+// storage and the host libm (compiled with -ffp-contract=off: the doubles are the ones the CPU renderer computes) and sorts
+// each layer's edges.  It is the definition the device pipeline is held to, the fallback for batches the device hands back
+// (see `Uncertain` in rig_figure_geom.h) and what rig_figure_debug_edges exposes to the tests.
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
 
+#include "rig_figure_geom.h"
 #include "rig_figure_host.h"
 
 namespace rig {
 namespace {
 
-constexpr double kPi = 3.14159265358979323846;
-constexpr double kVertexDistEps = 1e-14;
-constexpr double kIntersectionEps = 1.0e-30;
-constexpr double kCollinearityEps = 1e-30;
-constexpr int kCurveRecursionLimit = 32;
+using geom::SV;
 
-struct Pt {
-    double x, y;
+struct VecSeq {
+    std::vector<SV> &v;
+    int size() const { return (int)v.size(); }
+    SV &operator[](int i) { return v[(size_t)i]; }
+    SV &back() { return v.back(); }
+    void push_back(const SV &x) { v.push_back(x); }
+    void pop_back() { v.pop_back(); }
+    void clear() { v.clear(); }
 };
-inline double dist2(double ax, double ay, double bx, double by)
-{
-    const double dx = bx - ax, dy = by - ay;
-    return dx * dx + dy * dy;
-}
-
-// ---- last stage: clip in doubles, round to 24.8, collect edges ------------------------------------
-class ClipToCells {
-public:
-    ClipToCells(std::vector<FEdge> &edges, double x1, double y1, double x2, double y2)
-        : edges_(edges), cx1_(x1), cy1_(y1), cx2_(x2), cy2_(y2) {}
-    void move_to(double x, double y)
-    {
-        close();
-        sx_ = px_ = x;
-        sy_ = py_ = y;
-        pf_ = flags(x, y);
-        open_ = false;
-        pi_ok_ = false;
-    }
-    void line_to(double x2, double y2)
-    {
-        open_ = true;
-        const unsigned f2 = flags(x2, y2);
-        if ((pf_ | f2) == 0u) {                                  // both ends inside the box (nearly every segment): no clipping,
-            const int ix2 = iround(x2 * 256), iy2 = iround(y2 * 256);      // and the start was rounded as the previous end
-            const int ix1 = pi_ok_ ? ipx_ : iround(px_ * 256), iy1 = pi_ok_ ? ipy_ : iround(py_ * 256);
-            cells_line(ix1, iy1, ix2, iy2);
-            ipx_ = ix2; ipy_ = iy2; pi_ok_ = true;
-            px_ = x2; py_ = y2; pf_ = f2;
-            return;
-        }
-        pi_ok_ = false;
-        if ((pf_ & 10u) == (f2 & 10u) && (pf_ & 10u) != 0u) {   // both above or both below the box
-            px_ = x2; py_ = y2; pf_ = f2;
-            return;
-        }
-        const double x1 = px_, y1 = py_;
-        const unsigned f1 = pf_;
-        double y3, y4;
-        unsigned f3, f4;
-        switch (((f1 & 5u) << 1) | (f2 & 5u)) {
-        case 0: span(x1, y1, x2, y2, f1, f2); break;
-        case 1:
-            y3 = y1 + (cx2_ - x1) * (y2 - y1) / (x2 - x1); f3 = flags_y(y3);
-            span(x1, y1, cx2_, y3, f1, f3);
-            span(cx2_, y3, cx2_, y2, f3, f2);
-            break;
-        case 2:
-            y3 = y1 + (cx2_ - x1) * (y2 - y1) / (x2 - x1); f3 = flags_y(y3);
-            span(cx2_, y1, cx2_, y3, f1, f3);
-            span(cx2_, y3, x2, y2, f3, f2);
-            break;
-        case 3: span(cx2_, y1, cx2_, y2, f1, f2); break;
-        case 4:
-            y3 = y1 + (cx1_ - x1) * (y2 - y1) / (x2 - x1); f3 = flags_y(y3);
-            span(x1, y1, cx1_, y3, f1, f3);
-            span(cx1_, y3, cx1_, y2, f3, f2);
-            break;
-        case 6:
-            y3 = y1 + (cx2_ - x1) * (y2 - y1) / (x2 - x1);
-            y4 = y1 + (cx1_ - x1) * (y2 - y1) / (x2 - x1);
-            f3 = flags_y(y3); f4 = flags_y(y4);
-            span(cx2_, y1, cx2_, y3, f1, f3);
-            span(cx2_, y3, cx1_, y4, f3, f4);
-            span(cx1_, y4, cx1_, y2, f4, f2);
-            break;
-        case 8:
-            y3 = y1 + (cx1_ - x1) * (y2 - y1) / (x2 - x1); f3 = flags_y(y3);
-            span(cx1_, y1, cx1_, y3, f1, f3);
-            span(cx1_, y3, x2, y2, f3, f2);
-            break;
-        case 9:
-            y3 = y1 + (cx1_ - x1) * (y2 - y1) / (x2 - x1);
-            y4 = y1 + (cx2_ - x1) * (y2 - y1) / (x2 - x1);
-            f3 = flags_y(y3); f4 = flags_y(y4);
-            span(cx1_, y1, cx1_, y3, f1, f3);
-            span(cx1_, y3, cx2_, y4, f3, f4);
-            span(cx2_, y4, cx2_, y2, f4, f2);
-            break;
-        case 12: span(cx1_, y1, cx1_, y2, f1, f2); break;
-        default: break;
-        }
-        pf_ = f2; px_ = x2; py_ = y2;
-    }
-    void close()
-    {
-        if (open_) {
-            line_to(sx_, sy_);
-            open_ = false;
-        }
-    }
-
-private:
-    static int iround(double v) { return (int)((v < 0.0) ? v - 0.5 : v + 0.5); }
-    unsigned flags(double x, double y) const
-    {
-        return (unsigned)(x > cx2_) | ((unsigned)(y > cy2_) << 1) | ((unsigned)(x < cx1_) << 2) | ((unsigned)(y < cy1_) << 3);
-    }
-    unsigned flags_y(double y) const { return ((unsigned)(y > cy2_) << 1) | ((unsigned)(y < cy1_) << 3); }
-    void cells_line(int x1, int y1, int x2, int y2)
-    {
-        if (y1 == y2) return;                       // adds nothing to any cell
-        const long dx = (long)x2 - (long)x1, lim = 16384L << 8;
-        if (dx >= lim || dx <= -lim) {              // agg splits very long edges in the middle
-            const int mx = (int)(((long)x1 + x2) >> 1), my = (int)(((long)y1 + y2) >> 1);
-            cells_line(x1, y1, mx, my);
-            cells_line(mx, my, x2, y2);
-            return;
-        }
-        edges_.push_back(FEdge{x1, y1, x2, y2});
-    }
-    void span(double x1, double y1, double x2, double y2, unsigned f1, unsigned f2)
-    {
-        f1 &= 10u;
-        f2 &= 10u;
-        if ((f1 | f2) == 0u) {
-            cells_line(iround(x1 * 256), iround(y1 * 256), iround(x2 * 256), iround(y2 * 256));
-            return;
-        }
-        if (f1 == f2) return;
-        double tx1 = x1, ty1 = y1, tx2 = x2, ty2 = y2;
-        if (f1 & 8u) { tx1 = x1 + (cy1_ - y1) * (x2 - x1) / (y2 - y1); ty1 = cy1_; }
-        if (f1 & 2u) { tx1 = x1 + (cy2_ - y1) * (x2 - x1) / (y2 - y1); ty1 = cy2_; }
-        if (f2 & 8u) { tx2 = x1 + (cy1_ - y1) * (x2 - x1) / (y2 - y1); ty2 = cy1_; }
-        if (f2 & 2u) { tx2 = x1 + (cy2_ - y1) * (x2 - x1) / (y2 - y1); ty2 = cy2_; }
-        cells_line(iround(tx1 * 256), iround(ty1 * 256), iround(tx2 * 256), iround(ty2 * 256));
-    }
-    std::vector<FEdge> &edges_;
-    double cx1_, cy1_, cx2_, cy2_;
-    double px_ = 0, py_ = 0, sx_ = 0, sy_ = 0;
-    unsigned pf_ = 0;
-    int ipx_ = 0, ipy_ = 0;      // the previous point in 24.8 fixed point, valid if pi_ok_
-    bool pi_ok_ = false;
-    bool open_ = false;
+struct VecEdges {
+    std::vector<FEdge> &e;
+    void push(int x1, int y1, int x2, int y2) { e.push_back(FEdge{x1, y1, x2, y2}); }
 };
-
-// ---- stroker --------------------------------------------------------------------------------------
-struct SV {
-    double x, y, d;   // d: distance to the next vertex of the sequence
-    double nx, ny;    // half-width offset of the segment to the next vertex: w (y' - y) / d, w (x' - x) / d (set by finish())
-};
-class StrokeGen {
-public:
-    StrokeGen(std::vector<SV> &storage, double linewidth, int cap, int join, ClipToCells &sink) : sink_(sink), seq_(storage), cap_(cap), join_(join)
-    {
-        w_ = linewidth * 0.5;
-        if (w_ < 0) { wabs_ = -w_; wsign_ = -1; }
-        else { wabs_ = w_; wsign_ = 1; }
-        weps_ = w_ / 1024.0;
-        miter_limit_ = linewidth;     // _draw_path: stroke.miter_limit(points_to_pixels(gc.linewidth))
-    }
-    void begin(double x, double y)
-    {
-        seq_.clear();
-        push(x, y);
-    }
-    void add(double x, double y) { push(x, y); }
-    // finishes the sub-path: closed = it ended with CLOSEPOLY
-    void finish(bool closed)
-    {
-        settle(closed);
-        const int n = (int)seq_.size();
-        if (n < 3) closed = false;
-        if (n < 2 + (closed ? 1 : 0)) return;
-        // math_stroke::calc_join derives both segments' offsets at every join, and every segment is visited by four joins (two per
-        // side); they are computed once here.  On the way back the segments run the other way: IEEE subtraction, multiplication
-        // and division are odd functions, so the offsets there are these negated (0.0 - v, which keeps a zero positive as the
-        // direct evaluation does).
-        const int nseg = closed ? n : n - 1;
-        for (int i = 0; i < nseg; i++) {
-            SV &c = seq_[i];
-            const SV &q = seq_[i + 1 < n ? i + 1 : 0];
-            c.nx = w_ * (q.y - c.y) / c.d;
-            c.ny = w_ * (q.x - c.x) / c.d;
-        }
-        first_ = true;
-        if (closed) {
-            for (int i = 0; i < n; i++) {
-                const SV &p = seq_[i ? i - 1 : n - 1], &c = seq_[i], &q = seq_[i + 1 < n ? i + 1 : 0];
-                join(p, c, q, p.nx, p.ny, c.nx, c.ny, p.d, c.d);
-            }
-            sink_.close();
-            first_ = true;
-            for (int i = n - 1; i >= 0; i--) {
-                const SV &p = seq_[i ? i - 1 : n - 1], &c = seq_[i], &q = seq_[i + 1 < n ? i + 1 : 0];
-                join(q, c, p, 0.0 - c.nx, 0.0 - c.ny, 0.0 - p.nx, 0.0 - p.ny, c.d, p.d);
-            }
-            sink_.close();
-        } else {
-            cap(seq_[0], seq_[1], seq_[0].d);
-            for (int i = 1; i + 1 < n; i++) join(seq_[i - 1], seq_[i], seq_[i + 1], seq_[i - 1].nx, seq_[i - 1].ny, seq_[i].nx, seq_[i].ny, seq_[i - 1].d, seq_[i].d);
-            cap(seq_[n - 1], seq_[n - 2], seq_[n - 2].d);
-            for (int i = n - 2; i >= 1; i--)
-                join(seq_[i + 1], seq_[i], seq_[i - 1], 0.0 - seq_[i].nx, 0.0 - seq_[i].ny, 0.0 - seq_[i - 1].nx, 0.0 - seq_[i - 1].ny, seq_[i].d, seq_[i - 1].d);
-            sink_.close();
-        }
-    }
-
-private:
-    // agg::vertex_sequence<vertex_dist>: a vertex is dropped once its predecessor turns out to coincide with it
-    static bool measure(SV &a, const SV &b)
-    {
-        a.d = sqrt(dist2(a.x, a.y, b.x, b.y));
-        const bool apart = a.d > kVertexDistEps;
-        if (!apart) a.d = 1.0 / kVertexDistEps;
-        return apart;
-    }
-    void push(double x, double y)
-    {
-        const size_t n = seq_.size();
-        if (n > 1 && !measure(seq_[n - 2], seq_[n - 1])) seq_.pop_back();
-        seq_.push_back(SV{x, y, 0.0, 0.0, 0.0});
-    }
-    void settle(bool closed)
-    {
-        while (seq_.size() > 1) {
-            const size_t n = seq_.size();
-            if (measure(seq_[n - 2], seq_[n - 1])) break;
-            const SV t = seq_[n - 1];
-            seq_.pop_back();
-            seq_.pop_back();
-            push(t.x, t.y);
-        }
-        if (closed)
-            while (seq_.size() > 1) {
-                if (measure(seq_.back(), seq_[0])) break;
-                seq_.pop_back();
-            }
-    }
-    void out(double x, double y)
-    {
-        if (first_) sink_.move_to(x, y);
-        else sink_.line_to(x, y);
-        first_ = false;
-    }
-    static double cross(double x1, double y1, double x2, double y2, double x, double y) { return (x - x2) * (y2 - y1) - (y - y2) * (x2 - x1); }
-    static bool intersect(double ax, double ay, double bx, double by, double cx, double cy, double dx, double dy, double &x, double &y)
-    {
-        const double num = (ay - cy) * (dx - cx) - (ax - cx) * (dy - cy);
-        const double den = (bx - ax) * (dy - cy) - (by - ay) * (dx - cx);
-        if (fabs(den) < kIntersectionEps) return false;
-        const double r = num / den;
-        x = ax + r * (bx - ax);
-        y = ay + r * (by - ay);
-        return true;
-    }
-    void arc(double x, double y, double dx1, double dy1, double dx2, double dy2)
-    {
-        double a1 = atan2(dy1 * wsign_, dx1 * wsign_), a2 = atan2(dy2 * wsign_, dx2 * wsign_);
-        double da = acos(wabs_ / (wabs_ + 0.125 / 1.0)) * 2;
-        out(x + dx1, y + dy1);
-        if (wsign_ > 0) {
-            if (a1 > a2) a2 += 2 * kPi;
-            const int n = (int)((a2 - a1) / da);
-            da = (a2 - a1) / (n + 1);
-            a1 += da;
-            for (int i = 0; i < n; i++) {
-                out(x + cos(a1) * w_, y + sin(a1) * w_);
-                a1 += da;
-            }
-        } else {
-            if (a1 < a2) a2 -= 2 * kPi;
-            const int n = (int)((a1 - a2) / da);
-            da = (a1 - a2) / (n + 1);
-            a1 -= da;
-            for (int i = 0; i < n; i++) {
-                out(x + cos(a1) * w_, y + sin(a1) * w_);
-                a1 -= da;
-            }
-        }
-        out(x + dx2, y + dy2);
-    }
-    // revert = true: matplotlib's 'miter' (agg::miter_join_revert) and the inner miter
-    void miter(const SV &v0, const SV &v1, const SV &v2, double dx1, double dy1, double dx2, double dy2, double mlimit)
-    {
-        double xi = v1.x, yi = v1.y;
-        const double lim = wabs_ * mlimit;
-        bool exceeded = true;
-        if (intersect(v0.x + dx1, v0.y - dy1, v1.x + dx1, v1.y - dy1, v1.x + dx2, v1.y - dy2, v2.x + dx2, v2.y - dy2, xi, yi)) {
-            const double di = sqrt(dist2(v1.x, v1.y, xi, yi));
-            if (di <= lim) {
-                out(xi, yi);
-                exceeded = false;
-            }
-        } else {
-            const double x2 = v1.x + dx1, y2 = v1.y - dy1;
-            if ((cross(v0.x, v0.y, v1.x, v1.y, x2, y2) < 0.0) == (cross(v1.x, v1.y, v2.x, v2.y, x2, y2) < 0.0)) {
-                out(v1.x + dx1, v1.y - dy1);
-                exceeded = false;
-            }
-        }
-        if (exceeded) {
-            out(v1.x + dx1, v1.y - dy1);
-            out(v1.x + dx2, v1.y - dy2);
-        }
-    }
-    // (dx1, dy1), (dx2, dy2): w (v1.y - v0.y) / len1, w (v1.x - v0.x) / len1 and the same for v1 -> v2
-    void join(const SV &v0, const SV &v1, const SV &v2, double dx1, double dy1, double dx2, double dy2, double len1, double len2)
-    {
-        const double cp = cross(v0.x, v0.y, v1.x, v1.y, v2.x, v2.y);
-        if ((cp > kVertexDistEps && w_ > 0) || (cp < -kVertexDistEps && w_ < 0)) {
-            double limit = ((len1 < len2) ? len1 : len2) / wabs_;
-            if (limit < 1.01) limit = 1.01;            // inner_miter_limit
-            miter(v0, v1, v2, dx1, dy1, dx2, dy2, limit);
-            return;
-        }
-        double dx = (dx1 + dx2) / 2, dy = (dy1 + dy2) / 2;
-        const double dbevel = sqrt(dx * dx + dy * dy);
-        if (join_ == RIG_JOIN_ROUND || join_ == RIG_JOIN_BEVEL) {
-            if (1.0 * (wabs_ - dbevel) < weps_) {     // nearly collinear: one point
-                if (intersect(v0.x + dx1, v0.y - dy1, v1.x + dx1, v1.y - dy1, v1.x + dx2, v1.y - dy2, v2.x + dx2, v2.y - dy2, dx, dy))
-                    out(dx, dy);
-                else
-                    out(v1.x + dx1, v1.y - dy1);
-                return;
-            }
-        }
-        if (join_ == RIG_JOIN_MITER) miter(v0, v1, v2, dx1, dy1, dx2, dy2, miter_limit_);
-        else if (join_ == RIG_JOIN_ROUND) arc(v1.x, v1.y, dx1, -dy1, dx2, -dy2);
-        else {
-            out(v1.x + dx1, v1.y - dy1);
-            out(v1.x + dx2, v1.y - dy2);
-        }
-    }
-    void cap(const SV &v0, const SV &v1, double len)
-    {
-        double dx1 = (v1.y - v0.y) / len, dy1 = (v1.x - v0.x) / len, dx2 = 0, dy2 = 0;
-        dx1 *= w_;
-        dy1 *= w_;
-        if (cap_ != RIG_CAP_ROUND) {
-            if (cap_ == RIG_CAP_PROJECTING) {
-                dx2 = dy1 * wsign_;
-                dy2 = dx1 * wsign_;
-            }
-            out(v0.x - dx1 - dx2, v0.y + dy1 - dy2);
-            out(v0.x + dx1 - dx2, v0.y - dy1 - dy2);
-            return;
-        }
-        double da = acos(wabs_ / (wabs_ + 0.125 / 1.0)) * 2;
-        const int n = (int)(kPi / da);
-        da = kPi / (n + 1);
-        out(v0.x - dx1, v0.y + dy1);
-        if (wsign_ > 0) {
-            double a1 = atan2(dy1, -dx1);
-            a1 += da;
-            for (int i = 0; i < n; i++) {
-                out(v0.x + cos(a1) * w_, v0.y + sin(a1) * w_);
-                a1 += da;
-            }
-        } else {
-            double a1 = atan2(-dy1, dx1);
-            a1 -= da;
-            for (int i = 0; i < n; i++) {
-                out(v0.x + cos(a1) * w_, v0.y + sin(a1) * w_);
-                a1 -= da;
-            }
-        }
-        out(v0.x + dx1, v0.y - dy1);
-    }
-
-    ClipToCells &sink_;
-    std::vector<SV> &seq_;        // caller-owned, so that its capacity survives from artist to artist
-    double w_, wabs_, weps_, miter_limit_;
-    int wsign_, cap_, join_;
-    bool first_ = true;
-};
-
-// ---- curve flattening -------------------------------------------------------------------------------
-template <class Emit>
-void quad_split(Emit &emit, double x1, double y1, double x2, double y2, double x3, double y3, int level)
-{
-    if (level > kCurveRecursionLimit) return;
-    const double x12 = (x1 + x2) / 2, y12 = (y1 + y2) / 2, x23 = (x2 + x3) / 2, y23 = (y2 + y3) / 2;
-    const double x123 = (x12 + x23) / 2, y123 = (y12 + y23) / 2;
-    const double dx = x3 - x1, dy = y3 - y1;
-    double d = fabs(((x2 - x3) * dy - (y2 - y3) * dx));
-    if (d > kCollinearityEps) {
-        if (d * d <= 0.25 * (dx * dx + dy * dy)) { emit(x123, y123); return; }
-    } else {
-        const double da = dx * dx + dy * dy;
-        if (da == 0) d = dist2(x1, y1, x2, y2);
-        else {
-            d = ((x2 - x1) * dx + (y2 - y1) * dy) / da;
-            if (d > 0 && d < 1) return;
-            if (d <= 0) d = dist2(x2, y2, x1, y1);
-            else if (d >= 1) d = dist2(x2, y2, x3, y3);
-            else d = dist2(x2, y2, x1 + d * dx, y1 + d * dy);
-        }
-        if (d < 0.25) { emit(x2, y2); return; }
-    }
-    quad_split(emit, x1, y1, x12, y12, x123, y123, level + 1);
-    quad_split(emit, x123, y123, x23, y23, x3, y3, level + 1);
-}
-template <class Emit>
-void cubic_split(Emit &emit, double x1, double y1, double x2, double y2, double x3, double y3, double x4, double y4, int level)
-{
-    if (level > kCurveRecursionLimit) return;
-    const double x12 = (x1 + x2) / 2, y12 = (y1 + y2) / 2, x23 = (x2 + x3) / 2, y23 = (y2 + y3) / 2;
-    const double x34 = (x3 + x4) / 2, y34 = (y3 + y4) / 2;
-    const double x123 = (x12 + x23) / 2, y123 = (y12 + y23) / 2, x234 = (x23 + x34) / 2, y234 = (y23 + y34) / 2;
-    const double x1234 = (x123 + x234) / 2, y1234 = (y123 + y234) / 2;
-    const double dx = x4 - x1, dy = y4 - y1;
-    double d2 = fabs(((x2 - x4) * dy - (y2 - y4) * dx));
-    double d3 = fabs(((x3 - x4) * dy - (y3 - y4) * dx));
-    const int sel = ((d2 > kCollinearityEps) ? 2 : 0) + ((d3 > kCollinearityEps) ? 1 : 0);
-    if (sel == 0) {
-        double k = dx * dx + dy * dy;
-        if (k == 0) {
-            d2 = dist2(x1, y1, x2, y2);
-            d3 = dist2(x4, y4, x3, y3);
-        } else {
-            k = 1 / k;
-            double da1 = x2 - x1, da2 = y2 - y1;
-            d2 = k * (da1 * dx + da2 * dy);
-            da1 = x3 - x1; da2 = y3 - y1;
-            d3 = k * (da1 * dx + da2 * dy);
-            if (d2 > 0 && d2 < 1 && d3 > 0 && d3 < 1) return;
-            if (d2 <= 0) d2 = dist2(x2, y2, x1, y1);
-            else if (d2 >= 1) d2 = dist2(x2, y2, x4, y4);
-            else d2 = dist2(x2, y2, x1 + d2 * dx, y1 + d2 * dy);
-            if (d3 <= 0) d3 = dist2(x3, y3, x1, y1);
-            else if (d3 >= 1) d3 = dist2(x3, y3, x4, y4);
-            else d3 = dist2(x3, y3, x1 + d3 * dx, y1 + d3 * dy);
-        }
-        if (d2 > d3) {
-            if (d2 < 0.25) { emit(x2, y2); return; }
-        } else {
-            if (d3 < 0.25) { emit(x3, y3); return; }
-        }
-    } else {
-        const double dd = sel == 1 ? d3 : (sel == 2 ? d2 : d2 + d3);
-        if (dd * dd <= 0.25 * (dx * dx + dy * dy)) { emit(x23, y23); return; }
-    }
-    cubic_split(emit, x1, y1, x12, y12, x123, y123, x1234, y1234, level + 1);
-    cubic_split(emit, x1234, y1234, x234, y234, x34, y34, x4, y4, level + 1);
-}
-
-// ---- first stage: affine, snapping ------------------------------------------------------------------
-struct Affine {
-    double sx, shy, shx, sy, tx, ty;
-    void then(const Affine &m)   // agg::trans_affine::multiply
-    {
-        const double t0 = sx * m.sx + shy * m.shx, t2 = shx * m.sx + sy * m.shx, t4 = tx * m.sx + ty * m.shx + m.tx;
-        shy = sx * m.shy + shy * m.sy;
-        sy = shx * m.shy + sy * m.sy;
-        ty = tx * m.shy + ty * m.sy + m.ty;
-        sx = t0; shx = t2; tx = t4;
-    }
-    void apply(double &x, double &y) const
-    {
-        const double t = x;
-        x = t * sx + y * shx + tx;
-        y = t * shy + y * sy + ty;
-    }
-};
-inline bool is_vertex_code(int c) { return c >= RIG_PATH_MOVETO && c <= RIG_PATH_CURVE4; }
-
-struct Node {
-    double x, y;
-    int code;
-};
-
-// flattened sub-paths of one artist -> fill sink or stroker
-template <class OnMove, class OnLine, class OnClose>
-void walk_flat(const std::vector<Node> &path, OnMove on_move, OnLine on_line, OnClose on_close)
-{
-    double lx = 0, ly = 0;
-    const size_t n = path.size();
-    for (size_t i = 0; i < n; i++) {
-        const Node &v = path[i];
-        if (v.code == RIG_PATH_STOP) break;
-        if (v.code == RIG_PATH_CURVE3 && i + 1 < n) {
-            const Node &e = path[++i];
-            auto emit = [&](double x, double y) { on_line(x, y); };
-            quad_split(emit, lx, ly, v.x, v.y, e.x, e.y, 0);
-            on_line(e.x, e.y);
-            lx = e.x; ly = e.y;
-        } else if (v.code == RIG_PATH_CURVE4 && i + 2 < n) {
-            const Node &c2 = path[++i];
-            const Node &e = path[++i];
-            auto emit = [&](double x, double y) { on_line(x, y); };
-            cubic_split(emit, lx, ly, v.x, v.y, c2.x, c2.y, e.x, e.y, 0);
-            on_line(e.x, e.y);
-            lx = e.x; ly = e.y;
-        } else if (v.code == RIG_PATH_MOVETO) {
-            on_move(v.x, v.y);
-            lx = v.x; ly = v.y;
-        } else if (v.code == RIG_PATH_LINETO) {
-            on_line(v.x, v.y);
-            lx = v.x; ly = v.y;
-        } else if ((v.code & 0x0f) == 0x0f) {
-            on_close((v.code & 0x40) != 0);
-        }
-    }
-}
 
 void finish_layer(FigurePrepared &out, size_t e0, uint32_t rgba, int W, int H, std::vector<FEdge> &tmp, std::vector<uint32_t> &count)
 {
@@ -576,113 +80,34 @@ int figure_prepare(const rig_figure_scene &s, int W, int H, bool bgr, int i0, in
 {
     // scratch that keeps its capacity from call to call (a call covers a block of a few dozen images)
     struct Scratch {
-        std::vector<Node> path;
         std::vector<SV> stroke_storage;
         std::vector<FEdge> sort_tmp;
         std::vector<uint32_t> sort_count;
     };
     thread_local Scratch scratch;
-    std::vector<Node> &path = scratch.path;
-    std::vector<SV> &stroke_storage = scratch.stroke_storage;
-    std::vector<FEdge> &sort_tmp = scratch.sort_tmp;
-    std::vector<uint32_t> &sort_count = scratch.sort_count;
+    VecSeq seq{scratch.stroke_storage};
+    VecEdges edges{out.edges};
+    geom::Certain certain;
     for (int img = i0; img < i1; img++) {
         out.image_layer_begin.push_back((uint32_t)out.layers.size());
         for (uint32_t a = s.image_artist_begin[img]; a < s.image_artist_begin[img + 1]; a++) {
-            const uint32_t vb = s.artist_vertex_begin[a], ve = s.artist_vertex_begin[a + 1];
-            const double *af = s.affine + 6 * (size_t)a;
-            Affine tr{af[0], af[1], af[2], af[3], af[4], af[5]};
-            tr.then(Affine{1.0, 0.0, 0.0, -1.0, 0.0, 0.0});
-            tr.then(Affine{1.0, 0.0, 0.0, 1.0, 0.0, (double)H});
-            path.clear();
-            for (uint32_t i = vb; i < ve; i++) {
-                Node nd{s.vertices[2 * (size_t)i], s.vertices[2 * (size_t)i + 1], s.codes[i]};
-                if (is_vertex_code(nd.code)) tr.apply(nd.x, nd.y);
-                else if (nd.code != RIG_PATH_STOP && nd.code != RIG_PATH_CLOSEPOLY) {
-                    snprintf(err, errlen, "artist %u: unknown path code %d", a, nd.code);
-                    return RIG_E_INVALID;
-                }
-                if (!(isfinite(nd.x) && isfinite(nd.y))) {
-                    snprintf(err, errlen, "artist %u: non-finite vertex (matplotlib's PathNanRemover is not reproduced)", a);
-                    return RIG_E_UNSUPPORTED;
-                }
-                path.push_back(nd);
-            }
-            const double lw = s.linewidth[a];
-            if (!(lw >= 0.0) || !isfinite(lw)) {
+            geom::ArtistSetup art;
+            int what = 0;
+            if (geom::artist_setup(s, a, W, H, art, what)) {
+                if (what == 1) { snprintf(err, errlen, "artist %u: unknown path code", a); return RIG_E_INVALID; }
+                if (what == 2) { snprintf(err, errlen, "artist %u: non-finite vertex (matplotlib's PathNanRemover is not reproduced)", a); return RIG_E_UNSUPPORTED; }
                 snprintf(err, errlen, "artist %u: bad line width", a);
                 return RIG_E_INVALID;
             }
-            // PathSnapper
-            bool snap = s.snap[a] == RIG_SNAP_TRUE;
-            if (s.snap[a] == RIG_SNAP_AUTO && ve - vb <= 1024 && !path.empty()) {
-                snap = true;
-                double x0 = path[0].x, y0 = path[0].y;
-                for (size_t i = 1; i < path.size() && snap; i++) {
-                    const Node &v = path[i];
-                    if (v.code == RIG_PATH_CURVE3 || v.code == RIG_PATH_CURVE4) snap = false;
-                    else if (v.code == RIG_PATH_LINETO && !(fabs(x0 - v.x) < 1e-4 || fabs(y0 - v.y) < 1e-4)) snap = false;
-                    x0 = v.x; y0 = v.y;
-                }
-            }
-            if (snap) {
-                const double slw = s.edge_rgba[4 * (size_t)a + 3] == 0 ? 0.0 : lw;
-                const int r = (int)(slw + ((slw >= 0.0) ? 0.5 : -0.5));
-                const double sv = (r % 2) ? 0.5 : 0.0;
-                for (Node &v : path)
-                    if (is_vertex_code(v.code)) {
-                        v.x = floor(v.x + 0.5) + sv;
-                        v.y = floor(v.y + 0.5) + sv;
-                    }
-            }
-            // clip box of the rasteriser (RendererAgg::set_clipbox)
-            double bx1 = 0, by1 = 0, bx2 = W, by2 = H;
-            if (s.has_clip && s.has_clip[a] && s.clip) {
-                const double *c = s.clip + 4 * (size_t)a;
-                int x1 = std::max((int)floor(c[0] + 0.5), 0), y1 = std::max((int)floor((double)H - c[1] + 0.5), 0);
-                int x2 = std::min((int)floor(c[2] + 0.5), W), y2 = std::min((int)floor((double)H - c[3] + 0.5), H);
-                if (x1 > x2) std::swap(x1, x2);
-                if (y1 > y2) std::swap(y1, y2);
-                bx1 = x1; by1 = y1; bx2 = x2; by2 = y2;
-            }
-            auto pack = [&](const uint8_t *c) {
-                return bgr ? ((uint32_t)c[2] | ((uint32_t)c[1] << 8) | ((uint32_t)c[0] << 16) | ((uint32_t)c[3] << 24))
-                           : ((uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24));
-            };
-            if (s.has_face[a] && s.face_rgba[4 * (size_t)a + 3] != 0) {
+            if (art.face) {
                 const size_t e0 = out.edges.size();
-                ClipToCells sink(out.edges, bx1, by1, bx2, by2);
-                walk_flat(path, [&](double x, double y) { sink.move_to(x, y); }, [&](double x, double y) { sink.line_to(x, y); },
-                          [&](bool closed) { if (closed) sink.close(); });
-                sink.close();
-                finish_layer(out, e0, pack(s.face_rgba + 4 * (size_t)a), W, H, sort_tmp, sort_count);
+                geom::face_pass(art, edges);
+                finish_layer(out, e0, geom::pack_rgba(s.face_rgba + 4 * (size_t)a, bgr), W, H, scratch.sort_tmp, scratch.sort_count);
             }
-            if (lw != 0.0 && s.edge_rgba[4 * (size_t)a + 3] != 0) {
+            if (art.stroke) {
                 const size_t e0 = out.edges.size();
-                ClipToCells sink(out.edges, bx1, by1, bx2, by2);
-                StrokeGen gen(stroke_storage, lw, s.cap[a], s.join[a], sink);
-                // conv_adaptor_vcgen: every generator run starts from the last MOVETO seen
-                bool have = false;
-                double mx = 0, my = 0;
-                auto flush = [&](bool closed) {
-                    if (have) gen.finish(closed);
-                    gen.begin(mx, my);
-                    have = true;
-                };
-                walk_flat(path,
-                          [&](double x, double y) {
-                              if (have) gen.finish(false);
-                              mx = x; my = y;
-                              gen.begin(x, y);
-                              have = true;
-                          },
-                          [&](double x, double y) {
-                              if (!have) { mx = x; my = y; gen.begin(x, y); have = true; }
-                              else gen.add(x, y);
-                          },
-                          [&](bool closed) { flush(closed); });
-                if (have) gen.finish(false);
-                finish_layer(out, e0, pack(s.edge_rgba + 4 * (size_t)a), W, H, sort_tmp, sort_count);
+                geom::stroke_pass(art, s.cap[a], s.join[a], seq, edges, certain);
+                finish_layer(out, e0, geom::pack_rgba(s.edge_rgba + 4 * (size_t)a, bgr), W, H, scratch.sort_tmp, scratch.sort_count);
             }
         }
     }
