@@ -51,14 +51,18 @@ RIG_HD int iround(double v) { return (int)((v < 0.0) ? v - 0.5 : v + 0.5); }
 
 // Tracks values that came out of atan2 / acos / cos / sin.  The host instance is empty (the host IS the definition).
 // Error model: both libms are within 2 ulp on these calls; the angles are < 8 in magnitude and go through at most a few
-// dozen additions, the products with the half width (<= 2048 px) and the sums with a canvas coordinate keep the absolute error
-// below 1e-9 px by a wide margin.  A coordinate is later multiplied by 256 and rounded, or compared with a clip bound.
+// dozen additions, the products with the half width and the sums with a canvas coordinate (|v| <= 2048, ulp 4.5e-13) keep the
+// absolute error of a coordinate below 1e-11 px, i.e. 3e-9 after the multiplication by 256 that precedes the rounding.
+// A libm coordinate is either rounded directly (the segment lies inside the clip box) or feeds the clipper's intersection
+// formulas; the second case is not analysed: a pass that emitted a libm point AND clipped any segment is handed back.
 struct Uncertain {
     bool hit = false;
+    bool libm = false;
     RIG_HD void coordinate(double v, double c1, double c2)
     {
         const double s = v * 256.0, f = s - floor(s);
-        if (fabs(f - 0.5) < 1e-6 || fabs(v - c1) < 1e-8 || fabs(v - c2) < 1e-8) hit = true;
+        libm = true;
+        if (fabs(f - 0.5) < 1e-7 || fabs(v - c1) < 1e-8 || fabs(v - c2) < 1e-8) hit = true;
     }
     RIG_HD void quotient(double q)                 // truncated to an int
     {
@@ -69,12 +73,17 @@ struct Uncertain {
     {
         if (fabs(a - b) < 1e-12) hit = true;
     }
+    RIG_HD void pass_done(bool clipped)
+    {
+        if (libm && clipped) hit = true;
+    }
 };
 struct Certain {
     static constexpr bool hit = false;
     RIG_HD void coordinate(double, double, double) {}
     RIG_HD void quotient(double) {}
     RIG_HD void ordering(double, double) {}
+    RIG_HD void pass_done(bool) {}
 };
 
 // ---- last stage: clip in doubles, round to 24.8, collect edges ------------------------------------
@@ -105,6 +114,7 @@ public:
             return;
         }
         pi_ok_ = false;
+        clipped_ = true;
         if ((pf_ & 10u) == (f2 & 10u) && (pf_ & 10u) != 0u) {   // both above or both below the box
             px_ = x2; py_ = y2; pf_ = f2;
             return;
@@ -168,6 +178,7 @@ public:
     RIG_HD double cy1() const { return cy1_; }
     RIG_HD double cx2() const { return cx2_; }
     RIG_HD double cy2() const { return cy2_; }
+    RIG_HD bool clipped() const { return clipped_; }      // some segment had an end outside the box
 
 private:
     RIG_HD unsigned flags(double x, double y) const
@@ -212,6 +223,7 @@ private:
     int ipx_ = 0, ipy_ = 0;      // the previous point in 24.8 fixed point, valid if pi_ok_
     bool pi_ok_ = false;
     bool open_ = false;
+    bool clipped_ = false;
 };
 
 // ---- stroker --------------------------------------------------------------------------------------
@@ -774,6 +786,7 @@ RIG_HD void stroke_pass(const ArtistSetup &a, int cap, int join, Seq &seq, EdgeS
     } cl{st};
     walk_flat(a.path, mv, ln, cl);
     if (st.have) gen.finish(false);
+    unc.pass_done(sink.clipped());
 }
 
 RIG_HD uint32_t pack_rgba(const uint8_t *c, bool bgr)
