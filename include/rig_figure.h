@@ -10,10 +10,13 @@
  * points take instead (see INTEGRATION.md for the matplotlib-side walker).  Plain C types only; every function returns 0
  * or a negative RIG_E_* code (include/rig.h); no exception, abort or CPU rendering fallback exists behind this boundary.
  *
- * Pipeline: the library runs matplotlib's path converters and Agg's stroker on host threads (double precision, the same
- * libm the CPU renderer uses), uploads the resulting polygon edges (24.8 fixed point), and the CUDA kernel k_figure
- * accumulates Agg's coverage cells per band of rows in shared memory, blends with matplotlib's non-premultiplied blender
- * and writes each band with one TMA bulk store.
+ * Pipeline: the artist arrays are copied to HBM as they are; k_figure_path runs matplotlib's path converters, Agg's stroker and
+ * the rasteriser's clipper on the device (double precision; one thread per artist) and leaves polygon edges in 24.8 fixed
+ * point; k_figure accumulates Agg's coverage cells per band of rows in shared memory, blends with matplotlib's
+ * non-premultiplied blender and writes each band with one TMA bulk store.  The same geometry code also exists as a host
+ * pipeline (host threads, the libm the CPU renderer uses): it is the definition the device is held to, and the library runs it
+ * instead whenever the device cannot vouch for bit-identical integers (a cos / sin / atan2 value of a round join or cap
+ * that lands within the two libms' error of a rounding boundary) or a path exceeds the device's fixed scratch.
  */
 #ifndef RIG_FIGURE_H
 #define RIG_FIGURE_H
@@ -84,10 +87,20 @@ const char *rig_figure_last_error(const rig_figure_ctx *ctx);
 int rig_figure_render_batch(rig_figure_ctx *ctx, const rig_figure_scene *scene, uint8_t *out, int out_is_device, int out_layout,
                             void *stream);
 
-/* Two-step form for scenes that stay resident in HBM (bench.py `value`): upload runs the host path pipeline and copies
- * the edges to the device once; render_resident rasterises them into device memory.                                   */
+/* Where the geometry half of draw_path (transform, snap, curve flattening, stroking, clipping) runs.  RIG_GEOM_DEVICE is the
+ * default (environment RIG_FIG_GEOM=host overrides it at context creation); the results are identical.                 */
+#define RIG_GEOM_HOST 0
+#define RIG_GEOM_DEVICE 1
+int rig_figure_set_geometry(rig_figure_ctx *ctx, int mode);
+
+/* Two-step form for scenes that stay resident in HBM (bench.py `value`): upload copies the artist arrays to the device and
+ * runs the geometry once (polygon edges resident).  render_resident rasterises those edges into device memory (k_figure
+ * only); draw_resident is the whole draw_path for every artist of the resident scene -- k_figure_path from the artist arrays,
+ * then k_figure -- and needs a scene the device geometry accepted (RIG_E_UNSUPPORTED otherwise).  Both are asynchronous;
+ * rig_figure_sync waits and reports a draw_resident whose geometry kernel raised a status.                               */
 int rig_figure_upload(rig_figure_ctx *ctx, const rig_figure_scene *scene, int out_layout, void *stream);
 int rig_figure_render_resident(rig_figure_ctx *ctx, uint8_t *out_device, void *stream);
+int rig_figure_draw_resident(rig_figure_ctx *ctx, uint8_t *out_device, void *stream);
 int rig_figure_sync(rig_figure_ctx *ctx);
 /* The context's own stream (a cudaStream_t): what asynchronous calls run on when `stream` is NULL.  Hand it to a consumer of the
  * rendered images (e.g. rig_png_encode) to order it after the render without a host synchronisation.                     */
@@ -114,7 +127,12 @@ typedef struct rig_figure_stats {
     uint32_t reserved;
     double cover_ms;            /* summed CUDA-event time of k_figure since rig_figure_set_profiling(ctx, 1) */
     uint64_t timed_images;
-    double prepare_ms;          /* host time of the last upload's path pipeline */
+    double prepare_ms;          /* host time of the last upload: packing the artist arrays, or the host path pipeline */
+    double geom_ms;             /* summed CUDA-event time of k_figure_path since rig_figure_set_profiling(ctx, 1) */
+    uint32_t geom_launches;     /* k_figure_path launches covered by geom_ms */
+    uint32_t geom_fallbacks;    /* uploads the device geometry handed back to the host pipeline since creation */
+    uint32_t geom_status;       /* status word of the last device geometry run (0: accepted; bits: rig_figure_geom.h GEOM_*) */
+    uint32_t geom_resident;     /* 1: the resident scene came from the device geometry */
 } rig_figure_stats;
 int rig_figure_get_stats(rig_figure_ctx *ctx, rig_figure_stats *out);
 int rig_figure_set_profiling(rig_figure_ctx *ctx, int on);
@@ -124,6 +142,11 @@ int rig_figure_set_profiling(rig_figure_ctx *ctx, int on);
  * point, y down).  Returns the number of edges, or a negative RIG_E_* code (RIG_E_CAPACITY: more than edge_cap edges).  */
 int64_t rig_figure_debug_edges(const rig_figure_scene *scene, int W, int H, uint32_t *layers_out, int32_t *edges_out,
                                int64_t edge_cap, int64_t *n_layers_out);
+
+/* Debug/test hook: the layers and edges of the RESIDENT scene (whichever geometry produced them), copied back from the device
+ * in the format of rig_figure_debug_edges (empty passes dropped, edges re-packed in layer order).                        */
+int64_t rig_figure_debug_resident(rig_figure_ctx *ctx, uint32_t *layers_out, int32_t *edges_out, int64_t edge_cap,
+                                  int64_t *n_layers_out);
 
 #ifdef __cplusplus
 }

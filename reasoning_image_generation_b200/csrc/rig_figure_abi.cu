@@ -1,8 +1,12 @@
 // rig_figure_abi.cu -- the extern "C" boundary declared in include/rig_figure.h.
 //
-// Host flow of one render: run the path pipeline (rig_figure_path.cpp) over the borrowed artist arrays on a few host
-// threads, copy layers / edges / slab directories to HBM, launch k_figure (persistent, one CTA per SM).  With a host
-// destination the images go through two device staging buffers so the D2H copy of one chunk overlaps the next chunk.
+// Host flow of one render (device geometry, the default): pack the borrowed artist arrays into one page-locked blob, one H2D
+// copy, k_figure_path (transform, snap, curve flattening, stroking, clipping -> layers / edges / slab directories in HBM),
+// read back its status word and the per-image weights, launch k_figure (persistent, one CTA per SM).  If the status says the
+// device could not vouch for bit-exactness (see geom::Uncertain) or ran out of a fixed capacity, or with
+// rig_figure_set_geometry(ctx, RIG_GEOM_HOST), the host path pipeline (rig_figure_path.cpp) runs on a few host threads instead
+// and its layers / edges are copied to HBM.  With a host destination the images go through two device staging buffers so the
+// D2H copy of one chunk overlaps the next chunk.
 #include <cuda_runtime.h>
 #include <sched.h>
 #include <stdarg.h>
@@ -21,6 +25,7 @@
 
 #include "rig_figure.cuh"
 #include "rig_figure_host.h"
+#include "rig_figure_path.cuh"
 
 using namespace rig;
 
@@ -196,7 +201,23 @@ struct rig_figure_ctx {
     rig_figure_stats stats = {};
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool, ev_used;
-    std::vector<uint32_t> ev_images;
+    std::vector<uint32_t> ev_images;      // per event pair: images covered; bit 31 set: the pair brackets k_figure_path
+    // ---- device geometry (k_figure_path)
+    int geom_mode = RIG_GEOM_DEVICE;
+    bool resident_device_geom = false;    // the resident scene's artist arrays are in HBM (rig_figure_draw_resident can run)
+    bool draw_pending = false;            // a rig_figure_draw_resident whose status word has not been checked yet
+    HostBuf<uint8_t> blob_host[2];        // packed artist arrays (page-locked)
+    uint8_t *d_blob = nullptr;
+    size_t cap_blob = 0;
+    GeomParams gp = {};                   // device pointers of the resident scene
+    uint32_t total_slots = 0;
+    uint32_t *d_counters = nullptr, *h_counters = nullptr;
+    float *d_cost = nullptr, *h_cost = nullptr;
+    geom::SV *d_seq = nullptr;
+    FEdge *d_estage = nullptr;
+    uint32_t geom_threads = 0, seq_cap = 0, stage_cap = 0;
+    int geom_ctas_per_sm = 0;
+    std::vector<uint32_t> artist_order, artist_layer, image_layer_begin, bucket;
     char err[512] = "";
 };
 
@@ -347,7 +368,8 @@ void order_range(rig_figure_ctx *c, uint32_t i0, uint32_t i1)
     for (uint32_t i = i0; i < i1; i++) c->order[i0 + count[cls(i)]++] = i;
 }
 
-int upload(rig_figure_ctx *c, const rig_figure_scene *s, int layout, cudaStream_t st)
+// host geometry: the path pipeline on host threads, layers / edges / directories copied to HBM
+int upload_host_geometry(rig_figure_ctx *c, const rig_figure_scene *s, int layout, cudaStream_t st)
 {
     char msg[256] = "";
     static const bool trace = getenv("RIG_PREP_TRACE") != nullptr;
@@ -368,6 +390,7 @@ int upload(rig_figure_ctx *c, const rig_figure_scene *s, int layout, cudaStream_
     const auto tv2 = now();
     c->n_images = s->n_images;
     c->layout = layout;
+    c->resident_device_geom = false;
     c->order.resize(c->n_images);
     order_range(c, 0, (uint32_t)c->n_images);
     c->stats.edges = p.edges.size();
@@ -401,14 +424,205 @@ void fresolve_profiling(rig_figure_ctx *c)
     for (size_t i = 0; i + 1 < c->ev_used.size() && i / 2 < c->ev_images.size(); i += 2) {
         float a = 0;
         if (cudaEventElapsedTime(&a, c->ev_used[i], c->ev_used[i + 1]) == cudaSuccess) {
-            c->stats.cover_ms += a;
-            c->stats.timed_launches++;
-            c->stats.timed_images += c->ev_images[i / 2];
+            if (c->ev_images[i / 2] & 0x80000000u) {
+                c->stats.geom_ms += a;
+                c->stats.geom_launches++;
+            } else {
+                c->stats.cover_ms += a;
+                c->stats.timed_launches++;
+                c->stats.timed_images += c->ev_images[i / 2];
+            }
         }
     }
     for (cudaEvent_t e : c->ev_used) c->ev_pool.push_back(e);
     c->ev_used.clear();
     c->ev_images.clear();
+}
+
+// ---- device geometry ------------------------------------------------------------------------------------------------
+size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// sections of the packed scene blob (byte offsets, 16-byte aligned)
+struct BlobLayout {
+    size_t iab, avb, vertices, codes, affine, linewidth, cap, join, snap, edge_rgba, face_rgba, has_face, clip, has_clip, order, alayer, ilb, total;
+};
+BlobLayout blob_layout(const rig_figure_scene *s)
+{
+    const size_t ni = (size_t)s->n_images, na = (size_t)s->n_artists, nv = (size_t)s->n_vertices;
+    BlobLayout L;
+    size_t o = 0;
+    auto sec = [&](size_t bytes) { const size_t at = o; o = al16(o + bytes); return at; };
+    L.iab = sec(4 * (ni + 1)); L.avb = sec(4 * (na + 1)); L.vertices = sec(16 * nv); L.codes = sec(nv);
+    L.affine = sec(48 * na); L.linewidth = sec(8 * na); L.cap = sec(na); L.join = sec(na); L.snap = sec(na);
+    L.edge_rgba = sec(4 * na); L.face_rgba = sec(4 * na); L.has_face = sec(na);
+    L.clip = sec((s->clip && s->has_clip) ? 32 * na : 0); L.has_clip = sec((s->clip && s->has_clip) ? na : 0);
+    L.order = sec(4 * na); L.alayer = sec(4 * na); L.ilb = sec(4 * (ni + 1));
+    L.total = o;
+    return L;
+}
+
+int ensure_geom_scratch(rig_figure_ctx *c)
+{
+    if (c->d_seq) return RIG_OK;
+    int per_sm = 0;
+    FCK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_figure_path, GEOM_THREADS, sizeof(uint32_t) * GEOM_WARPS * (size_t)(c->H + 34)));
+    if (per_sm < 1) return ffail(c, RIG_E_CUDA, "k_figure_path cannot be resident");
+    // Thread-private scratch: the stroker's vertex sequence (40 B per flattened vertex) and the pass's unsorted edges.  Sized for
+    // outlines a few times the canvas diagonal; longer ones set GEOM_SEQ_OVERFLOW / GEOM_EDGE_OVERFLOW and the batch goes to the host.
+    const int dim = std::max(c->W, c->H);
+    c->seq_cap = dim <= 1024 ? 512u : 2048u;
+    c->stage_cap = dim <= 1024 ? 1024u : 4096u;
+    if (const char *e = getenv("RIG_GEOM_SEQ_CAP")) c->seq_cap = (uint32_t)std::max(8, atoi(e));
+    if (const char *e = getenv("RIG_GEOM_STAGE_CAP")) c->stage_cap = (uint32_t)std::max(8, atoi(e));
+    const size_t per_thread = sizeof(geom::SV) * c->seq_cap + sizeof(FEdge) * c->stage_cap;
+    const size_t budget = (size_t)3 << 30;
+    int ctas = per_sm * c->sm_count;
+    while (ctas > c->sm_count && (size_t)ctas * GEOM_THREADS * per_thread > budget) ctas -= c->sm_count;
+    c->geom_ctas_per_sm = ctas / c->sm_count;
+    c->geom_threads = (uint32_t)ctas * GEOM_THREADS;
+    FCK(c, cudaMalloc(&c->d_seq, sizeof(geom::SV) * c->seq_cap * (size_t)c->geom_threads));
+    FCK(c, cudaMalloc(&c->d_estage, sizeof(FEdge) * c->stage_cap * (size_t)c->geom_threads));
+    return RIG_OK;
+}
+
+// k_figure_path over the resident artist arrays (counters reset first); asynchronous
+int run_geometry(rig_figure_ctx *c, cudaStream_t st)
+{
+    static const uint32_t init[GC_WORDS] = {0u, 0u, 0u, 0u, 0xffffffffu, 0u, 0u, 0u};
+    FCK(c, cudaMemcpyAsync(c->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
+    const uint32_t na = (uint32_t)c->gp.s.n_artists;
+    if (na == 0) return RIG_OK;
+    const uint32_t want = (na + GEOM_THREADS - 1) / GEOM_THREADS;
+    const uint32_t grid = std::max(1u, std::min(want, c->geom_threads / GEOM_THREADS));
+    if (c->profiling) fprof_event(c, st);
+    k_figure_path<<<grid, GEOM_THREADS, sizeof(uint32_t) * GEOM_WARPS * (size_t)(c->H + 34), st>>>(c->gp);
+    c->stats.kernel_launches++;
+    if (c->profiling) { fprof_event(c, st); c->ev_images.push_back(0x80000000u | (uint32_t)c->n_images); }
+    FCK(c, cudaGetLastError());
+    return RIG_OK;
+}
+
+// Device geometry.  Returns RIG_OK, a negative code, or +1: the device declined (status word in stats.geom_status), run the host pipeline.
+int upload_device_geometry(rig_figure_ctx *c, const rig_figure_scene *s, int layout, cudaStream_t st)
+{
+    const size_t ni = (size_t)s->n_images, na = (size_t)s->n_artists, nv = (size_t)s->n_vertices;
+    if (nv > ((size_t)1 << 27)) return 1;
+    int rc = ensure_geom_scratch(c);
+    if (rc) return rc;
+    const auto t0 = std::chrono::steady_clock::now();
+    // ---- layer slots (one per face / stroke the artist asks for), the images' first slots, the work order
+    c->artist_layer.resize(na);
+    c->image_layer_begin.resize(ni + 1);
+    c->artist_order.resize(na);
+    {
+        uint32_t slots = 0;
+        size_t a = 0;
+        for (size_t i = 0; i < ni; i++) {
+            c->image_layer_begin[i] = slots;
+            for (const size_t a1 = s->image_artist_begin[i + 1]; a < a1; a++) {
+                c->artist_layer[a] = slots;
+                slots += (s->has_face[a] && s->face_rgba[4 * a + 3] != 0) ? 1u : 0u;
+                slots += (s->edge_rgba[4 * a + 3] != 0 && s->linewidth[a] != 0.0) ? 1u : 0u;
+            }
+        }
+        c->image_layer_begin[ni] = slots;
+        c->total_slots = slots;
+        // longest paths first, equal lengths together (the lanes of a warp then run the same patch type)
+        constexpr uint32_t kB = 1024;
+        c->bucket.assign(kB + 1, 0u);
+        auto key = [&](size_t k) { return kB - 1u - std::min<uint32_t>(s->artist_vertex_begin[k + 1] - s->artist_vertex_begin[k], kB - 1u); };
+        for (size_t k = 0; k < na; k++) c->bucket[key(k) + 1]++;
+        for (uint32_t b = 0; b < kB; b++) c->bucket[b + 1] += c->bucket[b];
+        for (size_t k = 0; k < na; k++) c->artist_order[c->bucket[key(k)]++] = (uint32_t)k;
+    }
+    // ---- pack everything into one page-locked blob (workers copy 1 MB pieces), one DMA
+    const BlobLayout L = blob_layout(s);
+    const unsigned slot = c->prep_next++ & 1u;
+    FCK(c, cudaEventSynchronize(c->ev_h2d[slot]));
+    HostBuf<uint8_t> &hb = c->blob_host[slot];
+    if (!hb.resize_discard(L.total)) return ffail(c, RIG_E_CUDA, "out of page-locked host memory for %zu bytes of artist arrays", L.total);
+    struct Seg { size_t at; const void *src; size_t bytes; };
+    const Seg segs[] = {
+        {L.iab, s->image_artist_begin, 4 * (ni + 1)}, {L.avb, s->artist_vertex_begin, 4 * (na + 1)}, {L.vertices, s->vertices, 16 * nv},
+        {L.codes, s->codes, nv}, {L.affine, s->affine, 48 * na}, {L.linewidth, s->linewidth, 8 * na}, {L.cap, s->cap, na}, {L.join, s->join, na},
+        {L.snap, s->snap, na}, {L.edge_rgba, s->edge_rgba, 4 * na}, {L.face_rgba, s->face_rgba, 4 * na}, {L.has_face, s->has_face, na},
+        {L.clip, s->clip, (s->clip && s->has_clip) ? 32 * na : 0}, {L.has_clip, s->has_clip, (s->clip && s->has_clip) ? na : 0},
+        {L.order, c->artist_order.data(), 4 * na}, {L.alayer, c->artist_layer.data(), 4 * na}, {L.ilb, c->image_layer_begin.data(), 4 * (ni + 1)}};
+    constexpr size_t kPiece = (size_t)1 << 20;
+    std::vector<Seg> pieces;
+    for (const Seg &g : segs)
+        for (size_t o = 0; o < g.bytes; o += kPiece) pieces.push_back(Seg{g.at + o, (const uint8_t *)g.src + o, std::min(kPiece, g.bytes - o)});
+    const std::function<void(int)> copy_piece = [&](int k) { memcpy(hb.data() + pieces[k].at, pieces[k].src, pieces[k].bytes); };
+    if (pieces.size() < 4 || c->host->pool.size() == 1) { for (size_t k = 0; k < pieces.size(); k++) copy_piece((int)k); }
+    else c->host->pool.run((int)pieces.size(), copy_piece);
+    c->stats.prepare_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if ((rc = ensure(c, c->d_blob, c->cap_blob, L.total))) return rc;
+    FCK(c, cudaMemcpyAsync(c->d_blob, hb.data(), L.total, cudaMemcpyHostToDevice, st));
+    FCK(c, cudaMemcpyAsync(c->d_begin, hb.data() + L.ilb, 4 * (ni + 1), cudaMemcpyHostToDevice, st));
+    FCK(c, cudaEventRecord(c->ev_h2d[slot], st));
+    // ---- output arenas: directory entries have an exact bound, edges start from an estimate and grow on demand
+    const size_t dir_bound = (size_t)c->total_slots * (size_t)(c->H / FIG_SLAB_ROWS + 3);
+    if ((rc = ensure(c, c->d_layers, c->cap_layers, c->total_slots))) return rc;
+    if ((rc = ensure(c, c->d_dir, c->cap_dir, dir_bound))) return rc;
+    if ((rc = ensure(c, c->d_edges, c->cap_edges, 12 * nv + 16 * na))) return rc;
+    GeomParams &P = c->gp;
+    rig_figure_scene &d = P.s;
+    d = *s;
+    const uint8_t *B = c->d_blob;
+    d.image_artist_begin = (const uint32_t *)(B + L.iab); d.artist_vertex_begin = (const uint32_t *)(B + L.avb);
+    d.vertices = (const double *)(B + L.vertices); d.codes = B + L.codes; d.affine = (const double *)(B + L.affine);
+    d.linewidth = (const double *)(B + L.linewidth); d.cap = B + L.cap; d.join = B + L.join; d.snap = B + L.snap;
+    d.edge_rgba = B + L.edge_rgba; d.face_rgba = B + L.face_rgba; d.has_face = B + L.has_face;
+    d.clip = (s->clip && s->has_clip) ? (const double *)(B + L.clip) : nullptr;
+    d.has_clip = (s->clip && s->has_clip) ? B + L.has_clip : nullptr;
+    P.artist_order = (const uint32_t *)(B + L.order); P.artist_layer = (const uint32_t *)(B + L.alayer);
+    P.W = c->W; P.H = c->H; P.bgr = layout == RIG_LAYOUT_BGR;
+    P.counters = c->d_counters; P.seq = c->d_seq; P.stage = c->d_estage; P.seq_cap = c->seq_cap; P.stage_cap = c->stage_cap;
+    c->n_images = s->n_images;
+    c->layout = layout;
+    uint32_t status = 0;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        P.layers = c->d_layers; P.edges = c->d_edges; P.dir = c->d_dir;
+        P.edge_cap = (uint32_t)std::min<size_t>(c->cap_edges, 0xfffffff0u); P.dir_cap = (uint32_t)std::min<size_t>(c->cap_dir, 0xfffffff0u);
+        if ((rc = run_geometry(c, st))) return rc;
+        if (ni) k_figure_cost<<<(unsigned)((ni + 255) / 256), 256, 0, st>>>(c->d_begin, c->d_layers, (uint32_t)ni, c->d_cost);
+        c->stats.kernel_launches++;
+        FCK(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(uint32_t) * GC_WORDS, cudaMemcpyDeviceToHost, st));
+        if (ni) FCK(c, cudaMemcpyAsync(c->h_cost, c->d_cost, sizeof(float) * ni, cudaMemcpyDeviceToHost, st));
+        FCK(c, cudaStreamSynchronize(st));
+        status = c->h_counters[GC_STATUS];
+        if (!(status & geom::GEOM_ARENA_OVERFLOW)) break;
+        const size_t need = (size_t)c->h_counters[GC_EDGES] + 64;
+        if (need <= c->cap_edges) break;                  // (cannot happen: the directory bound is exact)
+        if ((rc = ensure(c, c->d_edges, c->cap_edges, need))) return rc;
+    }
+    c->stats.geom_status = status;
+    if (status) {
+        c->stats.geom_fallbacks++;
+        return 1;
+    }
+    c->stats.edges = c->h_counters[GC_EDGES];
+    c->stats.layers = c->total_slots;
+    c->cost.resize(ni);
+    for (size_t i = 0; i < ni; i++) c->cost[i] = c->h_cost[i];
+    c->order.resize(ni);
+    order_range(c, 0, (uint32_t)ni);
+    if (ni) FCK(c, cudaMemcpyAsync(c->d_order, c->order.data(), sizeof(uint32_t) * ni, cudaMemcpyHostToDevice, st));
+    c->resident_device_geom = true;
+    return RIG_OK;
+}
+
+int upload(rig_figure_ctx *c, const rig_figure_scene *s, int layout, cudaStream_t st)
+{
+    if (c->geom_mode == RIG_GEOM_DEVICE) {
+        char msg[256] = "";
+        int rc = validate(c, s, msg, sizeof msg);
+        if (rc) return ffail(c, rc, "%s", msg);
+        if (layout != RIG_LAYOUT_RGB && layout != RIG_LAYOUT_BGR) return ffail(c, RIG_E_INVALID, "bad out_layout %d", layout);
+        rc = upload_device_geometry(c, s, layout, st);
+        if (rc <= 0) return rc;
+    }
+    return upload_host_geometry(c, s, layout, st);
 }
 
 // images order[i0 .. i1) of the resident scene; image id k is written at out_dev + (k - img_base) * H * W * 3
@@ -505,8 +719,14 @@ int rig_figure_create(int device, int W, int H, int max_images, int max_artists,
         FCKC(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
         FCKC(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
         c->prep[i].set_pinned(true);
+        c->blob_host[i].pinned = true;
     }
     c->host = new HostPrep();
+    if (const char *ev = getenv("RIG_FIG_GEOM")) c->geom_mode = (ev[0] == 'h' || ev[0] == '0') ? RIG_GEOM_HOST : RIG_GEOM_DEVICE;
+    FCKC(cudaMalloc(&c->d_counters, sizeof(uint32_t) * GC_WORDS));
+    FCKC(cudaMallocHost((void **)&c->h_counters, sizeof(uint32_t) * GC_WORDS));
+    FCKC(cudaMalloc(&c->d_cost, sizeof(float) * (size_t)max_images));
+    FCKC(cudaMallocHost((void **)&c->h_cost, sizeof(float) * (size_t)max_images));
     FCKC(cudaMalloc(&c->d_begin, sizeof(uint32_t) * ((size_t)max_images + 1)));
     FCKC(cudaMalloc(&c->d_order, sizeof(uint32_t) * (size_t)max_images));
     FCKC(cudaMalloc(&c->d_work, sizeof(uint32_t) * 4));
@@ -525,6 +745,9 @@ void rig_figure_destroy(rig_figure_ctx *c)
     cudaFree(c->d_layers); cudaFree(c->d_edges); cudaFree(c->d_dir); cudaFree(c->d_begin); cudaFree(c->d_order); cudaFree(c->d_work);
     cudaFree(c->d_stage[0]); cudaFree(c->d_stage[1]);
     cudaFree(c->d_blank[0]); cudaFree(c->d_blank[1]);
+    cudaFree(c->d_blob); cudaFree(c->d_counters); cudaFree(c->d_cost); cudaFree(c->d_seq); cudaFree(c->d_estage);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_cost) cudaFreeHost(c->h_cost);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_used) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
@@ -593,7 +816,64 @@ int rig_figure_sync(rig_figure_ctx *c)
         FCK(c, cudaDeviceSynchronize());
         fresolve_profiling(c);
     }
+    if (c->draw_pending) {
+        // the status word of the last rig_figure_draw_resident (the same artists as at upload, so it cannot differ from then)
+        c->draw_pending = false;
+        FCK(c, cudaDeviceSynchronize());
+        FCK(c, cudaMemcpy(c->h_counters, c->d_counters, sizeof(uint32_t) * GC_WORDS, cudaMemcpyDeviceToHost));
+        if (c->h_counters[GC_STATUS]) return ffail(c, RIG_E_CUDA, "k_figure_path status 0x%x on the resident scene", c->h_counters[GC_STATUS]);
+    }
     return RIG_OK;
+}
+
+int rig_figure_set_geometry(rig_figure_ctx *c, int mode)
+{
+    if (!c) return RIG_E_INVALID;
+    if (mode != RIG_GEOM_HOST && mode != RIG_GEOM_DEVICE) return ffail(c, RIG_E_INVALID, "bad geometry mode %d", mode);
+    c->geom_mode = mode;
+    return RIG_OK;
+}
+
+int rig_figure_draw_resident(rig_figure_ctx *c, uint8_t *out_device, void *stream)
+{
+    if (!c) return RIG_E_INVALID;
+    if (!out_device && c->n_images) return ffail(c, RIG_E_INVALID, "out_device is NULL");
+    if (((uintptr_t)out_device) % 16) return ffail(c, RIG_E_INVALID, "out_device must be 16-byte aligned");
+    if (!c->resident_device_geom)
+        return ffail(c, RIG_E_UNSUPPORTED, "the resident scene was prepared by the host pipeline (geometry mode, or the device handed it back: status 0x%x)",
+                     c->stats.geom_status);
+    FCK(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    int rc = run_geometry(c, st);
+    if (rc) return rc;
+    c->draw_pending = true;
+    return launch(c, 0, (uint32_t)c->n_images, out_device, 0, st);
+}
+
+int64_t rig_figure_debug_resident(rig_figure_ctx *c, uint32_t *layers_out, int32_t *edges_out, int64_t edge_cap, int64_t *n_layers_out)
+{
+    if (!c || !layers_out || !edges_out) return RIG_E_INVALID;
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return RIG_E_CUDA;
+    const size_t nl = (size_t)c->stats.layers, ni = (size_t)c->n_images;
+    std::vector<FLayer> layers(nl);
+    std::vector<uint32_t> begin(ni + 1);
+    if (nl && cudaMemcpy(layers.data(), c->d_layers, sizeof(FLayer) * nl, cudaMemcpyDeviceToHost) != cudaSuccess) return RIG_E_CUDA;
+    if (cudaMemcpy(begin.data(), c->d_begin, sizeof(uint32_t) * (ni + 1), cudaMemcpyDeviceToHost) != cudaSuccess) return RIG_E_CUDA;
+    int64_t ne = 0, out_l = 0;
+    size_t img = 0;
+    for (size_t l = 0; l < nl; l++) {
+        while (img + 1 < begin.size() && begin[img + 1] <= l) img++;
+        const FLayer &L = layers[l];
+        if (L.n_edges == 0) continue;                       // an empty slot (the host pipeline drops such passes)
+        if (ne + (int64_t)L.n_edges > edge_cap) return RIG_E_CAPACITY;
+        if (cudaMemcpy(edges_out + 4 * ne, c->d_edges + L.edge_begin, sizeof(FEdge) * L.n_edges, cudaMemcpyDeviceToHost) != cudaSuccess) return RIG_E_CUDA;
+        uint32_t *o = layers_out + 8 * out_l++;
+        o[0] = (uint32_t)img; o[1] = (uint32_t)ne; o[2] = L.n_edges; o[3] = L.rgba;
+        o[4] = (uint32_t)(int32_t)L.xmin; o[5] = (uint32_t)(int32_t)L.xmax; o[6] = (uint32_t)(int32_t)L.ymin; o[7] = (uint32_t)(int32_t)L.ymax;
+        ne += L.n_edges;
+    }
+    if (n_layers_out) *n_layers_out = out_l;
+    return ne;
 }
 
 int rig_figure_render_batch(rig_figure_ctx *c, const rig_figure_scene *scene, uint8_t *out, int out_is_device, int out_layout, void *stream)
@@ -652,6 +932,8 @@ int rig_figure_set_profiling(rig_figure_ctx *c, int on)
         c->stats.cover_ms = 0;
         c->stats.timed_launches = 0;
         c->stats.timed_images = 0;
+        c->stats.geom_ms = 0;
+        c->stats.geom_launches = 0;
     }
     return RIG_OK;
 }
@@ -659,6 +941,7 @@ int rig_figure_set_profiling(rig_figure_ctx *c, int on)
 int rig_figure_get_stats(rig_figure_ctx *c, rig_figure_stats *out)
 {
     if (!c || !out) return RIG_E_INVALID;
+    c->stats.geom_resident = c->resident_device_geom ? 1u : 0u;
     *out = c->stats;
     return RIG_OK;
 }

@@ -26,6 +26,14 @@
 #include "../../include/rig_figure.h"
 #include "rig_figure_core.h"
 
+// The large routines are real functions on the device (one copy each): inlined at every call site the kernel is several MB of
+// SASS and does not finish compiling.
+#if defined(__CUDACC__)
+#define RIG_HD_NI __host__ __device__ __noinline__
+#else
+#define RIG_HD_NI inline
+#endif
+
 namespace rig {
 namespace geom {
 
@@ -101,7 +109,7 @@ public:
         open_ = false;
         pi_ok_ = false;
     }
-    RIG_HD void line_to(double x2, double y2)
+    RIG_HD_NI void line_to(double x2, double y2)
     {
         open_ = true;
         const unsigned f2 = flags(x2, y2);
@@ -251,7 +259,7 @@ public:
     }
     RIG_HD void add(double x, double y) { push(x, y); }
     // finishes the sub-path: closed = it ended with CLOSEPOLY
-    RIG_HD void finish(bool closed)
+    RIG_HD_NI void finish(bool closed)
     {
         settle(closed);
         const int n = (int)seq_.size();
@@ -306,7 +314,7 @@ private:
         if (n > 1 && !measure(seq_[n - 2], seq_[n - 1])) seq_.pop_back();
         seq_.push_back(SV{x, y, 0.0, 0.0, 0.0});
     }
-    RIG_HD void settle(bool closed)
+    RIG_HD_NI void settle(bool closed)
     {
         while (seq_.size() > 1) {
             const int n = (int)seq_.size();
@@ -346,7 +354,7 @@ private:
         y = ay + r * (by - ay);
         return true;
     }
-    RIG_HD void arc(double x, double y, double dx1, double dy1, double dx2, double dy2)
+    RIG_HD_NI void arc(double x, double y, double dx1, double dy1, double dx2, double dy2)
     {
         double a1 = atan2(dy1 * wsign_, dx1 * wsign_), a2 = atan2(dy2 * wsign_, dx2 * wsign_);
         double da = acos(wabs_ / (wabs_ + 0.125 / 1.0)) * 2;
@@ -376,7 +384,7 @@ private:
         out(x + dx2, y + dy2);
     }
     // revert = true: matplotlib's 'miter' (agg::miter_join_revert) and the inner miter
-    RIG_HD void miter(const SV &v0, const SV &v1, const SV &v2, double dx1, double dy1, double dx2, double dy2, double mlimit)
+    RIG_HD_NI void miter(const SV &v0, const SV &v1, const SV &v2, double dx1, double dy1, double dx2, double dy2, double mlimit)
     {
         double xi = v1.x, yi = v1.y;
         const double lim = wabs_ * mlimit;
@@ -400,7 +408,7 @@ private:
         }
     }
     // (dx1, dy1), (dx2, dy2): w (v1.y - v0.y) / len1, w (v1.x - v0.x) / len1 and the same for v1 -> v2
-    RIG_HD void join(const SV &v0, const SV &v1, const SV &v2, double dx1, double dy1, double dx2, double dy2, double len1, double len2)
+    RIG_HD_NI void join(const SV &v0, const SV &v1, const SV &v2, double dx1, double dy1, double dx2, double dy2, double len1, double len2)
     {
         const double cp = cross(v0.x, v0.y, v1.x, v1.y, v2.x, v2.y);
         if ((cp > kVertexDistEps && w_ > 0) || (cp < -kVertexDistEps && w_ < 0)) {
@@ -427,7 +435,7 @@ private:
             out(v1.x + dx2, v1.y - dy2);
         }
     }
-    RIG_HD void cap(const SV &v0, const SV &v1, double len)
+    RIG_HD_NI void cap(const SV &v0, const SV &v1, double len)
     {
         double dx1 = (v1.y - v0.y) / len, dy1 = (v1.x - v0.x) / len, dx2 = 0, dy2 = 0;
         dx1 *= w_;
@@ -479,7 +487,7 @@ struct QuadTask { double x1, y1, x2, y2, x3, y3; int level; };
 struct CubicTask { double x1, y1, x2, y2, x3, y3, x4, y4; int level; };
 
 template <class Emit>
-RIG_HD void quad_split(Emit &emit, double x1, double y1, double x2, double y2, double x3, double y3)
+RIG_HD_NI void quad_split(Emit &emit, double x1, double y1, double x2, double y2, double x3, double y3)
 {
     QuadTask stack[kCurveRecursionLimit + 2];
     int sp = 0;
@@ -523,7 +531,7 @@ RIG_HD void quad_split(Emit &emit, double x1, double y1, double x2, double y2, d
 }
 
 template <class Emit>
-RIG_HD void cubic_split(Emit &emit, double x1, double y1, double x2, double y2, double x3, double y3, double x4, double y4)
+RIG_HD_NI void cubic_split(Emit &emit, double x1, double y1, double x2, double y2, double x3, double y3, double x4, double y4)
 {
     CubicTask stack[kCurveRecursionLimit + 2];
     int sp = 0;
@@ -646,7 +654,7 @@ struct ArtistSetup {
     double lw;
     bool face, stroke;
 };
-RIG_HD uint32_t artist_setup(const rig_figure_scene &s, uint32_t a, int W, int H, ArtistSetup &o, int &bad_what)
+RIG_HD_NI uint32_t artist_setup(const rig_figure_scene &s, uint32_t a, int W, int H, ArtistSetup &o, int &bad_what)
 {
     const uint32_t vb = s.artist_vertex_begin[a], ve = s.artist_vertex_begin[a + 1];
     const double *af = s.affine + 6 * (size_t)a;
@@ -706,7 +714,7 @@ RIG_HD uint32_t artist_setup(const rig_figure_scene &s, uint32_t a, int W, int H
 
 // flattened sub-paths of one artist -> fill sink or stroker
 template <class OnMove, class OnLine, class OnClose>
-RIG_HD void walk_flat(const PathView &path, OnMove &on_move, OnLine &on_line, OnClose &on_close)
+RIG_HD_NI void walk_flat(const PathView &path, OnMove &on_move, OnLine &on_line, OnClose &on_close)
 {
     double lx = 0, ly = 0;
     const uint32_t n = path.n;

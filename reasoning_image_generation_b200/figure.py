@@ -177,13 +177,17 @@ class RigFigureStats(ctypes.Structure):
     """struct rig_figure_stats (include/rig_figure.h)"""
     _fields_ = [('kernel_launches', ctypes.c_uint64), ('edges', ctypes.c_uint64), ('layers', ctypes.c_uint64),
                 ('timed_launches', ctypes.c_uint32), ('reserved', ctypes.c_uint32), ('cover_ms', ctypes.c_double),
-                ('timed_images', ctypes.c_uint64), ('prepare_ms', ctypes.c_double)]
+                ('timed_images', ctypes.c_uint64), ('prepare_ms', ctypes.c_double), ('geom_ms', ctypes.c_double),
+                ('geom_launches', ctypes.c_uint32), ('geom_fallbacks', ctypes.c_uint32), ('geom_status', ctypes.c_uint32),
+                ('geom_resident', ctypes.c_uint32)]
 
 
 FIGURE_EXPORTS = ('rig_figure_create', 'rig_figure_destroy', 'rig_figure_last_error', 'rig_figure_render_batch',
                   'rig_figure_upload', 'rig_figure_render_resident', 'rig_figure_sync', 'rig_figure_get_stats',
                   'rig_figure_set_profiling', 'rig_figure_debug_edges', 'rig_figure_stream', 'rig_figure_fence',
-                  'rig_figure_blank_bands', 'rig_figure_set_blank_flags')
+                  'rig_figure_blank_bands', 'rig_figure_set_blank_flags', 'rig_figure_set_geometry', 'rig_figure_draw_resident',
+                  'rig_figure_debug_resident')
+GEOM_HOST, GEOM_DEVICE = 0, 1
 
 _bound = False
 
@@ -221,6 +225,12 @@ def _lib():
         lib.rig_figure_set_profiling.restype = ctypes.c_int
         lib.rig_figure_debug_edges.argtypes = [ctypes.POINTER(RigFigureScene), ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int64, vp]
         lib.rig_figure_debug_edges.restype = ctypes.c_int64
+        lib.rig_figure_set_geometry.argtypes = [vp, ctypes.c_int]
+        lib.rig_figure_set_geometry.restype = ctypes.c_int
+        lib.rig_figure_draw_resident.argtypes = [vp, vp, vp]
+        lib.rig_figure_draw_resident.restype = ctypes.c_int
+        lib.rig_figure_debug_resident.argtypes = [vp, vp, vp, ctypes.c_int64, vp]
+        lib.rig_figure_debug_resident.restype = ctypes.c_int64
         _bound = True
     return lib
 
@@ -357,6 +367,27 @@ class FigureRenderer:
         with self._lock:
             self._check(self._lib.rig_figure_render_resident(self._h, out_ptr, stream or None))
 
+    def draw_resident(self, out_ptr: int, stream: int = 0):
+        """The whole draw_path of every artist of the resident scene: k_figure_path (transform, snap, flattening, stroking,
+        clipping, from the artist arrays in HBM) followed by k_figure."""
+        with self._lock:
+            self._check(self._lib.rig_figure_draw_resident(self._h, out_ptr, stream or None))
+
+    def set_geometry(self, mode: str):
+        """'device' (default): k_figure_path; 'host': the host path pipeline.  Same integers either way."""
+        self._check(self._lib.rig_figure_set_geometry(self._h, {'host': GEOM_HOST, 'device': GEOM_DEVICE}[mode]))
+
+    def resident_edges(self, cap: int = 1 << 22):
+        """(layers, edges) of the resident scene copied back from the device, in the format of `host_edges` (test hook)."""
+        layers = np.zeros((max(1, int(self.stats()['layers'])), 8), dtype=np.uint32)
+        edges = np.zeros((cap, 4), dtype=np.int32)
+        nl = ctypes.c_int64(0)
+        with self._lock:
+            n = self._lib.rig_figure_debug_resident(self._h, layers.ctypes.data, edges.ctypes.data, cap, ctypes.byref(nl))
+        if n < 0:
+            raise FigureError(int(n), 'rig_figure_debug_resident failed')
+        return layers[:nl.value].copy(), edges[:n].copy()
+
     def sync(self):
         with self._lock:
             self._check(self._lib.rig_figure_sync(self._h))
@@ -369,4 +400,5 @@ class FigureRenderer:
         self._check(self._lib.rig_figure_get_stats(self._h, ctypes.byref(st)))
         return dict(kernel_launches=int(st.kernel_launches), edges=int(st.edges), layers=int(st.layers),
                     timed_launches=int(st.timed_launches), cover_ms=float(st.cover_ms), timed_images=int(st.timed_images),
-                    prepare_ms=float(st.prepare_ms))
+                    prepare_ms=float(st.prepare_ms), geom_ms=float(st.geom_ms), geom_launches=int(st.geom_launches),
+                    geom_fallbacks=int(st.geom_fallbacks), geom_status=int(st.geom_status), geom_resident=int(st.geom_resident))

@@ -32,7 +32,7 @@ def test_every_declared_figure_symbol_is_exported(built):
     txt = open(os.path.join(ROOT, 'include', 'rig_figure.h')).read()
     txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
     names = sorted(set(re.findall(r'\b(rig_figure_[a-z_]+)\s*\(', txt)))
-    assert len(names) == 14
+    assert len(names) == 17
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(figure.FIGURE_EXPORTS) == names
