@@ -30,7 +30,6 @@ constexpr int FIG_ROWS = FIG_BAND_ROWS;
 constexpr int FIG_ACC = FIG_ACC_CELLS;     // accumulator columns per row; wider layers are resolved in column chunks (multiple of 32, <= 1024)
 constexpr int FIG_MAX_WARPS = 32;
 constexpr uint32_t FIG_NO_ROWS = 0x80007fffu;   // ymin = 32767, ymax = -32768: overlaps no band (a "1 > 0" range would overlap rows 0..1)
-constexpr uint32_t FIG_DIR_MIN_EDGES = 96; // layers with fewer edges are scanned whole (no slab directory look-up)
 
 struct FigureParams {
     const uint32_t *image_layer_begin;   // [n_images + 1]

@@ -465,19 +465,22 @@ int ensure_geom_scratch(rig_figure_ctx *c)
 {
     if (c->d_seq) return RIG_OK;
     int per_sm = 0;
-    FCK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_figure_path, GEOM_THREADS, sizeof(uint32_t) * GEOM_WARPS * (size_t)(c->H + 34)));
+    FCK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_figure_path, GEOM_THREADS, sizeof(uint32_t) * GEOM_WARPS * geom_warp_smem_words(c->H)));
     if (per_sm < 1) return ffail(c, RIG_E_CUDA, "k_figure_path cannot be resident");
     // Thread-private scratch: the stroker's vertex sequence (40 B per flattened vertex) and the pass's unsorted edges.  Sized for
     // outlines a few times the canvas diagonal; longer ones set GEOM_SEQ_OVERFLOW / GEOM_EDGE_OVERFLOW and the batch goes to the host.
     const int dim = std::max(c->W, c->H);
     c->seq_cap = dim <= 1024 ? 512u : 2048u;
     c->stage_cap = dim <= 1024 ? 1024u : 4096u;
-    if (const char *e = getenv("RIG_GEOM_SEQ_CAP")) c->seq_cap = (uint32_t)std::max(8, atoi(e));
-    if (const char *e = getenv("RIG_GEOM_STAGE_CAP")) c->stage_cap = (uint32_t)std::max(8, atoi(e));
-    const size_t per_thread = sizeof(geom::SV) * c->seq_cap + sizeof(FEdge) * c->stage_cap;
     const size_t budget = (size_t)3 << 30;
     int ctas = per_sm * c->sm_count;
-    while (ctas > c->sm_count && (size_t)ctas * GEOM_THREADS * per_thread > budget) ctas -= c->sm_count;
+    auto per_thread = [&] { return sizeof(geom::SV) * c->seq_cap + sizeof(FEdge) * c->stage_cap; };
+    // full occupancy first (the kernel is latency bound), at the price of shorter scratch: a warp-route path still has
+    // 8 * seq_cap vertices and 32 * stage_cap edges
+    while ((size_t)ctas * GEOM_THREADS * per_thread() > budget && c->seq_cap > (dim <= 1024 ? 256u : 1024u)) { c->seq_cap /= 2; c->stage_cap /= 2; }
+    while (ctas > c->sm_count && (size_t)ctas * GEOM_THREADS * per_thread() > budget) ctas -= c->sm_count;
+    if (const char *e = getenv("RIG_GEOM_SEQ_CAP")) c->seq_cap = (uint32_t)std::max(8, atoi(e));
+    if (const char *e = getenv("RIG_GEOM_STAGE_CAP")) c->stage_cap = (uint32_t)std::max(8, atoi(e));
     c->geom_ctas_per_sm = ctas / c->sm_count;
     c->geom_threads = (uint32_t)ctas * GEOM_THREADS;
     FCK(c, cudaMalloc(&c->d_seq, sizeof(geom::SV) * c->seq_cap * (size_t)c->geom_threads));
@@ -488,14 +491,16 @@ int ensure_geom_scratch(rig_figure_ctx *c)
 // k_figure_path over the resident artist arrays (counters reset first); asynchronous
 int run_geometry(rig_figure_ctx *c, cudaStream_t st)
 {
-    static const uint32_t init[GC_WORDS] = {0u, 0u, 0u, 0u, 0xffffffffu, 0u, 0u, 0u};
+    static uint32_t init[GC_WORDS] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    init[GC_BAD_ARTIST] = 0xffffffffu;
     FCK(c, cudaMemcpyAsync(c->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
     const uint32_t na = (uint32_t)c->gp.s.n_artists;
     if (na == 0) return RIG_OK;
-    const uint32_t want = (na + GEOM_THREADS - 1) / GEOM_THREADS;
+    const uint32_t want_warps = c->gp.n_long / 4u + (na - c->gp.n_long + 31u) / 32u;      // a warp takes several long paths in turn
+    const uint32_t want = (want_warps + GEOM_WARPS - 1) / GEOM_WARPS;
     const uint32_t grid = std::max(1u, std::min(want, c->geom_threads / GEOM_THREADS));
     if (c->profiling) fprof_event(c, st);
-    k_figure_path<<<grid, GEOM_THREADS, sizeof(uint32_t) * GEOM_WARPS * (size_t)(c->H + 34), st>>>(c->gp);
+    k_figure_path<<<grid, GEOM_THREADS, sizeof(uint32_t) * GEOM_WARPS * geom_warp_smem_words(c->H), st>>>(c->gp);
     c->stats.kernel_launches++;
     if (c->profiling) { fprof_event(c, st); c->ev_images.push_back(0x80000000u | (uint32_t)c->n_images); }
     FCK(c, cudaGetLastError());
@@ -534,7 +539,11 @@ int upload_device_geometry(rig_figure_ctx *c, const rig_figure_scene *s, int lay
         for (size_t k = 0; k < na; k++) c->bucket[key(k) + 1]++;
         for (uint32_t b = 0; b < kB; b++) c->bucket[b + 1] += c->bucket[b];
         for (size_t k = 0; k < na; k++) c->artist_order[c->bucket[key(k)]++] = (uint32_t)k;
+        uint32_t n_long = 0;
+        while (n_long < na && s->artist_vertex_begin[c->artist_order[n_long] + 1] - s->artist_vertex_begin[c->artist_order[n_long]] >= GEOM_LONG_MIN_VERTICES) n_long++;
+        c->gp.n_long = n_long;
     }
+    const auto t1 = std::chrono::steady_clock::now();
     // ---- pack everything into one page-locked blob (workers copy 1 MB pieces), one DMA
     const BlobLayout L = blob_layout(s);
     const unsigned slot = c->prep_next++ & 1u;
@@ -555,7 +564,11 @@ int upload_device_geometry(rig_figure_ctx *c, const rig_figure_scene *s, int lay
     const std::function<void(int)> copy_piece = [&](int k) { memcpy(hb.data() + pieces[k].at, pieces[k].src, pieces[k].bytes); };
     if (pieces.size() < 4 || c->host->pool.size() == 1) { for (size_t k = 0; k < pieces.size(); k++) copy_piece((int)k); }
     else c->host->pool.run((int)pieces.size(), copy_piece);
-    c->stats.prepare_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    const auto t2 = std::chrono::steady_clock::now();
+    c->stats.prepare_ms = std::chrono::duration<double, std::milli>(t2 - t0).count();
+    if (getenv("RIG_PREP_TRACE"))
+        fprintf(stderr, "upload (device geometry): slots + order %.3f ms, pack %zu B in %zu pieces %.3f ms\n",
+                std::chrono::duration<double, std::milli>(t1 - t0).count(), L.total, pieces.size(), std::chrono::duration<double, std::milli>(t2 - t1).count());
     if ((rc = ensure(c, c->d_blob, c->cap_blob, L.total))) return rc;
     FCK(c, cudaMemcpyAsync(c->d_blob, hb.data(), L.total, cudaMemcpyHostToDevice, st));
     FCK(c, cudaMemcpyAsync(c->d_begin, hb.data() + L.ilb, 4 * (ni + 1), cudaMemcpyHostToDevice, st));

@@ -35,6 +35,7 @@ struct alignas(16) FLayer {
     uint32_t pad;
 };
 constexpr int FIG_SLAB_ROWS = 16;
+constexpr uint32_t FIG_DIR_MIN_EDGES = 96;   // k_figure scans layers with fewer edges whole (no slab directory look-up)
 
 // ---- render_hline: one edge inside one row ------------------------------------------------------
 // acc(ex, dcover, darea) is called for every cell with a non-zero contribution.

@@ -109,7 +109,7 @@ public:
         open_ = false;
         pi_ok_ = false;
     }
-    RIG_HD_NI void line_to(double x2, double y2)
+    RIG_HD void line_to(double x2, double y2)
     {
         open_ = true;
         const unsigned f2 = flags(x2, y2);
@@ -121,6 +121,10 @@ public:
             px_ = x2; py_ = y2; pf_ = f2;
             return;
         }
+        line_to_clipped(x2, y2, f2);
+    }
+    RIG_HD_NI void line_to_clipped(double x2, double y2, unsigned f2)
+    {
         pi_ok_ = false;
         clipped_ = true;
         if ((pf_ & 10u) == (f2 & 10u) && (pf_ & 10u) != 0u) {   // both above or both below the box
@@ -384,7 +388,7 @@ private:
         out(x + dx2, y + dy2);
     }
     // revert = true: matplotlib's 'miter' (agg::miter_join_revert) and the inner miter
-    RIG_HD_NI void miter(const SV &v0, const SV &v1, const SV &v2, double dx1, double dy1, double dx2, double dy2, double mlimit)
+    RIG_HD void miter(const SV &v0, const SV &v1, const SV &v2, double dx1, double dy1, double dx2, double dy2, double mlimit)
     {
         double xi = v1.x, yi = v1.y;
         const double lim = wabs_ * mlimit;
@@ -407,6 +411,8 @@ private:
             out(v1.x + dx2, v1.y - dy2);
         }
     }
+public:
+    // One join / one cap on their own (the warp-cooperative device route evaluates them one per lane).
     // (dx1, dy1), (dx2, dy2): w (v1.y - v0.y) / len1, w (v1.x - v0.x) / len1 and the same for v1 -> v2
     RIG_HD_NI void join(const SV &v0, const SV &v1, const SV &v2, double dx1, double dy1, double dx2, double dy2, double len1, double len2)
     {
@@ -471,7 +477,9 @@ private:
         }
         out(v0.x + dx1, v0.y - dy1);
     }
+    RIG_HD double half_width() const { return w_; }
 
+private:
     Sink &sink_;
     Seq &seq_;        // caller-owned, so that its capacity survives from artist to artist
     Unc &unc_;
@@ -654,7 +662,11 @@ struct ArtistSetup {
     double lw;
     bool face, stroke;
 };
-RIG_HD_NI uint32_t artist_setup(const rig_figure_scene &s, uint32_t a, int W, int H, ArtistSetup &o, int &bad_what)
+// artist_setup in three steps, so that the device can run the scan over the vertices with one lane per vertex:
+//   artist_setup_begin   the path view (borrowed arrays + device transform)
+//   artist_scan_vertex   what PathSnapper's scan and the input validation learn from vertex i (and its predecessor)
+//   artist_setup_end     snapping decision, clip box, which passes the artist asks for
+RIG_HD void artist_setup_begin(const rig_figure_scene &s, uint32_t a, int H, ArtistSetup &o)
 {
     const uint32_t vb = s.artist_vertex_begin[a], ve = s.artist_vertex_begin[a + 1];
     const double *af = s.affine + 6 * (size_t)a;
@@ -668,20 +680,23 @@ RIG_HD_NI uint32_t artist_setup(const rig_figure_scene &s, uint32_t a, int W, in
     p.tr = tr;
     p.snap = false;
     p.snap_add = 0.0;
-    bad_what = 0;
-    // PathSnapper's scan (auto mode: only rectilinear paths of at most 1024 vertices are snapped) doubles as input validation
-    bool rectilinear = true;
-    double x0 = 0, y0 = 0;
-    for (uint32_t i = 0; i < p.n; i++) {
-        const Node nd = p.raw(i);
-        if (!is_vertex_code(nd.code) && nd.code != RIG_PATH_STOP && nd.code != RIG_PATH_CLOSEPOLY) { bad_what = 1; return GEOM_BAD_INPUT; }
-        if (!(isfinite(nd.x) && isfinite(nd.y))) { bad_what = 2; return GEOM_BAD_INPUT; }
-        if (i > 0 && rectilinear) {
-            if (nd.code == RIG_PATH_CURVE3 || nd.code == RIG_PATH_CURVE4) rectilinear = false;
-            else if (nd.code == RIG_PATH_LINETO && !(fabs(x0 - nd.x) < 1e-4 || fabs(y0 - nd.y) < 1e-4)) rectilinear = false;
-        }
-        x0 = nd.x; y0 = nd.y;
+}
+// bad: 0 fine, 1 unknown code, 2 non-finite vertex; not_rectilinear: the vertex rules out snapping in auto mode
+RIG_HD void artist_scan_vertex(const PathView &p, uint32_t i, const Node &prev, const Node &nd, int &bad, bool &not_rectilinear)
+{
+    (void)p;
+    bad = 0;
+    not_rectilinear = false;
+    if (!is_vertex_code(nd.code) && nd.code != RIG_PATH_STOP && nd.code != RIG_PATH_CLOSEPOLY) { bad = 1; return; }
+    if (!(isfinite(nd.x) && isfinite(nd.y))) { bad = 2; return; }
+    if (i > 0) {
+        if (nd.code == RIG_PATH_CURVE3 || nd.code == RIG_PATH_CURVE4) not_rectilinear = true;
+        else if (nd.code == RIG_PATH_LINETO && !(fabs(prev.x - nd.x) < 1e-4 || fabs(prev.y - nd.y) < 1e-4)) not_rectilinear = true;
     }
+}
+RIG_HD_NI uint32_t artist_setup_end(const rig_figure_scene &s, uint32_t a, int W, int H, bool rectilinear, ArtistSetup &o, int &bad_what)
+{
+    PathView &p = o.path;
     const double lw = s.linewidth[a];
     if (!(lw >= 0.0) || !isfinite(lw)) { bad_what = 3; return GEOM_BAD_INPUT; }
     o.lw = lw;
@@ -710,6 +725,25 @@ RIG_HD_NI uint32_t artist_setup(const rig_figure_scene &s, uint32_t a, int W, in
     o.face = s.has_face[a] && s.face_rgba[4 * (size_t)a + 3] != 0;
     o.stroke = lw != 0.0 && s.edge_rgba[4 * (size_t)a + 3] != 0;
     return 0;
+}
+RIG_HD_NI uint32_t artist_setup(const rig_figure_scene &s, uint32_t a, int W, int H, ArtistSetup &o, int &bad_what)
+{
+    artist_setup_begin(s, a, H, o);
+    const PathView &p = o.path;
+    bad_what = 0;
+    // PathSnapper's scan (auto mode: only rectilinear paths of at most 1024 vertices are snapped) doubles as input validation
+    bool rectilinear = true;
+    Node prev{0.0, 0.0, 0};
+    for (uint32_t i = 0; i < p.n; i++) {
+        const Node nd = p.raw(i);
+        int bad;
+        bool nr;
+        artist_scan_vertex(p, i, prev, nd, bad, nr);
+        if (bad) { bad_what = bad; return GEOM_BAD_INPUT; }
+        if (nr) rectilinear = false;
+        prev = nd;
+    }
+    return artist_setup_end(s, a, W, H, rectilinear, o, bad_what);
 }
 
 // flattened sub-paths of one artist -> fill sink or stroker

@@ -30,11 +30,15 @@ constexpr int GEOM_THREADS = 128;           // per CTA
 constexpr int GEOM_WARPS = GEOM_THREADS / 32;
 
 // counters[] slots
-constexpr int GC_WORK = 0, GC_EDGES = 1, GC_DIR = 2, GC_STATUS = 3, GC_BAD_ARTIST = 4, GC_BAD_WHAT = 5, GC_WORDS = 8;
+// (GC_EDGES, GC_DIR) form one 64-bit word: a layer placement reserves both with a single atomic
+constexpr int GC_WORK = 0, GC_WORK_LONG = 1, GC_EDGES = 2, GC_DIR = 3, GC_STATUS = 4, GC_BAD_ARTIST = 5, GC_BAD_WHAT = 6, GC_WORDS = 8;
+constexpr uint32_t GEOM_LONG_MIN_VERTICES = 12;   // paths at least this long go one per warp
+constexpr int GEOM_CMD_CAP = 1024;               // path commands the warp route parses (longer paths: serial on one lane)
 
 struct GeomParams {
     rig_figure_scene s;              // device pointers
-    const uint32_t *artist_order;    // [n_artists] artists in work order
+    const uint32_t *artist_order;    // [n_artists] artists in work order (longest paths first)
+    uint32_t n_long;                 // the first n_long of them take the warp-cooperative route (one warp per artist)
     const uint32_t *artist_layer;    // [n_artists] first layer slot of the artist
     int W, H, bgr;
     FLayer *layers;
@@ -46,6 +50,8 @@ struct GeomParams {
     FEdge *stage;                    // [threads * stage_cap]
     uint32_t seq_cap, stage_cap;
 };
+
+__host__ __device__ inline size_t geom_warp_smem_words(int H) { return (size_t)(H + 34 > GEOM_CMD_CAP ? H + 34 : GEOM_CMD_CAP); }
 
 struct DevSeq {
     geom::SV *p;
@@ -101,13 +107,14 @@ __device__ __forceinline__ void geom_place_layers(const GeomParams &P, int lane,
                                                   uint32_t *hist, uint32_t &status)
 {
     const uint32_t n = have_layer ? E.n : 0u;
-    const uint32_t nd = n ? (uint32_t)((E.ymax - E.ymin) / FIG_SLAB_ROWS + 2) : 0u;
+    const uint32_t nd = n >= FIG_DIR_MIN_EDGES ? (uint32_t)((E.ymax - E.ymin) / FIG_SLAB_ROWS + 2) : 0u;   // (smaller layers: never read)
     uint32_t etot, dtot;
     const uint32_t eoff = warp_excl_scan(n, lane, etot), doff = warp_excl_scan(nd, lane, dtot);
     uint32_t ebase = 0, dbase = 0;
     if (lane == 0 && etot) {
-        ebase = atomicAdd(P.counters + GC_EDGES, etot);
-        dbase = atomicAdd(P.counters + GC_DIR, dtot);
+        const unsigned long long got = atomicAdd((unsigned long long *)(P.counters + GC_EDGES), (unsigned long long)etot | ((unsigned long long)dtot << 32));
+        ebase = (uint32_t)got;
+        dbase = (uint32_t)(got >> 32);
     }
     ebase = __shfl_sync(0xffffffffu, ebase, 0);
     dbase = __shfl_sync(0xffffffffu, dbase, 0);
@@ -142,26 +149,9 @@ __device__ __forceinline__ void geom_place_layers(const GeomParams &P, int lane,
         const FEdge *from = (const FEdge *)(uintptr_t)sp;
         FEdge *to = P.edges + se;
         if (sn <= 32u) {
-            // one chunk: rank by comparing keys across the lanes (stable: ties in emission order)
-            int4 v = make_int4(0, 0, 0, 0);
-            int key = 0x7fffffff;
-            if ((uint32_t)lane < sn) {
-                v = *(const int4 *)(from + lane);
-                key = (min(v.y, v.w) >> 8) - symin;
-            }
-            uint32_t rank = 0;
-            for (uint32_t j = 0; j < sn; j++) {
-                const int kj = __shfl_sync(0xffffffffu, key, (int)j);
-                rank += (kj < key || (kj == key && (int)j < lane)) ? 1u : 0u;
-            }
-            if ((uint32_t)lane < sn) *(int4 *)(to + rank) = v;
-            // slab directory: dir[s] = edges whose first row < 16 s
-            const int rows = symax - symin + 1, slabs = (symax - symin) / FIG_SLAB_ROWS + 2;
-            for (int s = 0; s < slabs; s++) {
-                const int lim = min(s * FIG_SLAB_ROWS, rows);
-                const uint32_t c = __popc(__ballot_sync(0xffffffffu, key < lim));
-                if (lane == 0) P.dir[sd + s] = c;
-            }
+            // one chunk of k_figure's edge loop: the order inside it changes nothing (no sort, no directory: k_figure scans layers
+            // of fewer than FIG_DIR_MIN_EDGES edges whole)
+            if ((uint32_t)lane < sn) *(int4 *)(to + lane) = *(const int4 *)(from + lane);
             continue;
         }
         const int rows = symax - symin + 1;              // first rows lie in [0, rows)
@@ -186,8 +176,10 @@ __device__ __forceinline__ void geom_place_layers(const GeomParams &P, int lane,
             carry += __shfl_sync(0xffffffffu, inc, 31);
         }
         __syncwarp();
-        const int slabs = (symax - symin) / FIG_SLAB_ROWS + 2;
-        for (int s = lane; s < slabs; s += 32) P.dir[sd + s] = hist[min(s * FIG_SLAB_ROWS, rows)];
+        if (sn >= FIG_DIR_MIN_EDGES) {
+            const int slabs = (symax - symin) / FIG_SLAB_ROWS + 2;
+            for (int s = lane; s < slabs; s += 32) P.dir[sd + s] = hist[min(s * FIG_SLAB_ROWS, rows)];
+        }
         __syncwarp();
         for (uint32_t e0 = 0; e0 < sn; e0 += 32) {
             const uint32_t e = e0 + lane;
@@ -211,11 +203,294 @@ __device__ __forceinline__ void geom_place_layers(const GeomParams &P, int lane,
     }
 }
 
-__global__ void __launch_bounds__(GEOM_THREADS) k_figure_path(const GeomParams P)
+
+// ---- warp-cooperative route: one artist per warp ---------------------------------------------------------------------------
+// A stroker is sequential only in how it is written down: once the flattened, de-duplicated vertex list exists, every join
+// depends on three neighbouring vertices, every contour segment on two neighbouring contour points, and the clipper keeps
+// no state but the previous point.  So, for one path:
+//   parse     (uniform) the walk of walk_flat over the path codes -> a command list in shared memory
+//   flatten   lane = command: curve3_div / curve4_div twice (count, then store at the prefix-sum offset) -> P[0..N)
+//   measure   lane = vertex: distance to the next vertex (vertex_sequence); a coincident pair anywhere sends the path to the
+//             serial code on lane 0 (agg's de-duplication is order dependent)
+//   joins     lane = join: math_stroke::calc_join / calc_cap with a sink that keeps the <= 2 points; prefix sum -> contour C[]
+//   clip      lane = contour segment: rasterizer_sl_clip on (C[k], C[k+1]); prefix sum -> the warp's edge staging
+// The values are those of the serial code (same functions, same operands); the order of the edges is the emission order.
+// Only miter / bevel joins and butt / projecting caps take this route (round ones emit a variable number of libm points).
+struct WarpScratch {
+    double2 *P;            // flattened vertices
+    double *d, *nx, *ny;   // per vertex: distance to the next one, half-width offsets of that segment
+    double2 *C;            // contour points
+    uint32_t cap_pts, cap_contour;
+    FEdge *stage;          // the warp's 32 staging areas, contiguous
+    uint32_t stage_cap;
+};
+
+struct NoSeq {              // the stroker's vertex storage, for a StrokeGen that only evaluates single joins / caps
+    geom::SV dummy;
+    __device__ __forceinline__ int size() const { return 0; }
+    __device__ __forceinline__ geom::SV &operator[](int) { return dummy; }
+    __device__ __forceinline__ geom::SV &back() { return dummy; }
+    __device__ __forceinline__ void push_back(const geom::SV &) {}
+    __device__ __forceinline__ void pop_back() {}
+    __device__ __forceinline__ void clear() {}
+};
+struct TwoPoints {           // sink of one join / cap
+    double x[2], y[2];
+    int n;
+    bool overflow;
+    __device__ __forceinline__ void put(double px, double py)
+    {
+        if (n < 2) { x[n] = px; y[n] = py; n++; }
+        else overflow = true;
+    }
+    __device__ __forceinline__ void move_to(double px, double py) { put(px, py); }
+    __device__ __forceinline__ void line_to(double px, double py) { put(px, py); }
+    __device__ __forceinline__ void close() {}
+    __device__ __forceinline__ double cx1() const { return 0; }
+    __device__ __forceinline__ double cy1() const { return 0; }
+    __device__ __forceinline__ double cx2() const { return 0; }
+    __device__ __forceinline__ double cy2() const { return 0; }
+};
+struct LaneEdges {           // sink of one clipped contour segment (3 spans, each split at most once)
+    int4 e[6];
+    int n;
+    __device__ __forceinline__ void push(int x1, int y1, int x2, int y2)
+    {
+        if (n < 6) e[n++] = make_int4(x1, y1, x2, y2);
+    }
+};
+
+// parse: returns the number of commands, or -1 when the path does not have the one shape this route handles
+// (MOVETO, then LINETO / CURVE3 / CURVE4 commands, optionally one closing CLOSEPOLY at the very end)
+__device__ __forceinline__ int geom_warp_parse(const geom::PathView &path, uint32_t *cmd, int &closed)
+{
+    const uint32_t n = path.n;
+    closed = 0;
+    if (n < 2 || n > 0xffffffu || path.codes[0] != RIG_PATH_MOVETO) return -1;
+    int ncmd = 0;
+    uint32_t i = 1;
+    while (i < n) {
+        const uint32_t c = path.codes[i];
+        if (c == RIG_PATH_STOP) break;
+        if (ncmd >= GEOM_CMD_CAP) return -1;
+        if (c == RIG_PATH_CURVE3 && i + 1 < n) { cmd[ncmd++] = i | (3u << 24); i += 2; }
+        else if (c == RIG_PATH_CURVE4 && i + 2 < n) { cmd[ncmd++] = i | (4u << 24); i += 3; }
+        else if (c == RIG_PATH_LINETO) { cmd[ncmd++] = i | (2u << 24); i += 1; }
+        else if (c == RIG_PATH_CLOSEPOLY && (i + 1 == n || path.codes[i + 1] == RIG_PATH_STOP)) { closed = 1; break; }
+        else return -1;
+    }
+    return ncmd;
+}
+
+// flatten: P[0..N); returns N, or -1 on overflow of the scratch (status set).  Every lane subdivides its curve once, into its own
+// slice of the (still unused) contour area; the slices are then moved to their place in P[], command after command.
+__device__ __forceinline__ int geom_warp_flatten(const geom::PathView &path, const uint32_t *cmd, int ncmd, int lane, WarpScratch &ws, uint32_t &status)
+{
+    if (lane == 0) {
+        const geom::Node m = path.node(0);
+        ws.P[0] = make_double2(m.x, m.y);
+    }
+    const uint32_t slice_cap = ws.cap_contour / 32u;
+    double2 *slice = ws.C + (size_t)lane * slice_cap;
+    uint32_t base = 1;
+    for (int c0 = 0; c0 < ncmd; c0 += 32) {
+        const int j = c0 + lane;
+        uint32_t cnt = 0;
+        double2 single = make_double2(0, 0);
+        bool over = false;
+        if (j < ncmd) {
+            const uint32_t vi = cmd[j] & 0xffffffu, type = cmd[j] >> 24;
+            const geom::Node a = path.node(vi);
+            if (type == 2u) { cnt = 1; single = make_double2(a.x, a.y); }
+            else {
+                const geom::Node st = path.node(vi - 1), b = path.node(vi + 1);
+                struct SliceEmit {
+                    double2 *p;
+                    uint32_t n, cap;
+                    __device__ __forceinline__ void operator()(double x, double y)
+                    {
+                        if (n < cap) p[n] = make_double2(x, y);
+                        n++;
+                    }
+                } se{slice, 0u, slice_cap};
+                if (type == 3u) { geom::quad_split(se, st.x, st.y, a.x, a.y, b.x, b.y); se(b.x, b.y); }
+                else {
+                    const geom::Node c = path.node(vi + 2);
+                    geom::cubic_split(se, st.x, st.y, a.x, a.y, b.x, b.y, c.x, c.y);
+                    se(c.x, c.y);
+                }
+                cnt = se.n;
+                over = cnt > slice_cap;
+            }
+        }
+        uint32_t total;
+        const uint32_t off = warp_excl_scan(cnt, lane, total);
+        if (__any_sync(0xffffffffu, over) || base + total > ws.cap_pts) { status |= geom::GEOM_SEQ_OVERFLOW; return -1; }
+        __syncwarp();
+        if (cnt == 1u && j < ncmd && (cmd[j] >> 24) == 2u) ws.P[base + off] = single;
+        uint32_t curves = __ballot_sync(0xffffffffu, j < ncmd && (cmd[j] >> 24) != 2u);
+        while (curves) {
+            const int src = __ffs(curves) - 1;
+            curves &= curves - 1;
+            const uint32_t scnt = __shfl_sync(0xffffffffu, cnt, src), soff = __shfl_sync(0xffffffffu, off, src);
+            const double2 *from = ws.C + (size_t)src * slice_cap;
+            for (uint32_t k = lane; k < scnt; k += 32) ws.P[base + soff + k] = from[k];
+        }
+        __syncwarp();
+        base += total;
+    }
+    __syncwarp();
+    return (int)base;
+}
+
+// clip: the closed contour C[0..M) -> edges appended to the warp's staging (E: lane-private bounding cells, n_edges: uniform count)
+__device__ __forceinline__ void geom_warp_clip_contour(const double2 *C, int M, const geom::ArtistSetup &art, int lane, WarpScratch &ws, DevEdges &E,
+                                                       uint32_t &n_edges, uint32_t &status)
+{
+    if (M < 2) return;                                    // a lone move_to draws nothing
+    for (int k0 = 0; k0 < M; k0 += 32) {
+        const int k = k0 + lane;
+        LaneEdges le;
+        le.n = 0;
+        if (k < M) {
+            const double2 p = C[k], q = C[k + 1 < M ? k + 1 : 0];
+            geom::ClipToCells<LaneEdges> clip(le, art.bx1, art.by1, art.bx2, art.by2);
+            clip.move_to(p.x, p.y);
+            clip.line_to(q.x, q.y);
+        }
+        uint32_t total;
+        const uint32_t off = warp_excl_scan((uint32_t)le.n, lane, total);
+        if (n_edges + total > 32u * ws.stage_cap) { status |= geom::GEOM_EDGE_OVERFLOW; return; }
+        for (int t = 0; t < le.n; t++) {
+            const int4 v = le.e[t];
+            const int a = min(v.y, v.w) >> 8, b = max(v.y, v.w) >> 8;
+            E.ymin = min(E.ymin, a); E.ymax = max(E.ymax, b);
+            E.xmin = min(E.xmin, min(v.x, v.z) >> 8); E.xmax = max(E.xmax, max(v.x, v.z) >> 8);
+            E.maxspan = max(E.maxspan, b - a);
+            *(int4 *)(ws.stage + n_edges + off + t) = v;
+        }
+        n_edges += total;
+    }
+}
+
+// lane 0 ends up owning the layer: E.n = edges staged by the warp, bounding cells reduced over the lanes
+__device__ __forceinline__ void geom_warp_reduce_bounds(DevEdges &E, uint32_t n_edges, int lane, const WarpScratch &ws)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        E.ymin = min(E.ymin, __shfl_xor_sync(0xffffffffu, E.ymin, o)); E.ymax = max(E.ymax, __shfl_xor_sync(0xffffffffu, E.ymax, o));
+        E.xmin = min(E.xmin, __shfl_xor_sync(0xffffffffu, E.xmin, o)); E.xmax = max(E.xmax, __shfl_xor_sync(0xffffffffu, E.xmax, o));
+        E.maxspan = max(E.maxspan, __shfl_xor_sync(0xffffffffu, E.maxspan, o));
+    }
+    E.n = lane == 0 ? n_edges : 0u;
+    E.p = ws.stage;
+    __syncwarp();
+}
+
+// stroke of the flattened path P[0..N): returns false if the path must take the serial code (coincident vertices, too few)
+__device__ __forceinline__ bool geom_warp_stroke(int N, int closed, const geom::ArtistSetup &art, int cap_style, int join_style, int lane, WarpScratch &ws,
+                                                 DevEdges &E, uint32_t &n_edges, uint32_t &status)
+{
+    // ---- measure (vertex_sequence): d[i] = |P[i+1] - P[i]|, i < N - 1
+    bool coincident = false;
+    for (int i = lane; i < N - 1; i += 32) {
+        const double2 a = ws.P[i], b = ws.P[i + 1];
+        const double dd = sqrt(geom::dist2(a.x, a.y, b.x, b.y));
+        ws.d[i] = dd;
+        if (!(dd > geom::kVertexDistEps)) coincident = true;
+    }
+    if (__any_sync(0xffffffffu, coincident)) return false;
+    if (closed) {
+        // the closing vertex usually repeats the first one: agg drops it (and then looks at the new last vertex)
+        double2 f = ws.P[0], l = ws.P[N - 1];
+        double dd = sqrt(geom::dist2(l.x, l.y, f.x, f.y));
+        if (!(dd > geom::kVertexDistEps)) {
+            N -= 1;
+            if (N < 2) return false;
+            l = ws.P[N - 1];
+            dd = sqrt(geom::dist2(l.x, l.y, f.x, f.y));
+            if (!(dd > geom::kVertexDistEps)) return false;
+        }
+        if (lane == 0) ws.d[N - 1] = dd;
+    }
+    if (N < 3) closed = 0;
+    if (N < 2 + (closed ? 1 : 0)) return true;             // nothing to draw (the serial code returns here too)
+    __syncwarp();
+    // ---- half-width offsets per segment
+    const double w = art.lw * 0.5;
+    const int nseg = closed ? N : N - 1;
+    for (int i = lane; i < nseg; i += 32) {
+        const double2 c = ws.P[i], q = ws.P[i + 1 < N ? i + 1 : 0];
+        const double dd = ws.d[i];
+        ws.nx[i] = w * (q.y - c.y) / dd;
+        ws.ny[i] = w * (q.x - c.x) / dd;
+    }
+    __syncwarp();
+    // ---- joins and caps, in contour order.  Item t of a contour -> (kind, vertex):
+    //   closed: contour 0 = joins 0 .. N-1 forward, contour 1 = joins N-1 .. 0 backward
+    //   open:   one contour = cap(0), joins 1 .. N-2 forward, cap(N-1), joins N-2 .. 1 backward
+    NoSeq noseq;
+    geom::Certain certain;
+    const int n_contours = closed ? 2 : 1;
+    const int items = closed ? N : 2 + 2 * (N - 2);
+    if ((uint32_t)(2 * items) > ws.cap_contour) { status |= geom::GEOM_SEQ_OVERFLOW; return true; }
+    for (int ct = 0; ct < n_contours; ct++) {
+        uint32_t M = 0;
+        for (int t0 = 0; t0 < items; t0 += 32) {
+            const int t = t0 + lane;
+            TwoPoints tp;
+            tp.n = 0; tp.overflow = false;
+            if (t < items) {
+                geom::StrokeGen<NoSeq, TwoPoints, geom::Certain> gen(noseq, art.lw, cap_style, join_style, tp, certain);
+                int i;                // vertex
+                int kind;             // 0 forward join, 1 backward join, 2 cap at 0, 3 cap at N-1
+                if (closed) { kind = ct; i = ct == 0 ? t : N - 1 - t; }
+                else if (t == 0) { kind = 2; i = 0; }
+                else if (t <= N - 2) { kind = 0; i = t; }
+                else if (t == N - 1) { kind = 3; i = N - 1; }
+                else { kind = 1; i = N - 2 - (t - N); }
+                if (kind >= 2) {
+                    const int o = kind == 2 ? 1 : N - 2;                  // the neighbour the cap looks at
+                    const double2 a = ws.P[i], b = ws.P[o];
+                    const geom::SV v0{a.x, a.y, 0, 0, 0}, v1{b.x, b.y, 0, 0, 0};
+                    gen.cap(v0, v1, ws.d[kind == 2 ? 0 : N - 2]);
+                } else {
+                    const int ip = i ? i - 1 : N - 1, iq = i + 1 < N ? i + 1 : 0;
+                    const double2 a = ws.P[ip], b = ws.P[i], c = ws.P[iq];
+                    const geom::SV vp{a.x, a.y, 0, 0, 0}, vc{b.x, b.y, 0, 0, 0}, vq{c.x, c.y, 0, 0, 0};
+                    const double pnx = ws.nx[ip], pny = ws.ny[ip], cnx = ws.nx[i], cny = ws.ny[i], pd = ws.d[ip], cd = ws.d[i];
+                    if (kind == 0) gen.join(vp, vc, vq, pnx, pny, cnx, cny, pd, cd);
+                    else gen.join(vq, vc, vp, 0.0 - cnx, 0.0 - cny, 0.0 - pnx, 0.0 - pny, cd, pd);
+                }
+            }
+            if (tp.overflow) status |= geom::GEOM_SEQ_OVERFLOW;
+            uint32_t total;
+            const uint32_t off = warp_excl_scan((uint32_t)tp.n, lane, total);
+            for (int u = 0; u < tp.n; u++) ws.C[M + off + u] = make_double2(tp.x[u], tp.y[u]);
+            M += total;
+        }
+        __syncwarp();
+        geom_warp_clip_contour(ws.C, (int)M, art, lane, ws, E, n_edges, status);
+        __syncwarp();
+    }
+    return true;
+}
+
+// fill of the flattened path: the path itself is the contour (the rasteriser closes it)
+__device__ __forceinline__ void geom_warp_face(int N, const geom::ArtistSetup &art, int lane, WarpScratch &ws, DevEdges &E, uint32_t &n_edges, uint32_t &status)
+{
+    geom_warp_clip_contour(ws.P, N, art, lane, ws, E, n_edges, status);
+    __syncwarp();
+}
+
+#ifndef GEOM_MIN_CTAS
+#define GEOM_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(GEOM_THREADS, GEOM_MIN_CTAS) k_figure_path(const GeomParams P)
 {
     extern __shared__ uint32_t geom_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *hist = geom_smem + (size_t)warp * (size_t)(P.H + 34);
+    uint32_t *hist = geom_smem + (size_t)warp * geom_warp_smem_words(P.H);
     const size_t tid = (size_t)blockIdx.x * GEOM_THREADS + threadIdx.x;
     DevSeq seq;
     seq.p = P.seq + tid * P.seq_cap; seq.n = 0; seq.cap = (int)P.seq_cap; seq.overflow = false;
@@ -224,9 +499,111 @@ __global__ void __launch_bounds__(GEOM_THREADS) k_figure_path(const GeomParams P
     E.reset();
     uint32_t status = 0;
     const uint32_t n_art = (uint32_t)P.s.n_artists;
+    // ---- long paths: one per warp
+    {
+        WarpScratch ws;
+        const size_t wtid = tid - lane;                                  // the warp's first thread
+        uint8_t *sb = (uint8_t *)(P.seq + wtid * P.seq_cap);             // 32 * seq_cap * 40 bytes
+        ws.cap_pts = P.seq_cap * 8u;
+        ws.cap_contour = P.seq_cap * 32u;
+        ws.P = (double2 *)sb;                                            // 16 B * cap_pts
+        ws.d = (double *)(sb + (size_t)16 * ws.cap_pts);                 // 3 * 8 B * cap_pts
+        ws.nx = ws.d + ws.cap_pts;
+        ws.ny = ws.nx + ws.cap_pts;
+        ws.C = (double2 *)(sb + (size_t)40 * ws.cap_pts);                // 16 B * cap_contour  (total 40 * 8 + 16 * 32 = 832 <= 1280 B per seq_cap)
+        ws.stage = P.stage + wtid * P.stage_cap;
+        ws.stage_cap = P.stage_cap;
+        uint32_t *cmd = hist;
+        for (;;) {
+            uint32_t k = 0;
+            if (lane == 0) k = atomicAdd(P.counters + GC_WORK_LONG, 1u);
+            k = __shfl_sync(0xffffffffu, k, 0);
+            if (k >= P.n_long) break;
+            const uint32_t a = P.artist_order[k];
+            geom::ArtistSetup art;
+            geom::artist_setup_begin(P.s, a, P.H, art);
+            // the scan, one lane per vertex
+            int bad = 0;
+            bool nr = false;
+            for (uint32_t i = lane; i < art.path.n; i += 32) {
+                const geom::Node nd = art.path.raw(i);
+                const geom::Node prev = i ? art.path.raw(i - 1) : geom::Node{0.0, 0.0, 0};
+                int b1;
+                bool n1;
+                geom::artist_scan_vertex(art.path, i, prev, nd, b1, n1);
+                if (b1 && !bad) bad = b1;
+                nr |= n1;
+            }
+            const bool any_bad = __any_sync(0xffffffffu, bad != 0);
+            const bool rectilinear = !__any_sync(0xffffffffu, nr);
+            int what = 0;
+            uint32_t badbits = any_bad ? geom::GEOM_BAD_INPUT : geom::artist_setup_end(P.s, a, P.W, P.H, rectilinear, art, what);
+            const uint32_t slot = P.artist_layer[a];
+            bool run = true;
+            if (badbits) {
+                art.face = P.s.has_face[a] && P.s.face_rgba[4 * (size_t)a + 3] != 0;
+                art.stroke = P.s.edge_rgba[4 * (size_t)a + 3] != 0 && P.s.linewidth[a] != 0.0;
+                status |= badbits;
+                if (lane == 0 && atomicCAS(P.counters + GC_BAD_ARTIST, 0xffffffffu, a) == 0xffffffffu) P.counters[GC_BAD_WHAT] = (uint32_t)(what ? what : 2);
+                run = false;
+            }
+            const int cap_style = P.s.cap[a], join_style = P.s.join[a];
+            int closed = 0, N = -1;
+            bool parallel = false;
+            if (run) {
+                const int ncmd = geom_warp_parse(art.path, cmd, closed);
+                __syncwarp();
+                if (ncmd >= 0) {
+                    N = geom_warp_flatten(art.path, cmd, ncmd, lane, ws, status);
+                    parallel = N >= 0;
+                    if (N < 0) run = false;                              // scratch overflow: status set, the host takes the batch
+                }
+            }
+            // ---- pass 0: face
+            E.reset();
+            uint32_t n_edges = 0;
+            if (run && art.face) {
+                if (parallel) geom_warp_face(N, art, lane, ws, E, n_edges, status);
+                else if (lane == 0) { geom::face_pass(art, E); n_edges = E.n; }
+            }
+            if (E.overflow) status |= geom::GEOM_EDGE_OVERFLOW;
+            if (parallel) geom_warp_reduce_bounds(E, n_edges, lane, ws);
+            geom_place_layers(P, lane, lane == 0 && art.face, slot, geom::pack_rgba(P.s.face_rgba + 4 * (size_t)a, P.bgr != 0), E, hist, status);
+            __syncwarp();
+            // ---- pass 1: stroke
+            E.p = P.stage + tid * P.stage_cap;
+            E.reset();
+            n_edges = 0;
+            if (run && art.stroke) {
+                bool done = false;
+                if (parallel && join_style != RIG_JOIN_ROUND && cap_style != RIG_CAP_ROUND) {
+                    // (parse wrote the command list over hist; place_layers above reused it, flatten's output is in global scratch)
+                    done = geom_warp_stroke(N, closed, art, cap_style, join_style, lane, ws, E, n_edges, status);
+                    if (done) geom_warp_reduce_bounds(E, n_edges, lane, ws);
+                }
+                if (!done) {
+                    E.p = P.stage + tid * P.stage_cap;
+                    E.reset();
+                    if (lane == 0) {
+                        geom::Uncertain unc;
+                        seq.overflow = false;
+                        geom::stroke_pass(art, cap_style, join_style, seq, E, unc);
+                        if (unc.hit) status |= geom::GEOM_UNCERTAIN;
+                        if (seq.overflow) status |= geom::GEOM_SEQ_OVERFLOW;
+                    }
+                }
+            }
+            if (E.overflow) status |= geom::GEOM_EDGE_OVERFLOW;
+            geom_place_layers(P, lane, lane == 0 && art.stroke, slot + (art.face ? 1u : 0u), geom::pack_rgba(P.s.edge_rgba + 4 * (size_t)a, P.bgr != 0), E,
+                              hist, status);
+            __syncwarp();
+            E.p = P.stage + tid * P.stage_cap;
+        }
+    }
+    // ---- short paths: one per thread, 32 at a time
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(P.counters + GC_WORK, 32u);
+        if (lane == 0) base = P.n_long + atomicAdd(P.counters + GC_WORK, 32u);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n_art) break;
         const bool have = base + lane < n_art;

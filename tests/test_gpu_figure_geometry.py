@@ -19,6 +19,19 @@ from reasoning_image_generation_b200.synth_figure import synthetic_figure_scene
 pytestmark = pytest.mark.gpu
 
 
+def canon(layers, edges):
+    """Edges of every layer in a canonical order: layers of at most 32 edges keep the emission order on the device (one chunk of
+    k_figure's edge loop: the order inside it is irrelevant) while the host sorts them by first row; larger layers are sorted by
+    first row, stably, on both sides."""
+    out = edges.copy()
+    for L in layers:
+        b, n = int(L[1]), int(L[2])
+        if n <= 32:
+            e = out[b:b + n]
+            out[b:b + n] = e[np.lexsort((e[:, 3], e[:, 2], e[:, 1], e[:, 0]))]
+    return out
+
+
 def same_geometry(scene, max_artists=None):
     r = FigureRenderer(scene.W, scene.H, max_images=max(scene.n_images, 1), max_artists=max_artists or max(scene.n_artists, 1))
     r.set_geometry('device')
@@ -31,7 +44,7 @@ def same_geometry(scene, max_artists=None):
     r.close()
     assert dl.shape == hl.shape
     assert (dl == hl).all(), np.argwhere(dl != hl)[:5]
-    assert de.shape == he.shape and (de == he).all()
+    assert de.shape == he.shape and (canon(dl, de) == canon(hl, he)).all()
     return st
 
 
@@ -55,7 +68,7 @@ def test_stress_scene_same_edges(built):
     # round joins / caps go through libm: the device may hand the batch back (then the resident edges ARE the host's)
     assert st['geom_status'] in (0, 8), st
     assert dl.shape == hl.shape and (dl == hl).all()
-    assert de.shape == he.shape and (de == he).all()
+    assert de.shape == he.shape and (canon(dl, de) == canon(hl, he)).all()
 
 
 def test_large_canvas_same_edges(built):
@@ -130,7 +143,7 @@ def test_edge_arena_grows(built):
     hl, he = host_edges(sc)
     r.close()
     assert st['edges'] > 12 * sc.n_vertices + 16 * sc.n_artists or st['geom_status'] == 8
-    assert (dl == hl).all() and (de == he).all()
+    assert (dl == hl).all() and (canon(dl, de) == canon(hl, he)).all()
 
 
 def test_bad_input_is_named_by_the_host_pipeline(built):
