@@ -5,15 +5,18 @@
     python bench.py --impl reference [--gpus N] [--steps K] ...     # the reference's CPU path (oracle port)
 
 Headline workload (BASELINE.json configs[1]): multigraph single-shape variants (one outlined base patch with internal
-lines or occlusion masks) at 512x512, the figure path: host path pipeline once at upload, then k_figure per step.
-A "step" is one pass of the hot path over one batch of synthetic figure scenes, per GPU.
-  value      whole-job images/s, scenes already resident in HBM (polygon edges in 24.8 fixed point), CUDA events on the
-             launching stream, barrier + synchronize on both sides, max over ranks
-  e2e        the same metric through the public API (FigureRenderer.render) with HOST buffers: the host path pipeline
-             (transform, snap, curve flattening, stroking, clipping), H2D of the edges, rendering and the D2H copy of every
-             pixel into pinned host memory are inside the timed region
+lines or occlusion masks) at 512x512, the figure path.  A "step" is one pass of the hot path -- the whole of
+RendererAgg.draw_path for every artist -- over one batch of synthetic figure scenes, per GPU: k_figure_path
+(transform, snap, curve flattening, stroking, clipping: artist arrays -> polygon edges) followed by k_figure (coverage, blend,
+store).
+  value      whole-job images/s, ARTIST ARRAYS already resident in HBM (what draw_path receives: path vertices + codes, affine,
+             line width, cap / join / snap, colours), CUDA events on the launching stream, barrier + synchronize on both sides,
+             max over ranks
+  e2e        the same metric through the public API (FigureRenderer.iter_png = fig.savefig for a batch) with HOST buffers:
+             packing + H2D of the artist arrays, both kernels, the device-side PNG encode and the D2H copy of the files into
+             pinned host memory are inside the timed region
   roofline   k_figure (the dominant kernel): algorithmic bytes (786,432 per image) / its CUDA-event time, against the
-             measured HBM figure in MEASURED_PEAKS.json
+             measured HBM figure in MEASURED_PEAKS.json; whole_step_frac covers both kernels
   cpu_baseline  oracle/aggdraw.c (the restated matplotlib/Agg renderer) on this box's host cores, bounded sample
   sequence_panels  the same quantities for the sequence-panel path (k_expand + k_raster, BASELINE configs[3] shape), with
              its own roofline, e2e and cpu_baseline, plus the near-duplicate stage (`dedup`)
@@ -320,7 +323,10 @@ def figure_leg(env, args, sampler):
     r = FigureRenderer(512, 512, device=env.local, max_images=n, max_artists=max(scene.n_artists, 1))
     out = torch.empty((n, 512, 512, 3), dtype=torch.uint8, device='cuda')
     r.upload(scene, 'rgb')
-    render = lambda: r.render_resident(out.data_ptr(), stream=env.st)   # noqa: E731
+    if not r.stats()['geom_resident']:
+        raise SystemExit('bench.py: the device geometry handed the step scene back to the host pipeline (status 0x%x); the headline '
+                         'is defined on k_figure_path + k_figure' % r.stats()['geom_status'])
+    render = lambda: r.draw_resident(out.data_ptr(), stream=env.st)   # noqa: E731
     if sampler is not None:
         sampler.start()
     n_warm = timed_steps(env, render, r.sync, args.steps, args.warmup)
@@ -346,20 +352,23 @@ def figure_leg(env, args, sampler):
     multi = synthetic_figure_scene(n_multi, 512, 512, seed=2000, kind='multi', first=env.rank * n_multi)
     r.upload(multi, 'rgb')
     for _ in range(3):
-        r.render_resident(out.data_ptr(), stream=env.st)
+        r.draw_resident(out.data_ptr(), stream=env.st)
     r.sync()
     r.set_profiling(True)
     for _ in range(max(2, args.steps // 2)):
-        r.render_resident(out.data_ptr(), stream=env.st)
+        r.draw_resident(out.data_ptr(), stream=env.st)
     r.sync()
     mst = r.stats()
     r.set_profiling(False)
-    (multi_ms,) = env.max_over_ranks(mst['cover_ms'] / max(1, mst['timed_launches']))
+    multi_cover, multi_geom = env.max_over_ranks(mst['cover_ms'] / max(1, mst['timed_launches']), mst['geom_ms'] / max(1, mst['geom_launches']))
+    multi_ms = multi_cover + multi_geom
     multi_info = {'value': env.world * n_multi / (multi_ms / 1e3), 'unit': 'images/s', 'images_per_step_per_gpu': n_multi,
-                  'ms_per_step': multi_ms, 'edges_per_image': mst['edges'] / n_multi, 'layers_per_image': mst['layers'] / n_multi,
+                  'ms_per_step': multi_ms, 'figure_ms': multi_cover, 'geometry_ms': multi_geom,
+                  'edges_per_image': mst['edges'] / n_multi, 'layers_per_image': mst['layers'] / n_multi,
                   'hbm_frac': n_multi * IMG_BYTES / (multi_ms / 1e3) / 1e9 / fallback_peak()[0],
+                  'hbm_frac_k_figure': n_multi * IMG_BYTES / (multi_cover / 1e3) / 1e9 / fallback_peak()[0],
                   'workload': 'BASELINE configs[2] shape: 2-3 outlined base patches, nested / adjacent / intersecting (synthetic), '
-                              'k_figure only, scenes resident in HBM'}
+                              'k_figure_path + k_figure, artist arrays resident in HBM'}
     del out
     torch.cuda.empty_cache()
 
@@ -376,7 +385,7 @@ def figure_leg(env, args, sampler):
     env.barrier()
     l0 = r2.stats()['kernel_launches'] + enc.stats()['kernel_launches']
     t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 4))
+    e2e_steps = args.e2e_steps                      # 32 x 32 768 images: a timed region of about a second
     digest = 0
     for _ in range(e2e_steps):
         for i0, buf, off in r2.iter_png(sub, enc, FIG_E2E_CHUNK):
@@ -387,8 +396,10 @@ def figure_leg(env, args, sampler):
     st2 = r2.stats()
     e2e_launches = st2['kernel_launches'] + enc.stats()['kernel_launches'] - l0
     e2e_value = env.world * FIG_E2E * e2e_steps / dt
-    # edges + layer headers of the step scene (the resident upload above holds the same scene) + per-image tables
-    h2d = int((16 * stats['edges'] + 32 * stats['layers']) * (FIG_E2E / n) + 8 * (FIG_E2E + 1))
+    # the artist arrays as the C ABI receives them + the three index tables the library adds (work order, layer slots)
+    h2d = int(sum(a.nbytes for a in (sub.image_artist_begin, sub.artist_vertex_begin, sub.vertices, sub.codes, sub.affine, sub.linewidth, sub.cap,
+                                      sub.join, sub.snap, sub.edge_rgba, sub.face_rgba, sub.has_face)) + 8 * sub.n_artists + 4 * (FIG_E2E + 1))
+    geom_fallbacks = st2['geom_fallbacks']
     enc.close()
     r2.close()
     # ---- the same through the raw-pixel API: every pixel copied to pinned host memory (PCIe-bound)
@@ -399,11 +410,12 @@ def figure_leg(env, args, sampler):
         r.render(sub_px, 'rgb', out=pinned)
     env.barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    px_steps = 4
+    for _ in range(px_steps):
         r.render(sub_px, 'rgb', out=pinned)
     torch.cuda.synchronize()
     (dt_px,) = env.max_over_ranks(time.perf_counter() - t0)
-    px_value = env.world * FIG_E2E_CHUNK * e2e_steps / dt_px
+    px_value = env.world * FIG_E2E_CHUNK * px_steps / dt_px
     per_img_edges = stats['edges'] / n
     checksum = int(pinned[::257, 200:312, 200:312, 0].astype('int64').sum())
     res = {
@@ -412,15 +424,17 @@ def figure_leg(env, args, sampler):
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': png_bytes // e2e_steps,
                 'images_per_step_per_gpu': FIG_E2E, 'chunk': FIG_E2E_CHUNK,
                 'png_bytes_per_image': png_bytes / (e2e_steps * FIG_E2E), 'gpu_launches': e2e_launches,
-                'note': 'FigureRenderer.iter_png = fig.savefig for a batch: host artist arrays in (path pipeline on host threads, '
-                        'edges uploaded), k_figure, device-side PNG encode (RGBA files), finished files copied to pinned host memory; host '
-                        'work of chunk k + 1 overlaps GPU work of chunk k; digest %d' % digest},
+                'timed_s': dt, 'steps': e2e_steps, 'geom_fallbacks': geom_fallbacks,
+                'note': 'FigureRenderer.iter_png = fig.savefig for a batch: host artist arrays in (packed, one H2D copy per chunk), '
+                        'k_figure_path + k_figure, device-side PNG encode (RGBA files), finished files copied to pinned host memory; '
+                        'chunk k + 1 is prepared and rendered while chunk k is encoded and copied; digest %d' % digest},
         'e2e_pixels': {'value': px_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d // max(1, FIG_E2E // FIG_E2E_CHUNK),
                        'd2h_bytes_per_step': FIG_E2E_CHUNK * IMG_BYTES, 'images_per_step_per_gpu': FIG_E2E_CHUNK,
                        'note': 'FigureRenderer.render: the same with every raw pixel copied to pinned host memory instead of PNG '
                                'files (PCIe-bound: 786,432 B per image); checksum %d' % checksum},
         'config': {'workload': FIG_WORKLOAD, 'images_per_step_per_gpu': n, 'l2': 'outputs (25.8 GB/step) exceed L2; no flush needed',
-                   'artists_per_step_per_gpu': scene.n_artists, 'edges_per_image': per_img_edges,
+                   'artists_per_step_per_gpu': scene.n_artists, 'vertices_per_step_per_gpu': scene.n_vertices, 'edges_per_image': per_img_edges,
+                   'resident_input': 'artist arrays (draw_path arguments), %d bytes per image' % (h2d // FIG_E2E),
                    'layers_per_image': stats['layers'] / n, 'out_layout': 'RGB', 'checksum': checksum_dev},
     }
     pin.close()
@@ -469,12 +483,13 @@ def sequence_leg(env, args, sampler, with_cpu):
         r.render(sub, 'rgb', out=pinned)
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 4))
-    for _ in range(e2e_steps):
+    px_steps = 4
+    for _ in range(px_steps):
         r.render(sub, 'rgb', out=pinned)
     torch.cuda.synchronize()
     (dt,) = env.max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * E2E_PANELS * e2e_steps / dt
+    e2e_value = world * E2E_PANELS * px_steps / dt
+    e2e_steps = args.e2e_steps
     h2d = 40 * sub.n_elements + 4 * (sub.n_panels + 1) + sub.n_panels
     d2h = E2E_PANELS * IMG_BYTES
     checksum = int(pinned[::257, 100, 100, 0].astype('int64').sum())
@@ -603,6 +618,7 @@ def sequence_leg(env, args, sampler, with_cpu):
                        'pinned host memory (PCIe-bound); checksum %d' % checksum},
         'e2e': {'value': e2e_png_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d_png, 'd2h_bytes_per_step': seq_png_bytes // e2e_steps,
                     'png_bytes_per_image': seq_png_bytes / (e2e_steps * n), 'panels_per_step_per_gpu': n, 'chunk': E2E_PANELS,
+                    'timed_s': dt_png, 'steps': e2e_steps,
                     'note': 'Renderer.iter_png = save_image / cv2.imwrite for a batch: host SoA scene in, panels rendered and '
                             'PNG-encoded on the device %d at a time, finished files copied to pinned host memory; the render of '
                             'chunk k + 1 overlaps the encode and copy of chunk k' % E2E_PANELS},
@@ -668,7 +684,10 @@ def run_ours(args):
                 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                              'traffic': traffic, 'kernel': 'k_figure', 'peak_source': peak_src, 'launches': stats['timed_launches'],
                              'images_per_launch': per_launch, 'figure_ms_per_step': stats['cover_ms'] / args.steps,
-                             'whole_step_frac': fig['value'] / world * IMG_BYTES / 1e9 / peak},
+                             'geometry_ms_per_step': stats['geom_ms'] / max(1, stats['geom_launches']), 'geometry_kernel': 'k_figure_path',
+                             'whole_step_frac': fig['value'] / world * IMG_BYTES / 1e9 / peak,
+                             'note': 'achieved / frac: k_figure alone (the dominant kernel); whole_step_frac: k_figure_path + k_figure, '
+                                     'i.e. the whole draw_path from artist arrays, = value x 786,432 B / peak'},
                 'cpu_baseline': cpu, 'clocks': fig['clocks'],
             }
             if seq:
@@ -699,6 +718,7 @@ def main():
     ap.add_argument('--workload', default='figure', choices=['figure', 'sequence'],
                     help='figure: BASELINE configs[1] (headline) + the sequence-panel path as a sub-object; sequence: that path only')
     ap.add_argument('--no-sequence', action='store_true', help='figure workload: skip the sequence-panel leg')
+    ap.add_argument('--e2e-steps', type=int, default=32, help='timed passes of the e2e legs over the step scene (about 1 s)')
     ap.add_argument('--seq-cpu-budget', type=float, default=10.0, help='seconds of CPU work for the sequence-panel cpu_baseline')
     args = ap.parse_args()
     if args.impl == 'reference':

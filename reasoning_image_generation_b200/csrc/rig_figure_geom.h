@@ -661,6 +661,9 @@ struct ArtistSetup {
     double bx1, by1, bx2, by2;    // clip box of the rasteriser
     double lw;
     bool face, stroke;
+    // the artist's scalar attributes, read by artist_setup_begin (all its loads are issued together, before the scan)
+    double clip_in[4];
+    uint8_t snap_mode, edge_alpha, face_alpha, has_face, has_clip;
 };
 // artist_setup in three steps, so that the device can run the scan over the vertices with one lane per vertex:
 //   artist_setup_begin   the path view (borrowed arrays + device transform)
@@ -680,6 +683,16 @@ RIG_HD void artist_setup_begin(const rig_figure_scene &s, uint32_t a, int H, Art
     p.tr = tr;
     p.snap = false;
     p.snap_add = 0.0;
+    o.lw = s.linewidth[a];
+    o.snap_mode = s.snap[a];
+    o.edge_alpha = s.edge_rgba[4 * (size_t)a + 3];
+    o.face_alpha = s.face_rgba[4 * (size_t)a + 3];
+    o.has_face = s.has_face[a];
+    o.has_clip = (s.has_clip && s.clip) ? s.has_clip[a] : (uint8_t)0;
+    if (o.has_clip) {
+        const double *c = s.clip + 4 * (size_t)a;
+        o.clip_in[0] = c[0]; o.clip_in[1] = c[1]; o.clip_in[2] = c[2]; o.clip_in[3] = c[3];
+    }
 }
 // bad: 0 fine, 1 unknown code, 2 non-finite vertex; not_rectilinear: the vertex rules out snapping in auto mode
 RIG_HD void artist_scan_vertex(const PathView &p, uint32_t i, const Node &prev, const Node &nd, int &bad, bool &not_rectilinear)
@@ -694,24 +707,23 @@ RIG_HD void artist_scan_vertex(const PathView &p, uint32_t i, const Node &prev, 
         else if (nd.code == RIG_PATH_LINETO && !(fabs(prev.x - nd.x) < 1e-4 || fabs(prev.y - nd.y) < 1e-4)) not_rectilinear = true;
     }
 }
-RIG_HD_NI uint32_t artist_setup_end(const rig_figure_scene &s, uint32_t a, int W, int H, bool rectilinear, ArtistSetup &o, int &bad_what)
+RIG_HD uint32_t artist_setup_end(int W, int H, bool rectilinear, ArtistSetup &o, int &bad_what)
 {
     PathView &p = o.path;
-    const double lw = s.linewidth[a];
+    const double lw = o.lw;
     if (!(lw >= 0.0) || !isfinite(lw)) { bad_what = 3; return GEOM_BAD_INPUT; }
-    o.lw = lw;
-    bool snap = s.snap[a] == RIG_SNAP_TRUE;
-    if (s.snap[a] == RIG_SNAP_AUTO && p.n <= 1024 && p.n != 0) snap = rectilinear;
+    bool snap = o.snap_mode == RIG_SNAP_TRUE;
+    if (o.snap_mode == RIG_SNAP_AUTO && p.n <= 1024 && p.n != 0) snap = rectilinear;
     if (snap) {
-        const double slw = s.edge_rgba[4 * (size_t)a + 3] == 0 ? 0.0 : lw;
+        const double slw = o.edge_alpha == 0 ? 0.0 : lw;
         const int r = (int)(slw + ((slw >= 0.0) ? 0.5 : -0.5));
         p.snap = true;
         p.snap_add = (r % 2) ? 0.5 : 0.0;
     }
     // clip box of the rasteriser (RendererAgg::set_clipbox)
     o.bx1 = 0; o.by1 = 0; o.bx2 = W; o.by2 = H;
-    if (s.has_clip && s.has_clip[a] && s.clip) {
-        const double *c = s.clip + 4 * (size_t)a;
+    if (o.has_clip) {
+        const double *c = o.clip_in;
         int x1 = (int)floor(c[0] + 0.5), y1 = (int)floor((double)H - c[1] + 0.5);
         int x2 = (int)floor(c[2] + 0.5), y2 = (int)floor((double)H - c[3] + 0.5);
         if (x1 < 0) x1 = 0;
@@ -722,8 +734,8 @@ RIG_HD_NI uint32_t artist_setup_end(const rig_figure_scene &s, uint32_t a, int W
         if (y1 > y2) { const int t = y1; y1 = y2; y2 = t; }
         o.bx1 = x1; o.by1 = y1; o.bx2 = x2; o.by2 = y2;
     }
-    o.face = s.has_face[a] && s.face_rgba[4 * (size_t)a + 3] != 0;
-    o.stroke = lw != 0.0 && s.edge_rgba[4 * (size_t)a + 3] != 0;
+    o.face = o.has_face && o.face_alpha != 0;
+    o.stroke = lw != 0.0 && o.edge_alpha != 0;
     return 0;
 }
 RIG_HD_NI uint32_t artist_setup(const rig_figure_scene &s, uint32_t a, int W, int H, ArtistSetup &o, int &bad_what)
@@ -743,7 +755,7 @@ RIG_HD_NI uint32_t artist_setup(const rig_figure_scene &s, uint32_t a, int W, in
         if (nr) rectilinear = false;
         prev = nd;
     }
-    return artist_setup_end(s, a, W, H, rectilinear, o, bad_what);
+    return artist_setup_end(W, H, rectilinear, o, bad_what);
 }
 
 // flattened sub-paths of one artist -> fill sink or stroker

@@ -260,26 +260,59 @@ struct LaneEdges {           // sink of one clipped contour segment (3 spans, ea
     }
 };
 
-// parse: returns the number of commands, or -1 when the path does not have the one shape this route handles
-// (MOVETO, then LINETO / CURVE3 / CURVE4 commands, optionally one closing CLOSEPOLY at the very end)
-__device__ __forceinline__ int geom_warp_parse(const geom::PathView &path, uint32_t *cmd, int &closed)
+// parse: the command list of walk_flat's walk over the path codes, 32 vertices at a time.  Returns the number of commands, or -1
+// when the path does not have the one shape this route handles: MOVETO, then LINETO / CURVE3 / CURVE4 commands whose control
+// vertices carry the curve's own code (runs of CURVE4 in threes, of CURVE3 in twos), optionally one closing CLOSEPOLY at the very
+// end; vertices after a STOP are ignored as walk_flat ignores them.  Anything else takes the serial code on lane 0.
+__device__ __forceinline__ int geom_warp_parse(const geom::PathView &path, uint32_t *cmd, int &closed, int lane)
 {
     const uint32_t n = path.n;
     closed = 0;
     if (n < 2 || n > 0xffffffu || path.codes[0] != RIG_PATH_MOVETO) return -1;
     int ncmd = 0;
-    uint32_t i = 1;
-    while (i < n) {
-        const uint32_t c = path.codes[i];
-        if (c == RIG_PATH_STOP) break;
-        if (ncmd >= GEOM_CMD_CAP) return -1;
-        if (c == RIG_PATH_CURVE3 && i + 1 < n) { cmd[ncmd++] = i | (3u << 24); i += 2; }
-        else if (c == RIG_PATH_CURVE4 && i + 2 < n) { cmd[ncmd++] = i | (4u << 24); i += 3; }
-        else if (c == RIG_PATH_LINETO) { cmd[ncmd++] = i | (2u << 24); i += 1; }
-        else if (c == RIG_PATH_CLOSEPOLY && (i + 1 == n || path.codes[i + 1] == RIG_PATH_STOP)) { closed = 1; break; }
-        else return -1;
+    uint32_t carry4 = 0, carry3 = 0;                 // length of the curve run that ends at the previous chunk's last vertex
+    bool ok = true;
+    for (uint32_t b = 1; b < n; b += 32) {
+        const uint32_t v = b + lane;
+        const uint32_t c = v < n ? path.codes[v] : (uint32_t)RIG_PATH_STOP;
+        const uint32_t cnext = v + 1 < n ? path.codes[v + 1] : (uint32_t)RIG_PATH_STOP;
+        const uint32_t mstop = __ballot_sync(0xffffffffu, c == RIG_PATH_STOP);
+        const uint32_t live_mask = mstop ? ((1u << (__ffs(mstop) - 1)) - 1u) : 0xffffffffu;     // lanes before the first STOP
+        const bool live = (live_mask >> lane) & 1u;
+        const uint32_t m4 = __ballot_sync(0xffffffffu, c == RIG_PATH_CURVE4), m3 = __ballot_sync(0xffffffffu, c == RIG_PATH_CURVE3);
+        const uint32_t lt = (1u << lane) - 1u;
+        bool start = false, bad = false;
+        uint32_t type = 0;
+        if (live) {
+            if (c == RIG_PATH_LINETO) { start = true; type = 2u; }
+            else if (c == RIG_PATH_CURVE4 || c == RIG_PATH_CURVE3) {
+                const bool four = c == RIG_PATH_CURVE4;
+                const uint32_t below = ~(four ? m4 : m3) & lt;                  // lanes before this one that are not in the run
+                const uint32_t pos = below ? (uint32_t)lane - (32u - (uint32_t)__clz(below)) : (uint32_t)lane + (four ? carry4 : carry3);
+                const uint32_t period = four ? 3u : 2u;
+                start = pos % period == 0u;
+                type = four ? 4u : 3u;
+                if (cnext != c && (pos + 1u) % period != 0u) bad = true;         // the run ends in the middle of a curve
+            } else if (c == RIG_PATH_CLOSEPOLY) {
+                if (cnext != RIG_PATH_STOP) bad = true;                           // only as the path's last command
+            } else bad = true;                                                    // a second MOVETO, other end-poly flags, unknown codes
+        }
+        const uint32_t mclose = __ballot_sync(0xffffffffu, live && c == RIG_PATH_CLOSEPOLY);
+        if (mclose) closed = 1;
+        const uint32_t mstart = __ballot_sync(0xffffffffu, start);
+        if (__any_sync(0xffffffffu, bad) || ncmd + __popc(mstart) > GEOM_CMD_CAP) { ok = false; break; }
+        if (start) cmd[ncmd + __popc(mstart & lt)] = v | (type << 24);
+        ncmd += __popc(mstart);
+        // run lengths carried into the next chunk (from lane 31's point of view)
+        {
+            const uint32_t below4 = ~m4, below3 = ~m3;
+            carry4 = (m4 >> 31) ? (below4 ? 31u - (31u - (uint32_t)__clz(below4)) : 32u + carry4) : 0u;
+            carry3 = (m3 >> 31) ? (below3 ? 31u - (31u - (uint32_t)__clz(below3)) : 32u + carry3) : 0u;
+        }
+        if (mstop || mclose) break;
     }
-    return ncmd;
+    __syncwarp();
+    return ok ? ncmd : -1;
 }
 
 // flatten: P[0..N); returns N, or -1 on overflow of the scratch (status set).  Every lane subdivides its curve once, into its own
@@ -522,6 +555,8 @@ __global__ void __launch_bounds__(GEOM_THREADS, GEOM_MIN_CTAS) k_figure_path(con
             const uint32_t a = P.artist_order[k];
             geom::ArtistSetup art;
             geom::artist_setup_begin(P.s, a, P.H, art);
+            const int cap_style = P.s.cap[a], join_style = P.s.join[a];
+            const uint32_t slot = P.artist_layer[a];
             // the scan, one lane per vertex
             int bad = 0;
             bool nr = false;
@@ -537,21 +572,19 @@ __global__ void __launch_bounds__(GEOM_THREADS, GEOM_MIN_CTAS) k_figure_path(con
             const bool any_bad = __any_sync(0xffffffffu, bad != 0);
             const bool rectilinear = !__any_sync(0xffffffffu, nr);
             int what = 0;
-            uint32_t badbits = any_bad ? geom::GEOM_BAD_INPUT : geom::artist_setup_end(P.s, a, P.W, P.H, rectilinear, art, what);
-            const uint32_t slot = P.artist_layer[a];
+            uint32_t badbits = any_bad ? geom::GEOM_BAD_INPUT : geom::artist_setup_end(P.W, P.H, rectilinear, art, what);
             bool run = true;
             if (badbits) {
-                art.face = P.s.has_face[a] && P.s.face_rgba[4 * (size_t)a + 3] != 0;
-                art.stroke = P.s.edge_rgba[4 * (size_t)a + 3] != 0 && P.s.linewidth[a] != 0.0;
+                art.face = art.has_face && art.face_alpha != 0;
+                art.stroke = art.edge_alpha != 0 && art.lw != 0.0;
                 status |= badbits;
                 if (lane == 0 && atomicCAS(P.counters + GC_BAD_ARTIST, 0xffffffffu, a) == 0xffffffffu) P.counters[GC_BAD_WHAT] = (uint32_t)(what ? what : 2);
                 run = false;
             }
-            const int cap_style = P.s.cap[a], join_style = P.s.join[a];
             int closed = 0, N = -1;
             bool parallel = false;
             if (run) {
-                const int ncmd = geom_warp_parse(art.path, cmd, closed);
+                const int ncmd = geom_warp_parse(art.path, cmd, closed, lane);
                 __syncwarp();
                 if (ncmd >= 0) {
                     N = geom_warp_flatten(art.path, cmd, ncmd, lane, ws, status);
@@ -568,8 +601,10 @@ __global__ void __launch_bounds__(GEOM_THREADS, GEOM_MIN_CTAS) k_figure_path(con
             }
             if (E.overflow) status |= geom::GEOM_EDGE_OVERFLOW;
             if (parallel) geom_warp_reduce_bounds(E, n_edges, lane, ws);
-            geom_place_layers(P, lane, lane == 0 && art.face, slot, geom::pack_rgba(P.s.face_rgba + 4 * (size_t)a, P.bgr != 0), E, hist, status);
-            __syncwarp();
+            if (art.face) {
+                geom_place_layers(P, lane, lane == 0, slot, geom::pack_rgba(P.s.face_rgba + 4 * (size_t)a, P.bgr != 0), E, hist, status);
+                __syncwarp();
+            }
             // ---- pass 1: stroke
             E.p = P.stage + tid * P.stage_cap;
             E.reset();
@@ -594,9 +629,10 @@ __global__ void __launch_bounds__(GEOM_THREADS, GEOM_MIN_CTAS) k_figure_path(con
                 }
             }
             if (E.overflow) status |= geom::GEOM_EDGE_OVERFLOW;
-            geom_place_layers(P, lane, lane == 0 && art.stroke, slot + (art.face ? 1u : 0u), geom::pack_rgba(P.s.edge_rgba + 4 * (size_t)a, P.bgr != 0), E,
-                              hist, status);
-            __syncwarp();
+            if (art.stroke) {
+                geom_place_layers(P, lane, lane == 0, slot + (art.face ? 1u : 0u), geom::pack_rgba(P.s.edge_rgba + 4 * (size_t)a, P.bgr != 0), E, hist, status);
+                __syncwarp();
+            }
             E.p = P.stage + tid * P.stage_cap;
         }
     }
@@ -619,8 +655,8 @@ __global__ void __launch_bounds__(GEOM_THREADS, GEOM_MIN_CTAS) k_figure_path(con
             if (bad) {
                 // the slots the host counted from the flags stay empty (the placement below is warp-wide, so this lane goes
                 // through it like the others); the host pipeline, which runs next, names the error
-                art.face = P.s.has_face[a] && P.s.face_rgba[4 * (size_t)a + 3] != 0;
-                art.stroke = P.s.edge_rgba[4 * (size_t)a + 3] != 0 && P.s.linewidth[a] != 0.0;
+                art.face = art.has_face && art.face_alpha != 0;
+                art.stroke = art.edge_alpha != 0 && art.lw != 0.0;
                 status |= bad;
                 if (atomicCAS(P.counters + GC_BAD_ARTIST, 0xffffffffu, a) == 0xffffffffu) P.counters[GC_BAD_WHAT] = (uint32_t)what;
                 run = false;
