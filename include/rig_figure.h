@@ -114,7 +114,7 @@ int rig_figure_fence(rig_figure_ctx *ctx, void **event_out);
  * switched on with rig_figure_set_blank_flags(ctx, 1) (off by default: the byte store per band costs k_figure about 2 %):
  * one byte per band of *rows_per_band_out rows, image-major ([n_images][ceil(H / rows)]), in device memory; 1 = no artist reaches
  * the band, every pixel in it is the white background.  Written by k_figure on the render's stream; rig_figure_blank_bands gives
- * the flags of the last render, valid until the second next render (NULL if that render wrote none).  A consumer of the images
+ * the flags of the last render, valid until the fourth next render (NULL if that render wrote none).  A consumer of the images
  * (rig_png_set_blank_hint) can skip those rows without reading them.                                                      */
 int rig_figure_set_blank_flags(rig_figure_ctx *ctx, int on);
 int rig_figure_blank_bands(rig_figure_ctx *ctx, const uint8_t **flags_dev_out, int *rows_per_band_out);

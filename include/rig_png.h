@@ -6,10 +6,11 @@
  *     fig.savefig(save_path, dpi=dpi, ...)  (matplotlib -> libpng)     /root/reference/multigraph_generation/generator.py:256
  * At GPU render rates that is the end-to-end bottleneck twice over: host zlib, and before it the PCIe copy of 786 KB of
  * raw pixels per image.  These entry points encode the images where they are rendered: filter (Sub), LZ77 restricted to
- * zero runs, fixed-Huffman deflate, Adler-32 and CRC-32 all run in CUDA kernels, and only the finished PNG byte streams
- * (typically 5-20 KB per 512 x 512 image of this data set) cross PCIe.  The streams are standard PNG (8-bit RGB or RGBA, one IDAT
- * chunk, zlib stream of byte-aligned fixed-Huffman blocks): any decoder reads them; they are NOT byte-identical to what
- * libpng would write, and the parity criterion is that they decode to exactly the rendered pixels.
+ * zero runs, Huffman coding, Adler-32 and CRC-32 all run in CUDA kernels, and only the finished PNG byte streams (typically
+ * 3-12 KB per 512 x 512 image of this data set, about what libpng writes) cross PCIe.  The streams are standard PNG (8-bit RGB
+ * or RGBA, one IDAT chunk, a zlib stream of one dynamic-Huffman block whose code the context builds once from a model of this
+ * data set's token statistics): any decoder reads them; they are NOT byte-identical to what libpng would write, and the
+ * parity criterion is that they decode to exactly the rendered pixels.
  * Plain C types only; every function returns 0 or a negative RIG_E_* code (include/rig.h).
  */
 #ifndef RIG_PNG_H
@@ -77,6 +78,12 @@ typedef struct rig_png_stats {
 } rig_png_stats;
 int rig_png_get_stats(rig_png_ctx *ctx, rig_png_stats *out);
 int rig_png_set_profiling(rig_png_ctx *ctx, int on);
+
+/* Debug/test hook, needs no GPU: the Huffman code a context for `channels`-channel files uses.  len_out[286]: code lengths of
+ * the literal/length symbols; hdr_out[96] / *hdr_bits_out: the deflate block header (BFINAL = 1, BTYPE = 10, code description) as
+ * an LSB-first bit string; lut_out[516]: the device token tables (code bits | number of bits << 24): [v] literal v, [256 + l]
+ * match of length l = 3..258 at distance 1 (length code, extra bits, the one-bit distance code), [515] end of block.          */
+int rig_png_debug_code(int channels, uint8_t *len_out, uint32_t *hdr_out, uint32_t *hdr_bits_out, uint32_t *lut_out);
 
 #ifdef __cplusplus
 }

@@ -192,8 +192,8 @@ struct rig_figure_ctx {
     size_t cap_layers = 0, cap_edges = 0, cap_dir = 0, cap_images = 0;
     uint8_t *d_stage[2] = {nullptr, nullptr};
     size_t stage_images = 0;
-    // blank-band flags of the last two device-destination renders (a consumer reads one while the next render writes the other)
-    uint8_t *d_blank[2] = {nullptr, nullptr};
+    // blank-band flags of the last four device-destination renders (a consumer reads one while later renders write the others)
+    uint8_t *d_blank[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned blank_next = 0;
     bool want_blank = false;
     const uint8_t *last_blank = nullptr;
@@ -540,7 +540,8 @@ int upload_device_geometry(rig_figure_ctx *c, const rig_figure_scene *s, int lay
         for (uint32_t b = 0; b < kB; b++) c->bucket[b + 1] += c->bucket[b];
         for (size_t k = 0; k < na; k++) c->artist_order[c->bucket[key(k)]++] = (uint32_t)k;
         uint32_t n_long = 0;
-        while (n_long < na && s->artist_vertex_begin[c->artist_order[n_long] + 1] - s->artist_vertex_begin[c->artist_order[n_long]] >= GEOM_LONG_MIN_VERTICES) n_long++;
+        static const uint32_t long_min = getenv("RIG_GEOM_LONG_MIN") ? (uint32_t)std::max(2, atoi(getenv("RIG_GEOM_LONG_MIN"))) : GEOM_LONG_MIN_VERTICES;
+        while (n_long < na && s->artist_vertex_begin[c->artist_order[n_long] + 1] - s->artist_vertex_begin[c->artist_order[n_long]] >= long_min) n_long++;
         c->gp.n_long = n_long;
     }
     const auto t1 = std::chrono::steady_clock::now();
@@ -657,7 +658,7 @@ int launch(rig_figure_ctx *c, uint32_t i0, uint32_t i1, uint8_t *out_dev, uint32
     P.blank = nullptr;
     c->last_blank = nullptr;
     if (c->want_blank && img_base == 0 && i0 == 0) {      // whole-batch launches into the caller's device buffer
-        P.blank = c->d_blank[c->blank_next++ & 1u];
+        P.blank = c->d_blank[c->blank_next++ & 3u];
         c->last_blank = P.blank;
     }
     const uint32_t bands = P.n_images * (uint32_t)((c->H + FIG_ROWS - 1) / FIG_ROWS);
@@ -743,7 +744,7 @@ int rig_figure_create(int device, int W, int H, int max_images, int max_artists,
     FCKC(cudaMalloc(&c->d_begin, sizeof(uint32_t) * ((size_t)max_images + 1)));
     FCKC(cudaMalloc(&c->d_order, sizeof(uint32_t) * (size_t)max_images));
     FCKC(cudaMalloc(&c->d_work, sizeof(uint32_t) * 4));
-    for (int i = 0; i < 2; i++) FCKC(cudaMalloc(&c->d_blank[i], (size_t)max_images * (size_t)((H + FIG_ROWS - 1) / FIG_ROWS)));
+    for (int i = 0; i < 4; i++) FCKC(cudaMalloc(&c->d_blank[i], (size_t)max_images * (size_t)((H + FIG_ROWS - 1) / FIG_ROWS)));
 #undef FCKC
     *out = c;
     return RIG_OK;
@@ -757,7 +758,7 @@ void rig_figure_destroy(rig_figure_ctx *c)
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     cudaFree(c->d_layers); cudaFree(c->d_edges); cudaFree(c->d_dir); cudaFree(c->d_begin); cudaFree(c->d_order); cudaFree(c->d_work);
     cudaFree(c->d_stage[0]); cudaFree(c->d_stage[1]);
-    cudaFree(c->d_blank[0]); cudaFree(c->d_blank[1]);
+    for (int i = 0; i < 4; i++) cudaFree(c->d_blank[i]);
     cudaFree(c->d_blob); cudaFree(c->d_counters); cudaFree(c->d_cost); cudaFree(c->d_seq); cudaFree(c->d_estage);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_cost) cudaFreeHost(c->h_cost);

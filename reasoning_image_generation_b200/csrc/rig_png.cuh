@@ -1,19 +1,25 @@
 // rig_png.cuh -- device-side PNG writer: filter + deflate + checksums in CUDA.
 //
 // Replaces cv2.imwrite / fig.savefig's libpng on the host (src/utils.py:18-21; multigraph_generation/generator.py:256).
-// An image is cut into pieces of PNG_PIECE_ROWS rows; one warp encodes one piece into a byte-aligned run of deflate data:
-//     [fixed-Huffman block: per row, the Sub-filtered bytes as literals, zero runs as (length, distance 1) matches][EOB]
-//     [empty stored block 00 00 FF FF]                     <- zlib's "sync flush": the next piece starts on a byte boundary
-// so pieces can be produced independently and joined by byte offsets.  The puzzle images are flat colour with thin strokes:
-// after the Sub filter (x - left pixel) almost every byte is zero, and restricting LZ77 to zero runs loses little.
+// A file holds ONE dynamic-Huffman deflate block whose code is fixed per context (rig_png_code.h: built on the host from a
+// frequency model of this writer's token stream, so that "258 zeros", the literals 0 / 255 and the filter byte cost 2-4 bits;
+// files are half the size fixed-Huffman ones were and about libpng's).  An image is cut into pieces of PNG_PIECE_ROWS rows; one
+// warp encodes one piece into a BIT string
+//     per row: the Sub-filtered bytes as literals, zero runs as a literal 0 + (length, distance 1) matches
+// with no framing of its own, so pieces are produced independently and k_png_assemble concatenates them at bit offsets behind
+// the block header and closes the block.  The puzzle images are flat colour with thin strokes: after the Sub filter
+// (x - left pixel) almost every byte is zero, and restricting LZ77 to zero runs loses little.
 //   k_png_pieces    lanes own 48-byte chunks (16 pixels) of a row; zero runs are merged across lanes with a ballot; bits are
 //                   counted, offsets come from a warp scan, then the same walk emits them with shared-memory ORs
 //   k_png_sizes / k_png_scan   bytes per file and their exclusive prefix sum (file offsets)
-//   k_png_assemble  one warp per file: header, pieces, final empty block, Adler-32 (combined from per-piece partial sums),
-//                   CRC-32 (per-lane table-driven CRC of a contiguous segment, combined by polynomial multiplication), IEND
+//   k_png_assemble  one warp per file: PNG / zlib framing, the deflate stream gathered word by word (block header, the pieces'
+//                   bits at their prefix-sum offsets, end of block), Adler-32 (combined from per-piece partial sums), CRC-32
+//                   (per-lane table-driven CRC of a contiguous segment, combined by polynomial multiplication), IEND
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "rig_png_code.h"
 
 namespace rig {
 
@@ -27,12 +33,12 @@ constexpr int PNG_CHUNK_PX = 16;              // pixels per lane per pass: 48 fi
 #endif
 constexpr uint32_t PNG_CLAIM = PNG_CLAIM_PIECES;   // consecutive pieces a warp claims at a time
 constexpr uint32_t PNG_SLOT = 512;            // bytes reserved per piece; larger pieces go to the overflow arena
-constexpr uint32_t PNG_FILE_OVERHEAD = 65;    // signature 8 + IHDR 25 + IDAT 12 + zlib header 2 + final block 2 + Adler 4 + IEND 12
+constexpr uint32_t PNG_FILE_OVERHEAD = 63;    // signature 8 + IHDR 25 + IDAT 12 + zlib header 2 + Adler 4 + IEND 12
 constexpr uint32_t ADLER_MOD = 65521u;
 constexpr uint32_t CRC_POLY = 0xedb88320u;
 
 struct PngPiece {
-    uint32_t nbytes;     // deflate bytes of the piece
+    uint32_t nbits;      // deflate bits of the piece
     uint32_t where;      // byte offset of the piece in the scratch area
     uint32_t a, b;       // Adler partial sums over the piece's uncompressed bytes: sum d, sum d * (len - index), mod 65521
 };
@@ -41,45 +47,24 @@ struct PngTables {
     uint32_t crc[256];
     uint32_t x2n[32];    // x^(2^n) mod P (reflected), as zlib's crc32_combine uses
     uint8_t header[33];  // signature + IHDR chunk of this context's W x H
+    // the context's Huffman code (rig_png_code.h): token tables (code bits LSB-first | number of bits << 24) and the block header
+    uint32_t lit[256];
+    uint32_t match[259];
+    uint32_t eob;
+    uint32_t hdr_bits;
+    uint32_t hdr[PNG_HDR_WORDS];
 };
 
 __host__ __device__ inline size_t png_piece_buf_bytes(int W, int ch)   // worst case of one piece, + tail, rounded to 16
 {
-    const size_t bits = (size_t)PNG_ROWS * (1 + (size_t)ch * W) * 9 + 64;
+    const size_t bits = (size_t)PNG_ROWS * (1 + (size_t)ch * W) * PNG_MAX_CODE_BITS + 64;     // every byte a literal of the longest code
     return ((bits + 7) / 8 + 8 + 15) & ~(size_t)15;
-}
-
-__device__ __forceinline__ uint32_t png_rev(uint32_t code, int nbits) { return __brev(code) >> (32 - nbits); }
-// fixed-Huffman literal: bits (already reversed for LSB-first packing) and length
-__device__ __forceinline__ void png_literal(uint32_t v, uint32_t &code, int &nbits)
-{
-    if (v < 144u) { code = png_rev(0x30u + v, 8); nbits = 8; }
-    else { code = png_rev(0x190u + (v - 144u), 9); nbits = 9; }
-}
-// match of `len` (3..258) at distance 1: length symbol + extra bits + 5-bit distance code 0
-__device__ __forceinline__ void png_match(uint32_t len, uint32_t &code, int &nbits)
-{
-    uint32_t sym, eb = 0, extra = 0;
-    if (len == 258u) sym = 285u;
-    else {
-        const uint32_t l = len - 3u;
-        if (l < 8u) sym = 257u + l;
-        else {
-            eb = (31u - (uint32_t)__clz(l)) - 2u;
-            sym = 257u + 4u * eb + 4u + ((l >> eb) & 3u);
-            extra = l & ((1u << eb) - 1u);
-        }
-    }
-    if (sym < 280u) { code = png_rev(sym - 256u, 7); nbits = 7; }
-    else { code = png_rev(0xc0u + (sym - 280u), 8); nbits = 8; }
-    code |= extra << nbits;
-    nbits += (int)eb;
-    nbits += 5;            // distance code 0 (distance 1): five zero bits
 }
 
 // single-walk sink: the lane's bits go to its own staging words; they are moved to the piece buffer once the warp scan has
 // placed them
-constexpr int PNG_STAGE_WORDS = 24;      // >= (64 * 9 + 8 + 8 * 13 + 18 + 31) / 32 bits a chunk can need
+constexpr int PNG_STAGE_WORDS = 28;      // >= (10 + 64 * 10 + 9 * 16 + 2 * 10 + 31) / 32 words of bits a chunk can need (PNG_MAX_CODE_BITS = 10)
+static_assert(PNG_MAX_CODE_BITS <= 10, "PNG_STAGE_WORDS is sized for codes of at most 10 bits");
 struct PngStage {
     uint32_t *stage;
     unsigned long long acc = 0;
@@ -116,20 +101,10 @@ struct PngLut {
     uint32_t lit[256];      // literal byte
     uint32_t match[259];    // match of length 3..258 at distance 1
 };
-__device__ __forceinline__ void png_fill_lut(PngLut &T)
+__device__ __forceinline__ void png_fill_lut(PngLut &T, const PngTables *tab)
 {
-    for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) {
-        uint32_t code;
-        int nb;
-        png_literal(i, code, nb);
-        T.lit[i] = code | ((uint32_t)nb << 24);
-    }
-    for (uint32_t i = 3u + threadIdx.x; i <= 258u; i += blockDim.x) {
-        uint32_t code;
-        int nb;
-        png_match(i, code, nb);
-        T.match[i] = code | ((uint32_t)nb << 24);
-    }
+    for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) T.lit[i] = tab->lit[i];
+    for (uint32_t i = 3u + threadIdx.x; i <= 258u; i += blockDim.x) T.match[i] = tab->match[i];
 }
 // r zeros whose predecessor in the stream is a zero byte
 template <class Sink>
@@ -138,7 +113,7 @@ __device__ __forceinline__ void png_zero_matches(Sink &s, uint32_t r, const PngL
     const uint32_t full = T.match[258];
     while (r >= 258u) { s.put(full & 0xffffffu, (int)(full >> 24)); r -= 258u; }
     if (r >= 3u) { const uint32_t t = T.match[r]; s.put(t & 0xffffffu, (int)(t >> 24)); r = 0; }
-    while (r) { s.put(T.lit[0] & 0xffffffu, 8); r--; }
+    while (r) { s.put(T.lit[0] & 0xffffffu, (int)(T.lit[0] >> 24)); r--; }
 }
 // The tokens of one lane's chunk.  nz: bit i set = filtered byte i is non-zero; fb: the chunk's filtered bytes (shared memory);
 // skip: leading zeros that belong to a run an earlier lane emits; tail_extra: zeros after this chunk that continue its trailing
@@ -147,13 +122,13 @@ template <int CHUNK, class Sink>
 __device__ __forceinline__ void png_chunk_tokens(Sink &s, unsigned long long nz, const uint8_t *fb, int skip, uint32_t tail_extra, bool filter_byte,
                                                  const PngLut &T)
 {
-    if (filter_byte) s.put(T.lit[1] & 0xffffffu, 8);          // filter type 1 (Sub) opens the row
+    if (filter_byte) s.put(T.lit[1] & 0xffffffu, (int)(T.lit[1] >> 24));          // filter type 1 (Sub) opens the row
     int pos = skip;
     while (pos < CHUNK) {
         const unsigned long long rem = nz >> pos;
         if (rem & 1ull) {
             const uint32_t t = T.lit[fb[pos]];
-            if ((rem & 2ull) && pos + 1 < CHUNK) {             // two literals in one go (at most 18 bits)
+            if ((rem & 2ull) && pos + 1 < CHUNK) {             // two literals in one go (at most 30 bits)
                 const uint32_t u = T.lit[fb[pos + 1]];
                 s.put((t & 0xffffffu) | ((u & 0xffffffu) << (t >> 24)), (int)((t >> 24) + (u >> 24)));
                 pos += 2;
@@ -163,14 +138,14 @@ __device__ __forceinline__ void png_chunk_tokens(Sink &s, unsigned long long nz,
             }
         } else if ((rem & 6ull) != 0ull) {                     // one or two zeros between literals (the alpha delta of an RGBA
             const int gap = (rem & 2ull) ? 1 : 2;              // pixel): too short for a match, literal zeros
-            const uint32_t z = T.lit[0] & 0xffffffu;
-            s.put(gap == 2 ? (z | (z << 8)) : z, 8 * gap);
+            const uint32_t z = T.lit[0] & 0xffffffu, zb = T.lit[0] >> 24;
+            s.put(gap == 2 ? (z | (z << zb)) : z, (int)(zb * gap));
             pos += gap;
         } else {
             const int gap = rem ? (__ffsll((long long)rem) - 1) : (CHUNK - pos);
             uint32_t r = (uint32_t)gap;
             if (!rem) r += tail_extra;
-            s.put(T.lit[0] & 0xffffffu, 8);                    // the run's first zero is a literal
+            s.put(T.lit[0] & 0xffffffu, (int)(T.lit[0] >> 24));                    // the run's first zero is a literal
             png_zero_matches(s, r - 1u, T);
             pos += gap;
         }
@@ -185,13 +160,14 @@ struct PngParams {
     uint8_t *scratch;               // [n * pieces_per_image * PNG_SLOT][overflow arena]
     unsigned long long over_begin, over_cap;
     unsigned long long *counters;   // [0] overflow arena cursor, [1] error flag, [2] next unclaimed piece
+    const PngTables *tables;
     const uint8_t *blank;           // optional hint, [n][blank_bands]: 1 = rows [b * blank_rows, (b + 1) * blank_rows) are all white
     int blank_rows;
     uint32_t blank_bands;
 };
 
 // shared memory per warp: bit buffer + 32 chunks of filtered bytes + staging words + the bits of an all-white row
-__host__ __device__ inline size_t png_warp_smem(int W, int ch) { return png_piece_buf_bytes(W, ch) + 32 * PNG_CHUNK_PX * ch + 32 * 4 * PNG_STAGE_WORDS + 32; }
+__host__ __device__ inline size_t png_warp_smem(int W, int ch) { return png_piece_buf_bytes(W, ch) + 32 * PNG_CHUNK_PX * ch + 32 * 4 * PNG_STAGE_WORDS + 64; }
 
 // ORs the nbits bits that start at bit src_start of src into dst at bit dst_pos (dst is zero there); lanes share the words
 __device__ __forceinline__ void png_copy_bits(uint32_t *dst, uint32_t dst_pos, const uint32_t *src, uint32_t src_start, uint32_t nbits, int lane)
@@ -215,7 +191,7 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
     constexpr int CHUNK = PNG_CHUNK_PX * CH, FW = CHUNK / 4;      // filtered bytes / words per lane chunk
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ PngLut lut;
-    png_fill_lut(lut);
+    png_fill_lut(lut, P.tables);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = png_warp_smem(P.W, CH), bufb = png_piece_buf_bytes(P.W, CH);
@@ -229,7 +205,7 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
     const bool one_pass = chunks <= 32;        // rows of up to 512 pixels: a row that repeats the row above copies its bits
     // the bits of an all-white row (what most rows of this data set are): the virtual "row above" of every piece
     uint32_t white_bits = 0;
-    if (lane < 8) wrow[lane] = 0u;
+    if (lane < 16) wrow[lane] = 0u;
     for (uint32_t i = lane; i < buf_words; i += 32) buf[i] = 0u;
     __syncwarp();
     if (one_pass) {
@@ -237,12 +213,9 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
             PngEmit em;
             em.buf = wrow;
             em.pos = 0;
-            uint32_t code;
-            int nb;
-            em.put(png_rev(0x30u + 1u, 8), 8);
-            png_literal(255u, code, nb);
-            for (int q = 0; q < CH; q++) em.put(code, nb);
-            em.put(png_rev(0x30u, 8), 8);
+            em.put(lut.lit[1] & 0xffffffu, (int)(lut.lit[1] >> 24));
+            for (int q = 0; q < CH; q++) em.put(lut.lit[255] & 0xffffffu, (int)(lut.lit[255] >> 24));
+            em.put(lut.lit[0] & 0xffffffu, (int)(lut.lit[0] >> 24));
             png_zero_matches(em, RL - 1u - (uint32_t)CH - 1u, lut);
             white_bits = em.pos;
         }
@@ -251,8 +224,8 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
     __syncwarp();
     const unsigned long long total_pieces = (unsigned long long)P.n * P.pieces_per_image;
     uint32_t used_words = 0;                   // words of buf the previous piece dirtied
-    PngPiece canned;                           // this warp's first blank piece (nbytes 0: none yet)
-    canned.nbytes = 0u; canned.where = 0u; canned.a = 0u; canned.b = 0u;
+    PngPiece canned;                           // this warp's first blank piece (nbits 0: none yet)
+    canned.nbits = 0u; canned.where = 0u; canned.a = 0u; canned.b = 0u;
     // pieces are claimed a few at a time from a global cursor: blank pieces cost a fraction of drawn ones, and CTAs that become
     // resident late (behind a k_figure launch on another stream) must not be left with a full static share
     for (;;) {
@@ -278,7 +251,7 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
                 if (P.blank_rows == PNG_ROWS) hinted = __ldg(fl + piece) != 0;          // the renderer's bands are the pieces
                 else hinted = (__ldg(fl + y0 / P.blank_rows) & __ldg(fl + (y1 - 1) / P.blank_rows)) != 0;
             }
-            if (!hinted || !canned.nbytes)       // (the copy every other blank piece will point at is made from pixels that were read)
+            if (!hinted || !canned.nbits)       // (the copy every other blank piece will point at is made from pixels that were read)
             for (int y = y0; y < y1; y++)
                 for (int c = lane; c < chunks; c += 32) {
                     const uint4 *src = (const uint4 *)(img + (size_t)y * row_bytes + (size_t)c * 48);
@@ -286,15 +259,14 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
                     acc &= a.x & a.y & a.z & a.w & b.x & b.y & b.z & b.w & d.x & d.y & d.z & d.w;
                 }
             blank = __all_sync(0xffffffffu, acc == 0xffffffffu);
-            if (blank && canned.nbytes) {
+            if (blank && canned.nbits) {
                 if (lane == 0) P.pieces[gp] = canned;
                 continue;
             }
         }
         for (uint32_t i = lane; i < used_words; i += 32) buf[i] = 0u;
         __syncwarp();
-        uint32_t bitpos = 3;
-        if (lane == 0) buf[0] = 2u;          // BFINAL = 0, BTYPE = 01 (fixed Huffman), LSB first
+        uint32_t bitpos = 0;
         unsigned long long ad_a = 0, ad_b = 0;
         // the row above, as this lane saw it: raw words, Adler sums of its filtered chunk, where its bits are
         uint32_t pw[12];
@@ -449,25 +421,15 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
                 bitpos += __shfl_sync(0xffffffffu, incl, 31);
                 __syncwarp();
             }
-            if (one_pass && p_start != row_start) {    // (a copied row has already moved the reference to itself)
+            if (one_pass) {                             // the next row's "row above" (a copied row already points at itself)
                 p_src = buf;
                 p_start = row_start;
                 p_bits = bitpos - row_start;
-            } else if (one_pass) {
-                p_bits = bitpos - row_start;
             }
         }
-        // end of block (7 zero bits), empty stored block (3 zero bits, pad to a byte, 00 00 FF FF)
-        bitpos += 10;
-        bitpos = (bitpos + 7u) & ~7u;
+        // the piece is a bare bit string: k_png_assemble puts it behind its predecessor and closes the block after the last one
         __syncwarp();
-        if (lane == 0) {
-            PngEmit em;
-            em.buf = buf;
-            em.pos = bitpos + 16;
-            em.put(0xffffu, 16);
-        }
-        const uint32_t nbytes = bitpos / 8 + 4;
+        const uint32_t nbits = bitpos, nbytes = (nbits + 7u) / 8u;
         used_words = (nbytes + 3u) / 4u + 2u;
         // Adler partial sums of the piece
 #pragma unroll
@@ -481,7 +443,7 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
             unsigned long long off = 0;
             if (lane == 0) off = atomicAdd(P.counters, (unsigned long long)((nbytes + 15u) & ~15u));
             off = __shfl_sync(0xffffffffu, off, 0);
-            if (off + nbytes > P.over_cap) {
+            if (off + nbytes + 16u > P.over_cap) {
                 failed = true;
                 if (lane == 0) atomicExch(P.counters + 1, 1ull);
             }
@@ -495,14 +457,14 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
         }
         if (lane == 0) {
             PngPiece pc;
-            pc.nbytes = failed ? 0u : nbytes;
+            pc.nbits = failed ? 0u : nbits;
             pc.where = failed ? 0u : (uint32_t)(where / 16);      // scratch offsets are multiples of 16
             pc.a = (uint32_t)(ad_a % ADLER_MOD);
             pc.b = (uint32_t)(ad_b % ADLER_MOD);
             P.pieces[gp] = pc;
         }
         if (blank && !failed && nbytes <= PNG_SLOT) {
-            canned.nbytes = nbytes;
+            canned.nbits = nbits;
             canned.where = (uint32_t)(where / 16);
             canned.a = (uint32_t)(ad_a % ADLER_MOD);
             canned.b = (uint32_t)(ad_b % ADLER_MOD);
@@ -512,15 +474,22 @@ __global__ void __launch_bounds__(256) k_png_pieces(const PngParams P)
     }
 }
 
-__global__ void k_png_sizes(const PngPiece *__restrict__ pieces, int n, uint32_t ppi, unsigned long long *__restrict__ sizes)
+// bytes of the deflate stream of an image: block header, the pieces' bits, end of block, padded to a byte
+__host__ __device__ inline unsigned long long png_deflate_bytes(unsigned long long piece_bits, uint32_t hdr_bits, uint32_t eob_bits)
+{
+    return (piece_bits + hdr_bits + eob_bits + 7ull) / 8ull;
+}
+
+__global__ void k_png_sizes(const PngPiece *__restrict__ pieces, int n, uint32_t ppi, const PngTables *__restrict__ tables,
+                            unsigned long long *__restrict__ sizes)
 {
     const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (img >= n) return;
     unsigned long long s = 0;
-    for (uint32_t p = lane; p < ppi; p += 32) s += pieces[(size_t)img * ppi + p].nbytes;
+    for (uint32_t p = lane; p < ppi; p += 32) s += pieces[(size_t)img * ppi + p].nbits;
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) sizes[img] = s + PNG_FILE_OVERHEAD;
+    if (lane == 0) sizes[img] = png_deflate_bytes(s, tables->hdr_bits, tables->eob >> 24) + PNG_FILE_OVERHEAD;
 }
 
 // exclusive prefix sum of sizes[0..n) into offsets[0..n]; one CTA of 1024 threads
@@ -587,49 +556,62 @@ __device__ __forceinline__ void put_be32(uint8_t *p, uint32_t v)
     p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v;
 }
 
+// dynamic shared memory: per warp, (pieces_per_image + 1) bit offsets and pieces_per_image scratch positions
+__host__ __device__ inline size_t png_assemble_smem(uint32_t ppi, int warps) { return (size_t)warps * (2 * (size_t)ppi + 1) * sizeof(uint32_t); }
+
 __global__ void __launch_bounds__(256) k_png_assemble(const PngAssembleParams P)
 {
     __shared__ uint32_t crc_t[256];
     __shared__ uint32_t x2n[32];
+    extern __shared__ uint32_t asm_smem[];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) crc_t[i] = P.tables->crc[i];
     if (threadIdx.x < 32) x2n[threadIdx.x] = P.tables->x2n[threadIdx.x];
     __syncthreads();
-    const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, img = blockIdx.x * (blockDim.x >> 5) + warp, lane = threadIdx.x & 31;
     if (img >= P.n) return;
     const uint32_t ppi = P.pieces_per_image;
+    uint32_t *pre = asm_smem + (size_t)warp * (2 * (size_t)ppi + 1);      // pre[p]: bits of the pieces before p; pre[ppi]: all
+    uint32_t *where = pre + ppi + 1;
     const PngPiece *pcs = P.pieces + (size_t)img * ppi;
     uint8_t *file = P.out + P.offsets[img];
     const unsigned long long total = P.offsets[img + 1] - P.offsets[img];
-    const uint32_t data_len = (uint32_t)(total - PNG_FILE_OVERHEAD) + 8u;       // zlib header + pieces + final block + Adler
+    const uint32_t deflate_bytes = (uint32_t)(total - PNG_FILE_OVERHEAD);
+    const uint32_t data_len = deflate_bytes + 6u;                               // zlib header + deflate stream + Adler
     const uint32_t RL = 1u + (uint32_t)(P.ch * P.W);
     const unsigned long long ulen = (unsigned long long)P.H * RL;               // uncompressed (filtered) bytes
-    // lane l owns pieces [l * ppl, (l + 1) * ppl): a contiguous segment of the file
-    const uint32_t ppl = (ppi + 31u) / 32u;
-    const uint32_t p0 = min(ppi, (uint32_t)lane * ppl), p1 = min(ppi, p0 + ppl);
-    unsigned long long seg_bytes = 0, sa = 0, sb = 0;
-    for (uint32_t p = p0; p < p1; p++) {
-        const PngPiece pc = pcs[p];
-        seg_bytes += pc.nbytes;
-        const unsigned long long rows_before = (unsigned long long)p * PNG_ROWS, rows_p = min((unsigned long long)PNG_ROWS, (unsigned long long)P.H - rows_before);
-        const unsigned long long after = ulen - (rows_before + rows_p) * RL;
-        sa += pc.a;
-        sb += pc.b + (unsigned long long)pc.a * (after % ADLER_MOD);
-        sb %= ADLER_MOD;
-    }
-    // offsets of the segments, Adler-32 of the whole stream
-    unsigned long long incl = seg_bytes;
+    // ---- bit offsets of the pieces, Adler-32 of the whole stream (from the pieces' partial sums)
+    unsigned long long sa = 0, sb = 0;
+    uint32_t run = 0;
+    for (uint32_t base = 0; base < ppi; base += 32u) {
+        const uint32_t p = base + (uint32_t)lane;
+        PngPiece pc;
+        pc.nbits = 0; pc.where = 0; pc.a = 0; pc.b = 0;
+        if (p < ppi) {
+            pc = pcs[p];
+            const unsigned long long rows_before = (unsigned long long)p * PNG_ROWS, rows_p = min((unsigned long long)PNG_ROWS, (unsigned long long)P.H - rows_before);
+            const unsigned long long after = ulen - (rows_before + rows_p) * RL;
+            sa += pc.a;
+            sb += pc.b + (unsigned long long)pc.a * (after % ADLER_MOD);
+            sb %= ADLER_MOD;
+        }
+        uint32_t incl = pc.nbits;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (p < ppi) { pre[p] = run + incl - pc.nbits; where[p] = pc.where; }
+        run += __shfl_sync(0xffffffffu, incl, 31);
     }
+    if (lane == 0) pre[ppi] = run;
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         sa += __shfl_xor_sync(0xffffffffu, sa, o);
         sb += __shfl_xor_sync(0xffffffffu, sb, o);
     }
     const uint32_t adler = ((uint32_t)((ulen + sb) % ADLER_MOD) << 16) | (uint32_t)((1ull + sa) % ADLER_MOD);
-    // fixed parts
+    __syncwarp();
+    // ---- fixed parts
     for (int i = lane; i < 33; i += 32) file[i] = P.tables->header[i];
     uint8_t *idat = file + 33;
     if (lane == 0) {
@@ -637,38 +619,61 @@ __global__ void __launch_bounds__(256) k_png_assemble(const PngAssembleParams P)
         idat[4] = 'I'; idat[5] = 'D'; idat[6] = 'A'; idat[7] = 'T';
         idat[8] = 0x78; idat[9] = 0x01;
     }
-    uint8_t *body = idat + 10;                                   // first piece byte
-    const unsigned long long pieces_total = __shfl_sync(0xffffffffu, incl, 31);
-    uint8_t *tail = body + pieces_total;
+    uint8_t *body = idat + 10;                                   // first byte of the deflate stream
+    uint8_t *tail = body + deflate_bytes;
     if (lane == 31) {
-        tail[0] = 0x03; tail[1] = 0x00;                           // final block: fixed Huffman, immediately end of block
-        put_be32(tail + 2, adler);
+        put_be32(tail, adler);
         const uint8_t iend[12] = {0, 0, 0, 0, 'I', 'E', 'N', 'D', 0xae, 0x42, 0x60, 0x82};
-        for (int i = 0; i < 12; i++) tail[10 + i] = iend[i];
+        for (int i = 0; i < 12; i++) tail[8 + i] = iend[i];
     }
-    // ---- pass 1: the pieces, copied cooperatively (consecutive lanes write consecutive bytes of the file)
+    // ---- pass 1: the deflate stream, 32 bits per lane and step: [block header][piece 0][piece 1] ... [end of block][padding]
     {
-        unsigned long long run = 0;                          // bytes of the pieces before this group of 32
-        for (uint32_t base = 0; base < ppi; base += 32u) {
-            const uint32_t p = base + (uint32_t)lane;
-            PngPiece pc;
-            pc.nbytes = 0; pc.where = 0; pc.a = 0; pc.b = 0;
-            if (p < ppi) pc = pcs[p];
-            uint32_t pre = pc.nbytes;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
-                if (lane >= o) pre += t;
+        const uint32_t H0 = P.tables->hdr_bits, PB = run, eob = P.tables->eob & 0xffffffu, eob_bits = P.tables->eob >> 24;
+        const uint32_t n_words = (deflate_bytes + 3u) / 4u;
+        uint32_t p = 0;                                           // a piece at or before the lane's position (positions only grow)
+        for (uint32_t k = (uint32_t)lane; k < n_words; k += 32u) {
+            const uint32_t b0 = 32u * k;
+            uint32_t word = 0u;
+            if (b0 < H0) word = P.tables->hdr[k];                 // (the words behind the header's last bit are zero-padded)
+            uint32_t lo = (b0 > H0 ? b0 : H0) - H0;               // in piece space: bit 0 = first bit of piece 0
+            const uint32_t hi_abs = b0 + 32u < H0 + PB ? b0 + 32u : H0 + PB;
+            if (hi_abs > H0 && lo < hi_abs - H0) {
+                const uint32_t hi = hi_abs - H0;
+                // largest p with pre[p] <= lo
+                {
+                    uint32_t a = p, b = ppi;                      // pre[a] <= lo < pre[b] = PB ... find by bisection
+                    while (b - a > 1u) {
+                        const uint32_t m = (a + b) >> 1;
+                        if (pre[m] <= lo) a = m; else b = m;
+                    }
+                    p = a;
+                }
+                uint32_t q = p;
+                while (lo < hi) {
+                    const uint32_t pe = pre[q + 1];
+                    if (pe <= lo) { q++; continue; }              // (an empty piece)
+                    const uint32_t take = (hi < pe ? hi : pe) - lo;
+                    const uint32_t sbit = lo - pre[q];
+                    const uint32_t *src = (const uint32_t *)(P.scratch + (size_t)where[q] * 16);
+                    const uint32_t sw = sbit >> 5, ss = sbit & 31u;
+                    uint32_t v = __funnelshift_r(src[sw], src[sw + 1], ss);
+                    if (take < 32u) v &= (1u << take) - 1u;
+                    word |= v << (lo + H0 - b0);
+                    lo += take;
+                }
             }
-            const uint32_t cnt = min(32u, ppi - base);
-            for (uint32_t j = 0; j < cnt; j++) {
-                const uint32_t nb = __shfl_sync(0xffffffffu, pc.nbytes, (int)j), wh = __shfl_sync(0xffffffffu, pc.where, (int)j);
-                const uint32_t off = __shfl_sync(0xffffffffu, pre, (int)j) - nb;
-                const uint8_t *src = P.scratch + (size_t)wh * 16;
-                uint8_t *dst = body + run + off;
-                for (uint32_t i = (uint32_t)lane; i < nb; i += 32u) dst[i] = src[i];
+            // end of block
+            {
+                const uint32_t e0 = H0 + PB;
+                if (e0 >= b0 && e0 < b0 + 32u) word |= eob << (e0 - b0);
+                else if (e0 < b0 && e0 + eob_bits > b0) word |= eob >> (b0 - e0);
             }
-            run += __shfl_sync(0xffffffffu, pre, 31);
+            uint8_t *dst = body + 4u * k;
+            const uint32_t left = deflate_bytes - 4u * k;
+            dst[0] = (uint8_t)word;
+            if (left > 1u) dst[1] = (uint8_t)(word >> 8);
+            if (left > 2u) dst[2] = (uint8_t)(word >> 16);
+            if (left > 3u) dst[3] = (uint8_t)(word >> 24);
         }
     }
     __syncwarp();
@@ -688,7 +693,7 @@ __global__ void __launch_bounds__(256) k_png_assemble(const PngAssembleParams P)
         if ((lane & (2 * o - 1)) == 0) crc = crc_multmodp(xpow, crc) ^ rc;
         xpow = crc_multmodp(xpow, xpow);
     }
-    if (lane == 0) put_be32(tail + 6, crc);
+    if (lane == 0) put_be32(tail + 4, crc);
 }
 
 }  // namespace rig

@@ -33,6 +33,7 @@ struct rig_png_ctx {
     int device = 0, W = 0, H = 0, max_images = 0, ch = 3;
     uint32_t ppi = 0;
     int wpc = 4, sm_count = 1, ctas_per_sm = 1;
+    int asm_warps = 8;                 // warps (= files) per CTA of k_png_assemble
     size_t smem = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_asm = nullptr;
@@ -83,9 +84,9 @@ const char *rig_png_last_error(const rig_png_ctx *ctx) { return ctx ? ctx->err :
 size_t rig_png_bound(const rig_png_ctx *c, int n)
 {
     if (!c || n <= 0) return 0;
-    // literal-only worst case: 9 bits per filtered byte, plus per-piece and per-file framing
-    const size_t per_piece = ((size_t)PNG_ROWS * (1 + (size_t)c->ch * c->W) * 9 + 7) / 8 + 8;
-    return (size_t)n * ((size_t)c->ppi * per_piece + PNG_FILE_OVERHEAD);
+    // literal-only worst case: the longest code per filtered byte, plus the block header and the file framing
+    const size_t bits = (size_t)c->H * (1 + (size_t)c->ch * c->W) * PNG_MAX_CODE_BITS + PNG_HDR_WORDS * 32 + 15;
+    return (size_t)n * ((bits + 7) / 8 + PNG_FILE_OVERHEAD);
 }
 
 // cores this process may run on (its affinity mask: what a container's cpuset or taskset leaves), else the machine's
@@ -202,6 +203,22 @@ int rig_png_create(int device, int W, int H, int max_images, int channels, rig_p
         crc ^= 0xffffffffu;
         h[21] = (uint8_t)(crc >> 24); h[22] = (uint8_t)(crc >> 16); h[23] = (uint8_t)(crc >> 8); h[24] = (uint8_t)crc;
     }
+    {
+        PngCode code;
+        if (!png_build_code(channels, code)) {
+            pfail(c, RIG_E_UNSUPPORTED, "internal: the Huffman code description does not fit the header area");
+            return bail(RIG_E_UNSUPPORTED);
+        }
+        for (uint32_t v = 0; v < 256; v++) T.lit[v] = png_lut_literal(code, v);
+        T.match[0] = T.match[1] = T.match[2] = 0;
+        for (uint32_t l = 3; l <= 258; l++) T.match[l] = png_lut_match(code, l);
+        T.eob = png_lut_literal(code, 256);
+        T.hdr_bits = code.hdr_bits;
+        memcpy(T.hdr, code.hdr, sizeof T.hdr);
+    }
+    while (c->asm_warps > 1 && png_assemble_smem(c->ppi, c->asm_warps) + 2048 > prop.sharedMemPerBlockOptin) c->asm_warps /= 2;
+    if (png_assemble_smem(c->ppi, c->asm_warps) > 40 * 1024)
+        PCKC(cudaFuncSetAttribute(k_png_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)png_assemble_smem(c->ppi, c->asm_warps)));
     PCKC(cudaMalloc(&c->d_tables, sizeof T));
     PCKC(cudaMemcpy(c->d_tables, &T, sizeof T, cudaMemcpyHostToDevice));
     const size_t npieces = (size_t)max_images * c->ppi;
@@ -255,6 +272,7 @@ static int png_run_pieces(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int la
     P.imgs = imgs_dev; P.n = n; P.W = c->W; P.H = c->H; P.bgr = layout == RIG_LAYOUT_BGR;
     P.pieces_per_image = c->ppi; P.pieces = c->d_pieces; P.scratch = c->d_scratch;
     P.over_begin = c->over_begin; P.over_cap = c->scratch_bytes - c->over_begin; P.counters = c->d_counters;
+    P.tables = c->d_tables;
     P.blank = hint; P.blank_rows = hint_rows; P.blank_bands = hint ? (uint32_t)((c->H + hint_rows - 1) / hint_rows) : 0u;
     const unsigned long long npieces = (unsigned long long)n * c->ppi;
     {
@@ -264,7 +282,7 @@ static int png_run_pieces(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int la
         if (c->ch == 3) k_png_pieces<3><<<grid, c->wpc * 32, c->smem, st>>>(P);
         else k_png_pieces<4><<<grid, c->wpc * 32, c->smem, st>>>(P);
     }
-    k_png_sizes<<<(n + 7) / 8, 256, 0, st>>>(c->d_pieces, n, c->ppi, c->d_sizes);
+    k_png_sizes<<<(n + 7) / 8, 256, 0, st>>>(c->d_pieces, n, c->ppi, c->d_tables, c->d_sizes);
     k_png_scan<<<1, 1024, 0, st>>>(c->d_sizes, n, c->d_offsets);
     c->stats.kernel_launches += 3;
     PCK(c, cudaGetLastError());
@@ -287,7 +305,7 @@ static int png_run_assemble(rig_png_ctx *c, int n, uint8_t *dev_out, int slot)
     PngAssembleParams A;
     A.pieces = c->d_pieces; A.scratch = c->d_scratch; A.offsets = c->d_offsets; A.tables = c->d_tables; A.out = dev_out;
     A.n = n; A.W = c->W; A.H = c->H; A.ch = c->ch; A.pieces_per_image = c->ppi;
-    k_png_assemble<<<(n + 7) / 8, 256, 0, c->stream>>>(A);
+    k_png_assemble<<<(n + c->asm_warps - 1) / c->asm_warps, c->asm_warps * 32, png_assemble_smem(c->ppi, c->asm_warps), c->stream>>>(A);
     c->stats.kernel_launches++;
     PCK(c, cudaGetLastError());
     if (c->profiling) PCK(c, cudaEventRecord(c->ev1[slot], c->stream));
@@ -432,6 +450,21 @@ int rig_png_staging(rig_png_ctx *c, int n, uint8_t **out_dev)
         c->stage_cap = need;
     }
     *out_dev = c->d_stage;
+    return RIG_OK;
+}
+
+int rig_png_debug_code(int channels, uint8_t *len_out, uint32_t *hdr_out, uint32_t *hdr_bits_out, uint32_t *lut_out)
+{
+    if (!len_out || !hdr_out || !hdr_bits_out || !lut_out || (channels != 3 && channels != 4)) return RIG_E_INVALID;
+    PngCode code;
+    if (!png_build_code(channels, code)) return RIG_E_UNSUPPORTED;
+    memcpy(len_out, code.len, PNG_NLIT);
+    memcpy(hdr_out, code.hdr, sizeof code.hdr);
+    *hdr_bits_out = code.hdr_bits;
+    for (uint32_t v = 0; v < 256; v++) lut_out[v] = png_lut_literal(code, v);
+    lut_out[256] = lut_out[257] = lut_out[258] = 0;
+    for (uint32_t l = 3; l <= 258; l++) lut_out[256 + l] = png_lut_match(code, l);
+    lut_out[256 + 259] = png_lut_literal(code, 256);
     return RIG_OK;
 }
 

@@ -328,7 +328,7 @@ class FigureRenderer:
 
     def blank_bands(self):
         """(device pointer, rows per band) of the blank-band flags k_figure wrote during the last render into device memory: one byte
-        per band and image, 1 = only background pixels (rig_figure_blank_bands).  Valid until the second next render; (0, rows)
+        per band and image, 1 = only background pixels (rig_figure_blank_bands).  Valid until the fourth next render; (0, rows)
         unless `set_blank_flags(True)` was in force."""
         p, rows = ctypes.c_void_p(), ctypes.c_int()
         self._check(self._lib.rig_figure_blank_bands(self._h, ctypes.byref(p), ctypes.byref(rows)))

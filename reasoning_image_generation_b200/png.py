@@ -27,7 +27,7 @@ class RigPngStats(ctypes.Structure):
 
 PNG_EXPORTS = ('rig_png_create', 'rig_png_destroy', 'rig_png_last_error', 'rig_png_bound', 'rig_png_encode', 'rig_png_get_stats',
                'rig_png_set_profiling', 'rig_png_staging', 'rig_png_wait_event', 'rig_png_encode_begin', 'rig_png_encode_end',
-               'rig_png_set_blank_hint')
+               'rig_png_set_blank_hint', 'rig_png_debug_code')
 
 _bound = False
 _LAYOUTS = {'rgb': _abi.RIG_LAYOUT_RGB, 'bgr': _abi.RIG_LAYOUT_BGR}
@@ -197,7 +197,10 @@ def pipelined_png(encoder: 'PngEncoder', ranges: Sequence[Tuple[int, int]], chun
     if not starts:
         return
     two = overlap and len(starts) > 1
-    base = encoder.staging(2 * chunk if two else chunk)
+    # staging slots the worker may render into: with three, the render of chunk k + 2 is queued on the GPU while chunk k + 1 is
+    # being encoded, so a slow host wake-up (many ranks on one box) leaves no hole in the GPU's queue
+    n_slots = 3 if len(starts) > 2 else 2
+    base = encoder.staging(n_slots * chunk if two else chunk)
     if not two:
         for i0, i1 in starts:
             n_img, ev, *hint = render_chunk(i0, i1, base)
@@ -208,7 +211,7 @@ def pipelined_png(encoder: 'PngEncoder', ranges: Sequence[Tuple[int, int]], chun
             buf, off = encoder.encode(base, n_img, layout, 0)
             yield i0, buf, off
         return
-    free = threading.Semaphore(2)            # staging halves the worker may render into
+    free = threading.Semaphore(n_slots)
     ready: 'queue.Queue' = queue.Queue()
     stop = threading.Event()
 
@@ -218,7 +221,7 @@ def pipelined_png(encoder: 'PngEncoder', ranges: Sequence[Tuple[int, int]], chun
                 free.acquire()
                 if stop.is_set():
                     return
-                ptr = base + (k & 1) * chunk * img_bytes
+                ptr = base + (k % n_slots) * chunk * img_bytes
                 n_img, ev, *hint = render_chunk(i0, i1, ptr)
                 ready.put((i0, n_img, ptr, ev, hint[0] if hint else None))
         except BaseException as e:                               # re-raised on the consumer's thread
@@ -256,8 +259,8 @@ def pipelined_png(encoder: 'PngEncoder', ranges: Sequence[Tuple[int, int]], chun
         stop.set()
         if pending is not None:                                  # closed early: retire the slot in flight
             encoder.encode_end(pending[1])
-        free.release()
-        free.release()
+        for _ in range(n_slots):
+            free.release()
         t.join()
 
 

@@ -45,7 +45,7 @@ def test_every_declared_png_symbol_is_exported(built):
     txt = open(os.path.join(ROOT, 'include', 'rig_png.h')).read()
     txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
     names = sorted(set(re.findall(r'\b(rig_png_[a-z_]+)\s*\(', txt)))
-    assert len(names) == 12
+    assert len(names) == 13
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(png.PNG_EXPORTS) == names

@@ -68,8 +68,8 @@ def test_chunks_come_back_in_order_with_two_slots(overlap):
     assert got == [(0, 16), (16, 16), (32, 16), (48, 16), (64, 6)]
     assert [r[:2] for r in rendered] == chunk_plan(70, 16)
     if overlap:
-        # the two halves of the staging buffer alternate, and a chunk is begun before the previous one is ended
-        assert [r[2] for r in rendered] == [(1 << 20) + (k & 1) * 16 * 100 for k in range(5)]
+        # the three staging slots take turns, and a chunk is begun before the previous one is ended
+        assert [r[2] for r in rendered] == [(1 << 20) + (k % 3) * 16 * 100 for k in range(5)]
         kinds = [e[0] for e in enc.log if e[0] in ('begin', 'end')]
         assert kinds == ['begin', 'begin', 'end', 'begin', 'end', 'begin', 'end', 'begin', 'end', 'end']
     assert not enc.busy
@@ -89,7 +89,7 @@ def test_closing_early_retires_the_slot_and_stops_the_worker():
     next(it)
     it.close()
     assert not enc.busy                       # the chunk whose copy was in flight has been ended
-    assert len(calls) <= 5                    # the worker ran at most two chunks ahead, then stopped
+    assert len(calls) <= 6                    # the worker ran at most three chunks ahead, then stopped
 
 
 def test_worker_errors_surface_on_the_consumer():

@@ -9,12 +9,20 @@ from reasoning_image_generation_b200.figure import FigureRenderer  # noqa: E402
 from reasoning_image_generation_b200.png import PngEncoder  # noqa: E402
 from reasoning_image_generation_b200.synth_figure import synthetic_figure_scene  # noqa: E402
 
+import os
+DEV = int(os.environ.get('LOCAL_RANK', '0')) if os.environ.get('E2E_USE_LOCAL_RANK') else 0
+if os.environ.get('E2E_DIST'):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(DEV)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', DEV))
+    dist.barrier()
 n, chunk = 32768, (int(sys.argv[2]) if len(sys.argv) > 2 else 4096)
 ch = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 assert n % chunk == 0, 'chunk must divide n (a worker exception would leave the main loop waiting)'
 sc = synthetic_figure_scene(n, 512, 512, seed=1, kind='single')
-r = FigureRenderer(512, 512, max_images=chunk)
-enc = PngEncoder(512, 512, max_images=chunk, channels=ch)
+r = FigureRenderer(512, 512, device=DEV, max_images=chunk)
+enc = PngEncoder(512, 512, device=DEV, max_images=chunk, channels=ch)
 img = 512 * 512 * 3
 base = enc.staging(2 * chunk)
 starts = list(range(0, n, chunk))
