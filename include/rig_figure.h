@@ -77,7 +77,8 @@ typedef struct rig_figure_scene {
 typedef struct rig_figure_ctx rig_figure_ctx;
 
 /* Context on CUDA device `device` for W x H figures (the canvas savefig paints opaque white first), at most max_images
- * images and max_artists artists per call.  W must be a multiple of 16 and W, H <= 2048.                              */
+ * images and max_artists artists per call.  W must be a multiple of 16 and W, H <= 3072 (the reference's default
+ * savefig, 8 in x 300 dpi, is 2400 x 2400).                              */
 int rig_figure_create(int device, int W, int H, int max_images, int max_artists, rig_figure_ctx **out);
 void rig_figure_destroy(rig_figure_ctx *ctx);
 const char *rig_figure_last_error(const rig_figure_ctx *ctx);

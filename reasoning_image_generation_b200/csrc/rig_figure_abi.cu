@@ -682,8 +682,10 @@ int rig_figure_create(int device, int W, int H, int max_images, int max_artists,
 {
     if (!out) return ffail(nullptr, RIG_E_INVALID, "out is NULL");
     *out = nullptr;
-    if (W <= 0 || H <= 0 || W % 16 || W > 2048 || H > 2048)
-        return ffail(nullptr, RIG_E_INVALID, "unsupported canvas %dx%d (W %% 16 == 0 so that rows are 16-byte aligned; <= 2048)", W, H);
+    // 3072: fig_edge_rows' closed-form DDA state stays inside 32 bits (rows * |dy| < 2^32); the reference's default savefig is
+    // 8 in x 300 dpi = 2400 x 2400 (multigraph_generation/config.py:25), its CLI's 8 in x 200 dpi = 1600 x 1600
+    if (W <= 0 || H <= 0 || W % 16 || W > 3072 || H > 3072)
+        return ffail(nullptr, RIG_E_INVALID, "unsupported canvas %dx%d (W %% 16 == 0 so that rows are 16-byte aligned; <= 3072)", W, H);
     if (max_images <= 0 || max_artists <= 0) return ffail(nullptr, RIG_E_INVALID, "max_images/max_artists must be positive");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);

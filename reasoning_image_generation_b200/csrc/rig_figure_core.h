@@ -8,7 +8,7 @@
 // commutative, so the GPU accumulates them with shared-memory atomics in any order; what must be reproduced exactly
 // is each edge's split into rows and cells.  Agg walks an edge row by row with a DDA; here the state of that DDA at
 // the first row of a band is computed in closed form (floor((p + j q) / dy) decomposed so that everything stays in
-// 32 bits for canvases up to 2048 x 2048), and from there the walk is Agg's own.
+// 32 bits for canvases up to 3072 x 3072), and from there the walk is Agg's own.
 //
 // The same code is compiled for the CPU by tests/cpu_emul/figure_emul.cpp and checked against oracle/aggdraw.c.
 #pragma once
@@ -126,7 +126,8 @@ RIG_HD void fig_edge_rows(const FEdge &e, int r0, int r1, Acc &acc)
     const int lift = fig_floordiv(q, ady), rem = q - lift * ady;
     int xfrom = x1, yfrom = fy1, m = mod0;
     if (ja > 0) {
-        // mod0, rem < |dy| < 2^19 and ja <= 2^11 (canvas <= 2048 rows): the sum stays below 2^31
+        // mod0, rem < |dy| <= 256 * rows and ja <= rows: for canvases of up to 3072 rows the sum stays below 3072 * 786 432 + 786 432
+        // = 2.42e9 < 2^32 (unsigned arithmetic)
         const uint32_t t = (uint32_t)mod0 + (uint32_t)(ja - 1) * (uint32_t)rem;
         const uint32_t qd = t / (uint32_t)ady;
         m = (int)(t - qd * (uint32_t)ady);

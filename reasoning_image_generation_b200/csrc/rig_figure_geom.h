@@ -59,7 +59,7 @@ RIG_HD int iround(double v) { return (int)((v < 0.0) ? v - 0.5 : v + 0.5); }
 
 // Tracks values that came out of atan2 / acos / cos / sin.  The host instance is empty (the host IS the definition).
 // Error model: both libms are within 2 ulp on these calls; the angles are < 8 in magnitude and go through at most a few
-// dozen additions, the products with the half width and the sums with a canvas coordinate (|v| <= 2048, ulp 4.5e-13) keep the
+// dozen additions, the products with the half width and the sums with a canvas coordinate (|v| <= 4096, ulp 9e-13) keep the
 // absolute error of a coordinate below 1e-11 px, i.e. 3e-9 after the multiplication by 256 that precedes the rounding.
 // A libm coordinate is either rounded directly (the segment lies inside the clip box) or feeds the clipper's intersection
 // formulas; the second case is not analysed: a pass that emitted a libm point AND clipped any segment is handed back.

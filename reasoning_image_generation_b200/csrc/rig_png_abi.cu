@@ -337,7 +337,11 @@ int rig_png_encode_begin(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int lay
     unsigned long long total = 0;
     rc = png_run_pieces(c, imgs_dev, n, layout, stream, slot, &total, hint, hint_rows);
     if (rc) return rc;
-    if (total > out_capacity) return pfail(c, RIG_E_CAPACITY, "the PNG files need %llu bytes, out_capacity is %zu", total, out_capacity);
+    if (total > out_capacity) {
+        c->hint = hint;                      // the caller retries with a larger buffer: the hint is still good for that call
+        c->hint_rows = hint_rows;
+        return pfail(c, RIG_E_CAPACITY, "the PNG files need %llu bytes, out_capacity is %zu", total, out_capacity);
+    }
     if (c->out_caps[slot] < total) {
         if (c->d_outs[slot]) PCK(c, cudaFree(c->d_outs[slot]));
         c->d_outs[slot] = nullptr;

@@ -88,6 +88,22 @@ class FigureScene:
                            self.clip[a0:a1], self.has_clip[a0:a1])
 
 
+_SCENE_ARRAYS = ('image_artist_begin', 'artist_vertex_begin', 'vertices', 'codes', 'affine', 'linewidth', 'cap', 'join', 'snap',
+                 'edge_rgba', 'face_rgba', 'has_face', 'clip', 'has_clip')
+
+
+def scene_to_arrays(scene: FigureScene, prefix: str = '') -> Dict[str, np.ndarray]:
+    """The scene as a flat dict of arrays (np.savez-able; `scene_from_arrays` is the inverse)."""
+    d = {prefix + k: getattr(scene, k) for k in _SCENE_ARRAYS}
+    d[prefix + 'WH'] = np.array([scene.W, scene.H], dtype=np.int64)
+    return d
+
+
+def scene_from_arrays(d, prefix: str = '') -> FigureScene:
+    W, H = (int(v) for v in d[prefix + 'WH'])
+    return FigureScene(W, H, *[d[prefix + k] for k in _SCENE_ARRAYS])
+
+
 class FigureSceneBuilder:
     """Collects figures artist by artist, in draw order (matplotlib: sorted by zorder, then insertion)."""
 

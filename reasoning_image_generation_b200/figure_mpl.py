@@ -63,25 +63,57 @@ def _line_artist(l: Line2D) -> Dict[str, Any]:
                 snap=_snap(l), edgecolor=rgba, facecolor=None, clip=_clip(l, l.figure.bbox.height))
 
 
+def _drawn_children(ax):
+    """The artists Axes.draw would draw, in its order: children in insertion order, stably sorted by zorder.  With
+    ``ax.axis('off')`` (the reference: multigraph_generation/generator.py:490) the axes background, the spines, the two Axis
+    objects and the (empty) title texts are not drawn; anything else this walker cannot express raises."""
+    from matplotlib.axis import Axis
+    from matplotlib.spines import Spine
+    from matplotlib.text import Text
+    if ax.axison:
+        raise NotImplementedError('axes frame / ticks / background are not extracted (the reference calls ax.axis("off"))')
+    out = []
+    for a in ax.get_children():
+        if not a.get_visible():
+            continue
+        if a is ax.patch or isinstance(a, (Spine, Axis)):
+            continue                                           # not drawn when the axes are off
+        if isinstance(a, Text):
+            if a.get_text() == '':
+                continue                                       # the three title slots
+            raise NotImplementedError('text artists are not extracted')
+        if not isinstance(a, (Line2D, Patch)):
+            raise NotImplementedError(f'{type(a).__name__} artists are not extracted (collections, images, legends, ...)')
+        cp = a.get_clip_path()
+        if cp is not None:
+            raise NotImplementedError('clip paths other than the axes rectangle are not extracted')
+        out.append(a)
+    out.sort(key=lambda a: a.get_zorder())                     # stable: insertion order within a zorder
+    return out
+
+
 def extract_figure(fig, dpi: float | None = None) -> List[Dict[str, Any]]:
-    """The draw_path argument lists of every visible patch and solid line of `fig`, in draw order.  Text, images, markers,
-    dashed lines and hatches are outside what the reference's generator produces and raise NotImplementedError."""
+    """The draw_path argument lists of every visible patch and solid line of `fig`, in draw order.  Text, images, collections,
+    markers, dashed lines, hatches and non-rectangular clip paths are outside what the reference's generator produces and raise
+    NotImplementedError."""
     if dpi is not None:
         fig.set_dpi(dpi)
-    fig.canvas.draw_idle() if False else None
+    if fig.patch.get_visible():
+        fc = fig.patch.get_facecolor()
+        if tuple(round(float(c), 6) for c in fc) != (1.0, 1.0, 1.0, 1.0):
+            raise NotImplementedError('figure backgrounds other than opaque white (savefig\'s default facecolor)')
+    for a in list(fig.artists) + list(fig.lines) + list(fig.patches) + list(fig.texts) + list(fig.images) + list(fig.legends):
+        if a.get_visible():
+            raise NotImplementedError('figure-level artists are not extracted')
     artists: List[Dict[str, Any]] = []
     for ax in fig.axes:
         ax.apply_aspect()
-        children = [a for a in list(ax.patches) + list(ax.lines) if a.get_visible()]
-        if ax.axison and ax.get_frame_on():
-            raise NotImplementedError('axes frame / ticks are not extracted (the reference calls ax.axis("off"))')
-        children.sort(key=lambda a: a.get_zorder())          # stable: insertion order within a zorder
-        for a in children:
+        for a in _drawn_children(ax):
             if isinstance(a, Line2D):
                 if a.get_linestyle() not in ('-', 'solid') or a.get_marker() not in (None, 'None', '', ' '):
                     raise NotImplementedError('dashed lines / markers')
                 artists.append(_line_artist(a))
-            elif isinstance(a, Patch):
+            else:
                 if a.get_hatch():
                     raise NotImplementedError('hatches')
                 artists.append(_patch_artist(a))

@@ -9,6 +9,7 @@ bytes differ from libpng's (different deflate strategy).  No CPU encoding path e
 from __future__ import annotations
 
 import ctypes
+import re
 import os
 import threading
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -123,12 +124,17 @@ class PngEncoder:
             raise ValueError(f'{n} images > max_images {self.max_images}')
         with self._lock:
             s = self._begun & 1
-            for _ in range(2):
+            for _ in range(3):
                 pin = self._pins[s]
                 rc = self._lib.rig_png_encode_begin(self._h, imgs_ptr, n, _LAYOUTS[layout], pin.ptr, pin.nbytes, stream or None)
-                if rc == _abi.RIG_E_CAPACITY and b'out_capacity' in (self._lib.rig_png_last_error(self._h) or b''):
+                msg = (self._lib.rig_png_last_error(self._h) or b'') if rc == _abi.RIG_E_CAPACITY else b''
+                if b'out_capacity' in msg:
+                    # the message carries the exact size ("the PNG files need N bytes"): grow to it in one step (with slack for the
+                    # next batches), never past the worst case; the library keeps the blank-band hint for the retry
+                    m = re.search(rb'need (\d+) bytes', msg)
+                    need = int(m.group(1)) if m else 2 * pin.nbytes
                     pin.close()
-                    self._pins[s] = PinnedBuffer(min(self.bound(n), 2 * pin.nbytes + (1 << 24)))
+                    self._pins[s] = PinnedBuffer(min(self.bound(n), max(need + need // 4, 2 * pin.nbytes)))
                     continue
                 break
             if rc < 0:

@@ -22,10 +22,27 @@ def agg(built):
 
 def check(got, ref):
     diff = np.abs(got.astype(np.int16) - ref.astype(np.int16))
-    # the stated tolerance ...
-    assert diff.mean() <= 1.0 / 255 * 255 and (diff <= 2).mean() >= 0.995
+    # the stated tolerance (north_star: mean |diff| <= 1/255 of full scale = 1 level, >= 99.5 % of pixels within 2 levels) ...
+    assert diff.mean() <= 1.0 and (diff <= 2).mean() >= 0.995
     # ... and the bar actually held
     assert int((diff != 0).any(axis=-1).sum()) == 0
+
+
+def test_matplotlib_golden(built):
+    """k_figure_path + k_figure against pixels rendered by a real matplotlib (tests/golden/make_figure_golden.py); skipped until
+    someone with matplotlib has generated the fixture -- until then the figure path is oracle-exact, matplotlib parity unverified."""
+    import os
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'figure_mpl.npz')
+    if not os.path.exists(golden):
+        pytest.skip('tests/golden/figure_mpl.npz not generated (needs matplotlib)')
+    from test_figure_mpl import check_against_matplotlib
+    from reasoning_image_generation_b200.figure import scene_from_arrays
+    d = np.load(golden)
+    scene = scene_from_arrays(d, 'scene_')
+    r = FigureRenderer(scene.W, scene.H, max_images=scene.n_images, max_artists=max(scene.n_artists, 1))
+    got = r.render(scene, layout='rgb')
+    r.close()
+    check_against_matplotlib(got, d['pixels'], 'k_figure vs matplotlib ' + str(d['matplotlib_version']))
 
 
 @pytest.mark.parametrize('kind', ['single', 'multi'])
@@ -117,7 +134,7 @@ def test_fuzz_paths_caps_joins(agg):
     r.close()
 
 
-@pytest.mark.parametrize('size', [(256, 256), (640, 480), (1600, 1600), (48, 33), (16, 3), (2048, 37)])
+@pytest.mark.parametrize('size', [(256, 256), (640, 480), (1600, 1600), (2400, 2400), (48, 33), (16, 3), (3072, 37)])
 def test_other_canvas_sizes(agg, size):
     W, H = size
     sc = synthetic_figure_scene(5, W, H, seed=5, kind='single')
