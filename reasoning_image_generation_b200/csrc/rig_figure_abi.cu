@@ -8,6 +8,7 @@
 // and its layers / edges are copied to HBM.  With a host destination the images go through two device staging buffers so the
 // D2H copy of one chunk overlaps the next chunk.
 #include <cuda_runtime.h>
+#include <emmintrin.h>
 #include <sched.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -26,8 +27,61 @@
 #include "rig_figure.cuh"
 #include "rig_figure_host.h"
 #include "rig_figure_path.cuh"
+#include "rig_timeline.h"
 
 using namespace rig;
+
+// ---- optional timeline (rig_timeline.h) ---------------------------------------------------------------------------------------
+namespace rig {
+namespace {
+struct TimelineRec { const char *name; cudaStream_t st; cudaEvent_t e0, e1; };
+std::mutex g_tl_mutex;
+std::vector<TimelineRec> g_tl;
+std::vector<std::pair<cudaStream_t, size_t>> g_tl_open;
+}
+bool timeline_on()
+{
+    static const bool on = getenv("RIG_TIMELINE") != nullptr;
+    return on;
+}
+void timeline_mark(const char *name, cudaStream_t st, bool begin)
+{
+    std::lock_guard<std::mutex> g(g_tl_mutex);
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    if (begin) {
+        g_tl.push_back(TimelineRec{name, st, e, nullptr});
+        g_tl_open.push_back({st, g_tl.size() - 1});
+    } else {
+        for (size_t k = g_tl_open.size(); k-- > 0;)
+            if (g_tl_open[k].first == st && g_tl[g_tl_open[k].second].name == name) {
+                g_tl[g_tl_open[k].second].e1 = e;
+                g_tl_open.erase(g_tl_open.begin() + (long)k);
+                return;
+            }
+        cudaEventDestroy(e);
+    }
+}
+}  // namespace rig
+
+extern "C" int rig_timeline_dump(const char *path)
+{
+    std::lock_guard<std::mutex> g(rig::g_tl_mutex);
+    if (cudaDeviceSynchronize() != cudaSuccess) return RIG_E_CUDA;
+    FILE *f = fopen(path, "w");
+    if (!f) return RIG_E_INVALID;
+    fprintf(f, "name,stream,start_ms,end_ms\n");
+    for (const auto &r : rig::g_tl) {
+        if (!r.e1) continue;
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, rig::g_tl[0].e0, r.e0);
+        cudaEventElapsedTime(&b, rig::g_tl[0].e0, r.e1);
+        fprintf(f, "%s,%p,%.4f,%.4f\n", r.name, (void *)r.st, a, b);
+    }
+    fclose(f);
+    return RIG_OK;
+}
 
 namespace {
 thread_local char g_fig_create_err[512] = "";
@@ -207,11 +261,13 @@ struct rig_figure_ctx {
     bool resident_device_geom = false;    // the resident scene's artist arrays are in HBM (rig_figure_draw_resident can run)
     bool draw_pending = false;            // a rig_figure_draw_resident whose status word has not been checked yet
     HostBuf<uint8_t> blob_host[2];        // packed artist arrays (page-locked)
-    uint8_t *d_blob = nullptr;
-    size_t cap_blob = 0;
+    uint8_t *d_blob[2] = {nullptr, nullptr};      // two: the copy of batch k + 1's arrays runs (on copy_stream) under batch k's k_figure
+    size_t cap_blob[2] = {0, 0};
+    const uint32_t *cur_begin = nullptr;  // image_layer_begin of the resident scene: d_begin (host geometry) or inside the blob
     GeomParams gp = {};                   // device pointers of the resident scene
     uint32_t total_slots = 0;
     uint32_t *d_counters = nullptr, *h_counters = nullptr;
+    uint32_t *h_order = nullptr, *h_init = nullptr;      // page-locked: a pageable source would make the copy wait for other transfers
     float *d_cost = nullptr, *h_cost = nullptr;
     geom::SV *d_seq = nullptr;
     FEdge *d_estage = nullptr;
@@ -403,6 +459,7 @@ int upload_host_geometry(rig_figure_ctx *c, const rig_figure_scene *s, int layou
     if (!p.edges.empty()) FCK(c, cudaMemcpyAsync(c->d_edges, p.edges.data(), sizeof(FEdge) * p.edges.size(), cudaMemcpyHostToDevice, st));
     if (!p.dir.empty()) FCK(c, cudaMemcpyAsync(c->d_dir, p.dir.data(), sizeof(uint32_t) * p.dir.size(), cudaMemcpyHostToDevice, st));
     FCK(c, cudaMemcpyAsync(c->d_begin, p.image_layer_begin.data(), sizeof(uint32_t) * (c->n_images + 1), cudaMemcpyHostToDevice, st));
+    c->cur_begin = c->d_begin;
     if (c->n_images) FCK(c, cudaMemcpyAsync(c->d_order, c->order.data(), sizeof(uint32_t) * c->n_images, cudaMemcpyHostToDevice, st));
     FCK(c, cudaEventRecord(c->ev_h2d[slot], st));
     if (trace) fprintf(stderr, "upload: validate %.3f  wait %.3f  prepare %.3f  order %.3f  h2d-enqueue %.3f ms\n", ms(tv0, tv1), ms(tv1, t0), ms(t0, tv2), ms(tv2, tv3), ms(tv3, now()));
@@ -441,6 +498,24 @@ void fresolve_profiling(rig_figure_ctx *c)
 
 // ---- device geometry ------------------------------------------------------------------------------------------------
 size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// memcpy into the page-locked blob with non-temporal stores: the bytes are read next by the GPU's DMA engine, not by this core, and
+// a DMA read of lines that sit modified in a CPU cache measured 8x slower than one served from DRAM (3.9 MB in 0.6-0.8 ms
+// against 0.08 ms for a buffer the CPU had not just written: tools/h2d_probe.py, profiles/r2_notes.md).  dst is 16-byte aligned.
+void stream_copy(uint8_t *dst, const uint8_t *src, size_t n)
+{
+    size_t i = 0;
+    if ((((uintptr_t)dst) & 15u) == 0) {
+        for (; i + 64 <= n; i += 64) {
+            const __m128i a = _mm_loadu_si128((const __m128i *)(src + i)), b = _mm_loadu_si128((const __m128i *)(src + i + 16));
+            const __m128i c2 = _mm_loadu_si128((const __m128i *)(src + i + 32)), d = _mm_loadu_si128((const __m128i *)(src + i + 48));
+            _mm_stream_si128((__m128i *)(dst + i), a); _mm_stream_si128((__m128i *)(dst + i + 16), b);
+            _mm_stream_si128((__m128i *)(dst + i + 32), c2); _mm_stream_si128((__m128i *)(dst + i + 48), d);
+        }
+    }
+    if (i < n) memcpy(dst + i, src + i, n - i);
+    _mm_sfence();
+}
 
 // sections of the packed scene blob (byte offsets, 16-byte aligned)
 struct BlobLayout {
@@ -491,14 +566,13 @@ int ensure_geom_scratch(rig_figure_ctx *c)
 // k_figure_path over the resident artist arrays (counters reset first); asynchronous
 int run_geometry(rig_figure_ctx *c, cudaStream_t st)
 {
-    static uint32_t init[GC_WORDS] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    init[GC_BAD_ARTIST] = 0xffffffffu;
-    FCK(c, cudaMemcpyAsync(c->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
+    FCK(c, cudaMemcpyAsync(c->d_counters, c->h_init, sizeof(uint32_t) * GC_WORDS, cudaMemcpyHostToDevice, st));
     const uint32_t na = (uint32_t)c->gp.s.n_artists;
     if (na == 0) return RIG_OK;
     const uint32_t want_warps = c->gp.n_long / 4u + (na - c->gp.n_long + 31u) / 32u;      // a warp takes several long paths in turn
     const uint32_t want = (want_warps + GEOM_WARPS - 1) / GEOM_WARPS;
     const uint32_t grid = std::max(1u, std::min(want, c->geom_threads / GEOM_THREADS));
+    TimelineScope tl("k_figure_path", st);
     if (c->profiling) fprof_event(c, st);
     k_figure_path<<<grid, GEOM_THREADS, sizeof(uint32_t) * GEOM_WARPS * geom_warp_smem_words(c->H), st>>>(c->gp);
     c->stats.kernel_launches++;
@@ -562,7 +636,11 @@ int upload_device_geometry(rig_figure_ctx *c, const rig_figure_scene *s, int lay
     std::vector<Seg> pieces;
     for (const Seg &g : segs)
         for (size_t o = 0; o < g.bytes; o += kPiece) pieces.push_back(Seg{g.at + o, (const uint8_t *)g.src + o, std::min(kPiece, g.bytes - o)});
-    const std::function<void(int)> copy_piece = [&](int k) { memcpy(hb.data() + pieces[k].at, pieces[k].src, pieces[k].bytes); };
+    static const bool plain_copy = getenv("RIG_PACK_MEMCPY") != nullptr;
+    const std::function<void(int)> copy_piece = [&](int k) {
+        if (plain_copy) memcpy(hb.data() + pieces[k].at, pieces[k].src, pieces[k].bytes);
+        else stream_copy(hb.data() + pieces[k].at, (const uint8_t *)pieces[k].src, pieces[k].bytes);
+    };
     if (pieces.size() < 4 || c->host->pool.size() == 1) { for (size_t k = 0; k < pieces.size(); k++) copy_piece((int)k); }
     else c->host->pool.run((int)pieces.size(), copy_piece);
     const auto t2 = std::chrono::steady_clock::now();
@@ -570,10 +648,15 @@ int upload_device_geometry(rig_figure_ctx *c, const rig_figure_scene *s, int lay
     if (getenv("RIG_PREP_TRACE"))
         fprintf(stderr, "upload (device geometry): slots + order %.3f ms, pack %zu B in %zu pieces %.3f ms\n",
                 std::chrono::duration<double, std::milli>(t1 - t0).count(), L.total, pieces.size(), std::chrono::duration<double, std::milli>(t2 - t1).count());
-    if ((rc = ensure(c, c->d_blob, c->cap_blob, L.total))) return rc;
-    FCK(c, cudaMemcpyAsync(c->d_blob, hb.data(), L.total, cudaMemcpyHostToDevice, st));
-    FCK(c, cudaMemcpyAsync(c->d_begin, hb.data() + L.ilb, 4 * (ni + 1), cudaMemcpyHostToDevice, st));
-    FCK(c, cudaEventRecord(c->ev_h2d[slot], st));
+    // The blob goes up on the copy stream: nothing on the render stream has to finish first (the blob it replaces was last read by
+    // the geometry kernel two uploads ago), so the transfer runs under the previous batch's k_figure instead of behind it.
+    if ((rc = ensure(c, c->d_blob[slot], c->cap_blob[slot], L.total))) return rc;
+    {
+        TimelineScope tl("h2d_artists", c->copy_stream);
+        FCK(c, cudaMemcpyAsync(c->d_blob[slot], hb.data(), L.total, cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    FCK(c, cudaEventRecord(c->ev_h2d[slot], c->copy_stream));
+    FCK(c, cudaStreamWaitEvent(st, c->ev_h2d[slot], 0));
     // ---- output arenas: directory entries have an exact bound, edges start from an estimate and grow on demand
     const size_t dir_bound = (size_t)c->total_slots * (size_t)(c->H / FIG_SLAB_ROWS + 3);
     if ((rc = ensure(c, c->d_layers, c->cap_layers, c->total_slots))) return rc;
@@ -582,7 +665,8 @@ int upload_device_geometry(rig_figure_ctx *c, const rig_figure_scene *s, int lay
     GeomParams &P = c->gp;
     rig_figure_scene &d = P.s;
     d = *s;
-    const uint8_t *B = c->d_blob;
+    const uint8_t *B = c->d_blob[slot];
+    c->cur_begin = (const uint32_t *)(B + L.ilb);
     d.image_artist_begin = (const uint32_t *)(B + L.iab); d.artist_vertex_begin = (const uint32_t *)(B + L.avb);
     d.vertices = (const double *)(B + L.vertices); d.codes = B + L.codes; d.affine = (const double *)(B + L.affine);
     d.linewidth = (const double *)(B + L.linewidth); d.cap = B + L.cap; d.join = B + L.join; d.snap = B + L.snap;
@@ -599,10 +683,11 @@ int upload_device_geometry(rig_figure_ctx *c, const rig_figure_scene *s, int lay
         P.layers = c->d_layers; P.edges = c->d_edges; P.dir = c->d_dir;
         P.edge_cap = (uint32_t)std::min<size_t>(c->cap_edges, 0xfffffff0u); P.dir_cap = (uint32_t)std::min<size_t>(c->cap_dir, 0xfffffff0u);
         if ((rc = run_geometry(c, st))) return rc;
-        if (ni) k_figure_cost<<<(unsigned)((ni + 255) / 256), 256, 0, st>>>(c->d_begin, c->d_layers, (uint32_t)ni, c->d_cost);
+        if (ni) k_figure_cost<<<(unsigned)((ni + 255) / 256), 256, 0, st>>>(c->cur_begin, c->d_layers, (uint32_t)ni, c->h_cost, c->d_counters, c->h_counters);
         c->stats.kernel_launches++;
-        FCK(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(uint32_t) * GC_WORDS, cudaMemcpyDeviceToHost, st));
-        if (ni) FCK(c, cudaMemcpyAsync(c->h_cost, c->d_cost, sizeof(float) * ni, cudaMemcpyDeviceToHost, st));
+        // (k_figure_cost writes the weights and the counters straight into page-locked host memory: a D2H copy of a few KB
+        // would queue behind whatever large transfer the copy engine is busy with -- the previous batch's PNG files)
+        if (!ni) FCK(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(uint32_t) * GC_WORDS, cudaMemcpyDeviceToHost, st));
         FCK(c, cudaStreamSynchronize(st));
         status = c->h_counters[GC_STATUS];
         if (!(status & geom::GEOM_ARENA_OVERFLOW)) break;
@@ -621,7 +706,10 @@ int upload_device_geometry(rig_figure_ctx *c, const rig_figure_scene *s, int lay
     for (size_t i = 0; i < ni; i++) c->cost[i] = c->h_cost[i];
     c->order.resize(ni);
     order_range(c, 0, (uint32_t)ni);
-    if (ni) FCK(c, cudaMemcpyAsync(c->d_order, c->order.data(), sizeof(uint32_t) * ni, cudaMemcpyHostToDevice, st));
+    if (ni) {
+        memcpy(c->h_order, c->order.data(), sizeof(uint32_t) * ni);      // (the previous upload's copy from h_order finished before its sync returned)
+        FCK(c, cudaMemcpyAsync(c->d_order, c->h_order, sizeof(uint32_t) * ni, cudaMemcpyHostToDevice, st));
+    }
     c->resident_device_geom = true;
     return RIG_OK;
 }
@@ -645,7 +733,7 @@ int launch(rig_figure_ctx *c, uint32_t i0, uint32_t i1, uint8_t *out_dev, uint32
     if (i1 <= i0) return RIG_OK;
     FCK(c, cudaMemsetAsync(c->d_work, 0, sizeof(uint32_t), st));
     FigureParams P;
-    P.image_layer_begin = c->d_begin; P.layers = c->d_layers; P.edges = c->d_edges; P.dir = c->d_dir;
+    P.image_layer_begin = c->cur_begin; P.layers = c->d_layers; P.edges = c->d_edges; P.dir = c->d_dir;
     P.order = c->d_order + i0;
     P.out = out_dev - (size_t)img_base * c->H * c->W * 3;
     P.work = c->d_work;
@@ -664,6 +752,7 @@ int launch(rig_figure_ctx *c, uint32_t i0, uint32_t i1, uint8_t *out_dev, uint32
     const uint32_t bands = P.n_images * (uint32_t)((c->H + FIG_ROWS - 1) / FIG_ROWS);
     const uint32_t want = (bands + c->warps - 1) / c->warps;
     const uint32_t grid = std::max(1u, std::min((uint32_t)c->sm_count, want));
+    TimelineScope tl("k_figure", st);
     if (c->profiling) fprof_event(c, st);
     k_figure<<<grid, c->warps * 32, c->smem, st>>>(P);
     c->stats.kernel_launches++;
@@ -743,6 +832,9 @@ int rig_figure_create(int device, int W, int H, int max_images, int max_artists,
     FCKC(cudaMallocHost((void **)&c->h_counters, sizeof(uint32_t) * GC_WORDS));
     FCKC(cudaMalloc(&c->d_cost, sizeof(float) * (size_t)max_images));
     FCKC(cudaMallocHost((void **)&c->h_cost, sizeof(float) * (size_t)max_images));
+    FCKC(cudaMallocHost((void **)&c->h_order, sizeof(uint32_t) * (size_t)max_images));
+    FCKC(cudaMallocHost((void **)&c->h_init, sizeof(uint32_t) * GC_WORDS));
+    for (int i = 0; i < GC_WORDS; i++) c->h_init[i] = i == GC_BAD_ARTIST ? 0xffffffffu : 0u;
     FCKC(cudaMalloc(&c->d_begin, sizeof(uint32_t) * ((size_t)max_images + 1)));
     FCKC(cudaMalloc(&c->d_order, sizeof(uint32_t) * (size_t)max_images));
     FCKC(cudaMalloc(&c->d_work, sizeof(uint32_t) * 4));
@@ -761,9 +853,11 @@ void rig_figure_destroy(rig_figure_ctx *c)
     cudaFree(c->d_layers); cudaFree(c->d_edges); cudaFree(c->d_dir); cudaFree(c->d_begin); cudaFree(c->d_order); cudaFree(c->d_work);
     cudaFree(c->d_stage[0]); cudaFree(c->d_stage[1]);
     for (int i = 0; i < 4; i++) cudaFree(c->d_blank[i]);
-    cudaFree(c->d_blob); cudaFree(c->d_counters); cudaFree(c->d_cost); cudaFree(c->d_seq); cudaFree(c->d_estage);
+    cudaFree(c->d_blob[0]); cudaFree(c->d_blob[1]); cudaFree(c->d_counters); cudaFree(c->d_cost); cudaFree(c->d_seq); cudaFree(c->d_estage);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_cost) cudaFreeHost(c->h_cost);
+    if (c->h_order) cudaFreeHost(c->h_order);
+    if (c->h_init) cudaFreeHost(c->h_init);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_used) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
@@ -874,7 +968,7 @@ int64_t rig_figure_debug_resident(rig_figure_ctx *c, uint32_t *layers_out, int32
     std::vector<FLayer> layers(nl);
     std::vector<uint32_t> begin(ni + 1);
     if (nl && cudaMemcpy(layers.data(), c->d_layers, sizeof(FLayer) * nl, cudaMemcpyDeviceToHost) != cudaSuccess) return RIG_E_CUDA;
-    if (cudaMemcpy(begin.data(), c->d_begin, sizeof(uint32_t) * (ni + 1), cudaMemcpyDeviceToHost) != cudaSuccess) return RIG_E_CUDA;
+    if (cudaMemcpy(begin.data(), c->cur_begin, sizeof(uint32_t) * (ni + 1), cudaMemcpyDeviceToHost) != cudaSuccess) return RIG_E_CUDA;
     int64_t ne = 0, out_l = 0;
     size_t img = 0;
     for (size_t l = 0; l < nl; l++) {

@@ -683,10 +683,14 @@ __global__ void __launch_bounds__(GEOM_THREADS, GEOM_MIN_CTAS) k_figure_path(con
     if (status) atomicOr(P.counters + GC_STATUS, status);
 }
 
-// per-image scheduling weight for k_figure's costliest-first order: edges + 8 x the rows its layers resolve
-__global__ void k_figure_cost(const uint32_t *image_layer_begin, const FLayer *layers, uint32_t n_images, float *cost)
+// per-image scheduling weight for k_figure's costliest-first order: edges + 8 x the rows its layers resolve.  `cost` and
+// `counters_host` are page-locked HOST memory (unified addressing): the kernel that follows k_figure_path delivers its results
+// without a copy-engine transfer.
+__global__ void k_figure_cost(const uint32_t *image_layer_begin, const FLayer *layers, uint32_t n_images, float *cost, const uint32_t *counters,
+                              uint32_t *counters_host)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < GC_WORDS) counters_host[i] = counters[i];
     if (i >= n_images) return;
     float w = 0.f;
     for (uint32_t l = image_layer_begin[i]; l < image_layer_begin[i + 1]; l++) {

@@ -492,8 +492,12 @@ __global__ void k_png_sizes(const PngPiece *__restrict__ pieces, int n, uint32_t
     if (lane == 0) sizes[img] = png_deflate_bytes(s, tables->hdr_bits, tables->eob >> 24) + PNG_FILE_OVERHEAD;
 }
 
-// exclusive prefix sum of sizes[0..n) into offsets[0..n]; one CTA of 1024 threads
-__global__ void __launch_bounds__(1024) k_png_scan(const unsigned long long *__restrict__ sizes, int n, unsigned long long *__restrict__ offsets)
+// exclusive prefix sum of sizes[0..n) into offsets[0..n]; one CTA of 1024 threads.  offsets_host / counters_host are page-locked
+// HOST memory (unified addressing): the host waits for these numbers, and a copy-engine transfer of them would queue behind the
+// previous batch's files.
+__global__ void __launch_bounds__(1024) k_png_scan(const unsigned long long *__restrict__ sizes, int n, unsigned long long *__restrict__ offsets,
+                                                   unsigned long long *__restrict__ offsets_host, const unsigned long long *__restrict__ counters,
+                                                   unsigned long long *__restrict__ counters_host)
 {
     __shared__ unsigned long long part[1024];
     const int t = threadIdx.x;
@@ -512,9 +516,11 @@ __global__ void __launch_bounds__(1024) k_png_scan(const unsigned long long *__r
     unsigned long long run = t ? part[t - 1] : 0ull;
     for (int i = b; i < e; i++) {
         offsets[i] = run;
+        offsets_host[i] = run;
         run += sizes[i];
     }
-    if (t == 1023) offsets[n] = part[1023];
+    if (t == 1023) { offsets[n] = part[1023]; offsets_host[n] = part[1023]; }
+    if (t < 2) counters_host[t] = counters[t];
 }
 
 // a * b mod P over GF(2), reflected bit order (zlib crc32.c multmodp)

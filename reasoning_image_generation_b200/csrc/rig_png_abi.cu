@@ -12,6 +12,7 @@
 
 #include "../../include/rig_png.h"
 #include "rig_png.cuh"
+#include "rig_timeline.h"
 
 using namespace rig;
 
@@ -279,16 +280,15 @@ static int png_run_pieces(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int la
         // persistent warps: every warp prepares the bits of a white row once, then walks pieces with a grid stride
         const unsigned long long want = (npieces + c->wpc - 1) / c->wpc;
         const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)c->sm_count * c->ctas_per_sm);
+        TimelineScope tl("k_png_pieces", st);
         if (c->ch == 3) k_png_pieces<3><<<grid, c->wpc * 32, c->smem, st>>>(P);
         else k_png_pieces<4><<<grid, c->wpc * 32, c->smem, st>>>(P);
     }
     k_png_sizes<<<(n + 7) / 8, 256, 0, st>>>(c->d_pieces, n, c->ppi, c->d_tables, c->d_sizes);
-    k_png_scan<<<1, 1024, 0, st>>>(c->d_sizes, n, c->d_offsets);
+    unsigned long long *h_counters = c->h_counters;      // page-locked: k_png_scan writes the offsets and the counters there itself
+    k_png_scan<<<1, 1024, 0, st>>>(c->d_sizes, n, c->d_offsets, c->h_offs[slot], c->d_counters, h_counters);
     c->stats.kernel_launches += 3;
     PCK(c, cudaGetLastError());
-    PCK(c, cudaMemcpyAsync(c->h_offs[slot], c->d_offsets, sizeof(unsigned long long) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
-    unsigned long long *h_counters = c->h_counters;      // page-locked, so that the copy is asynchronous and the wait below sleeps
-    PCK(c, cudaMemcpyAsync(h_counters, c->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     // the host needs the sizes before it can go on (how it waits: see png_blocking_wait)
     if (!c->blocking) PCK(c, cudaStreamSynchronize(st));
     else {
@@ -305,7 +305,10 @@ static int png_run_assemble(rig_png_ctx *c, int n, uint8_t *dev_out, int slot)
     PngAssembleParams A;
     A.pieces = c->d_pieces; A.scratch = c->d_scratch; A.offsets = c->d_offsets; A.tables = c->d_tables; A.out = dev_out;
     A.n = n; A.W = c->W; A.H = c->H; A.ch = c->ch; A.pieces_per_image = c->ppi;
-    k_png_assemble<<<(n + c->asm_warps - 1) / c->asm_warps, c->asm_warps * 32, png_assemble_smem(c->ppi, c->asm_warps), c->stream>>>(A);
+    {
+        TimelineScope tl("k_png_assemble", c->stream);
+        k_png_assemble<<<(n + c->asm_warps - 1) / c->asm_warps, c->asm_warps * 32, png_assemble_smem(c->ppi, c->asm_warps), c->stream>>>(A);
+    }
     c->stats.kernel_launches++;
     PCK(c, cudaGetLastError());
     if (c->profiling) PCK(c, cudaEventRecord(c->ev1[slot], c->stream));
@@ -354,7 +357,10 @@ int rig_png_encode_begin(rig_png_ctx *c, const uint8_t *imgs_dev, int n, int lay
     // the copy runs on its own stream: the next batch's kernels start right behind k_png_assemble
     PCK(c, cudaEventRecord(c->ev_asm, c->stream));
     PCK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_asm, 0));
-    PCK(c, cudaMemcpyAsync(out_host, c->d_outs[slot], total, cudaMemcpyDeviceToHost, c->copy_stream));
+    {
+        TimelineScope tl("d2h_files", c->copy_stream);
+        PCK(c, cudaMemcpyAsync(out_host, c->d_outs[slot], total, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
     PCK(c, cudaEventRecord(c->ev_copy[slot], c->copy_stream));
     c->slot_busy[slot] = true;
     c->next_slot++;
