@@ -67,21 +67,21 @@ constexpr int PNG_STAGE_WORDS = 28;      // >= (10 + 64 * 10 + 9 * 16 + 2 * 10 +
 static_assert(PNG_MAX_CODE_BITS <= 10, "PNG_STAGE_WORDS is sized for codes of at most 10 bits");
 struct PngStage {
     uint32_t *stage;
-    unsigned long long acc = 0;
+    uint32_t acc = 0;            // the bits not yet written (fewer than 32)
     uint32_t nacc = 0, k = 0;
-    __device__ __forceinline__ void put(uint32_t code, int n)
+    __device__ __forceinline__ void put(uint32_t code, int n)       // n <= 32 bits of `code`, the rest of it zero
     {
-        acc |= (unsigned long long)code << nacc;
-        nacc += (uint32_t)n;
-        if (nacc >= 32u) {
-            stage[k++] = (uint32_t)acc;
-            acc >>= 32;
-            nacc -= 32u;
-        }
+        acc |= code << nacc;
+        const uint32_t tot = nacc + (uint32_t)n;
+        if (tot >= 32u) {
+            stage[k++] = acc;
+            acc = __funnelshift_rc(code, 0u, 32u - nacc);           // the bits of `code` that did not fit (a clamped shift: 0 when nacc is 0)
+            nacc = tot - 32u;
+        } else nacc = tot;
     }
     __device__ __forceinline__ uint32_t finish()      // flushes the tail, returns the number of bits
     {
-        stage[k] = (uint32_t)acc;
+        stage[k] = acc;
         return 32u * k + nacc;
     }
 };
