@@ -39,7 +39,7 @@ E2E_PANELS = 4096              # 3.2 GB pinned host destination per e2e step
 DEDUP_N = 10_000_000           # BASELINE configs[4]: hashes in the all-pairs timing input (5.0e13 pairs)
 FIG_PER_STEP = 32768           # 25.8 GB of pixels per step per GPU
 FIG_E2E = 32768               # images per e2e step (the whole step scene) ...
-FIG_E2E_CHUNK = 4096          # ... rendered + encoded 4096 at a time
+FIG_E2E_CHUNK = 4096          # ... rendered + encoded 4096 at a time (--e2e-chunk)
 FIG_METRIC = 'rendered images/sec at 512x512 (multigraph single-shape variants)'
 FIG_WORKLOAD = ('BASELINE configs[1]: multigraph single-shape variants, synthetic (SURVEY 8d: one outlined base patch -- circle / '
                 'ellipse / rectangle / rounded box / regular polygon / wedge, 1.5-2.0 pt, alpha 0.9 -- plus 1-6 internal lines or 1-3 '
@@ -376,11 +376,12 @@ def figure_leg(env, args, sampler):
     from reasoning_image_generation_b200.png import PngEncoder
     from reasoning_image_generation_b200.render import PinnedBuffer
     sub = scene.slice(0, FIG_E2E)
-    enc = PngEncoder(512, 512, device=env.local, max_images=FIG_E2E_CHUNK, channels=4)      # RGBA files, as fig.savefig writes them
-    r2 = FigureRenderer(512, 512, device=env.local, max_images=FIG_E2E_CHUNK, max_artists=max(sub.n_artists, 1))
+    e2e_chunk = args.e2e_chunk
+    enc = PngEncoder(512, 512, device=env.local, max_images=e2e_chunk, channels=4)      # RGBA files, as fig.savefig writes them
+    r2 = FigureRenderer(512, 512, device=env.local, max_images=e2e_chunk, max_artists=max(sub.n_artists, 1))
     png_bytes = 0
     for _ in range(2):
-        for i0, buf, off in r2.iter_png(sub, enc, FIG_E2E_CHUNK):
+        for i0, buf, off in r2.iter_png(sub, enc, e2e_chunk):
             pass
     env.barrier()
     l0 = r2.stats()['kernel_launches'] + enc.stats()['kernel_launches']
@@ -388,7 +389,7 @@ def figure_leg(env, args, sampler):
     e2e_steps = args.e2e_steps                      # 32 x 32 768 images: a timed region of about a second
     digest = 0
     for _ in range(e2e_steps):
-        for i0, buf, off in r2.iter_png(sub, enc, FIG_E2E_CHUNK):
+        for i0, buf, off in r2.iter_png(sub, enc, e2e_chunk):
             png_bytes += int(off[-1])
             digest ^= int(buf[int(off[1]) - 16]) if len(off) > 1 else 0
     torch.cuda.synchronize()
@@ -422,7 +423,7 @@ def figure_leg(env, args, sampler):
         'value': value, 'ms_per_step': ms_max / args.steps, 'warmup': n_warm, 'clocks': clocks,
         'launches': stats['kernel_launches'] - launches0, 'stats': stats, 'n': n, 'multi_shape': multi_info,
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': png_bytes // e2e_steps,
-                'images_per_step_per_gpu': FIG_E2E, 'chunk': FIG_E2E_CHUNK,
+                'images_per_step_per_gpu': FIG_E2E, 'chunk': e2e_chunk,
                 'png_bytes_per_image': png_bytes / (e2e_steps * FIG_E2E), 'gpu_launches': e2e_launches,
                 'timed_s': dt, 'steps': e2e_steps, 'geom_fallbacks': geom_fallbacks,
                 'note': 'FigureRenderer.iter_png = fig.savefig for a batch: host artist arrays in (packed, one H2D copy per chunk), '
@@ -719,6 +720,7 @@ def main():
                     help='figure: BASELINE configs[1] (headline) + the sequence-panel path as a sub-object; sequence: that path only')
     ap.add_argument('--no-sequence', action='store_true', help='figure workload: skip the sequence-panel leg')
     ap.add_argument('--e2e-steps', type=int, default=32, help='timed passes of the e2e legs over the step scene (about 1 s)')
+    ap.add_argument('--e2e-chunk', type=int, default=FIG_E2E_CHUNK, help='images rendered + encoded per chunk of the figure e2e leg')
     ap.add_argument('--seq-cpu-budget', type=float, default=10.0, help='seconds of CPU work for the sequence-panel cpu_baseline')
     args = ap.parse_args()
     if args.impl == 'reference':

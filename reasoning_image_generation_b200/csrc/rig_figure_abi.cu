@@ -540,6 +540,7 @@ int ensure_geom_scratch(rig_figure_ctx *c)
 {
     if (c->d_seq) return RIG_OK;
     int per_sm = 0;
+    FCK(c, cudaFuncSetAttribute(k_figure_path, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * GEOM_WARPS * geom_warp_smem_words(c->H))));
     FCK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_figure_path, GEOM_THREADS, sizeof(uint32_t) * GEOM_WARPS * geom_warp_smem_words(c->H)));
     if (per_sm < 1) return ffail(c, RIG_E_CUDA, "k_figure_path cannot be resident");
     // Thread-private scratch: the stroker's vertex sequence (40 B per flattened vertex) and the pass's unsorted edges.  Sized for

@@ -51,7 +51,17 @@ struct GeomParams {
     uint32_t seq_cap, stage_cap;
 };
 
-__host__ __device__ inline size_t geom_warp_smem_words(int H) { return (size_t)(H + 34 > GEOM_CMD_CAP ? H + 34 : GEOM_CMD_CAP); }
+// Vertices a warp-route path may have for its arrays (vertices, lengths, offsets, contour) to live in SHARED memory: 72 bytes per
+// vertex and warp; longer paths use the warp's global scratch.  Off by default: measured SLOWER (per 32 768 single-shape figures:
+// 0: 0.86 ms, 128: 1.15 ms, 192: 1.25 ms -- outlines of 100-200 vertices overflow and flatten twice, and the larger CTAs cost more
+// than the shorter round trips save; profiles/r2_notes.md).
+#ifndef GEOM_SMEM_PTS
+#define GEOM_SMEM_PTS 0
+#endif
+__host__ __device__ inline size_t geom_warp_smem_words(int H)
+{
+    return (size_t)(H + 34 > GEOM_CMD_CAP ? H + 34 : GEOM_CMD_CAP) + (size_t)GEOM_SMEM_PTS * 18;
+}
 
 struct DevSeq {
     geom::SV *p;
@@ -220,7 +230,8 @@ struct WarpScratch {
     double2 *P;            // flattened vertices
     double *d, *nx, *ny;   // per vertex: distance to the next one, half-width offsets of that segment
     double2 *C;            // contour points
-    uint32_t cap_pts, cap_contour;
+    double2 *slices;       // 32 areas of slice_cap points: where the lanes flatten their curves before the points are concatenated
+    uint32_t cap_pts, cap_contour, slice_cap;
     FEdge *stage;          // the warp's 32 staging areas, contiguous
     uint32_t stage_cap;
 };
@@ -315,7 +326,7 @@ __device__ __forceinline__ int geom_warp_parse(const geom::PathView &path, uint3
     return ok ? ncmd : -1;
 }
 
-// flatten: P[0..N); returns N, or -1 on overflow of the scratch (status set).  Every lane subdivides its curve once, into its own
+// flatten: P[0..N); returns N, -1 when a curve overflows its slice (status set) or -2 when the points do not fit ws.P.  Every lane subdivides its curve once, into its own
 // slice of the (still unused) contour area; the slices are then moved to their place in P[], command after command.
 __device__ __forceinline__ int geom_warp_flatten(const geom::PathView &path, const uint32_t *cmd, int ncmd, int lane, WarpScratch &ws, uint32_t &status)
 {
@@ -323,8 +334,8 @@ __device__ __forceinline__ int geom_warp_flatten(const geom::PathView &path, con
         const geom::Node m = path.node(0);
         ws.P[0] = make_double2(m.x, m.y);
     }
-    const uint32_t slice_cap = ws.cap_contour / 32u;
-    double2 *slice = ws.C + (size_t)lane * slice_cap;
+    const uint32_t slice_cap = ws.slice_cap;
+    double2 *slice = ws.slices + (size_t)lane * slice_cap;
     uint32_t base = 1;
     for (int c0 = 0; c0 < ncmd; c0 += 32) {
         const int j = c0 + lane;
@@ -358,7 +369,8 @@ __device__ __forceinline__ int geom_warp_flatten(const geom::PathView &path, con
         }
         uint32_t total;
         const uint32_t off = warp_excl_scan(cnt, lane, total);
-        if (__any_sync(0xffffffffu, over) || base + total > ws.cap_pts) { status |= geom::GEOM_SEQ_OVERFLOW; return -1; }
+        if (__any_sync(0xffffffffu, over)) { status |= geom::GEOM_SEQ_OVERFLOW; return -1; }
+        if (base + total > ws.cap_pts) return -2;                      // does not fit these arrays (the caller may have larger ones)
         __syncwarp();
         if (cnt == 1u && j < ncmd && (cmd[j] >> 24) == 2u) ws.P[base + off] = single;
         uint32_t curves = __ballot_sync(0xffffffffu, j < ncmd && (cmd[j] >> 24) != 2u);
@@ -366,7 +378,7 @@ __device__ __forceinline__ int geom_warp_flatten(const geom::PathView &path, con
             const int src = __ffs(curves) - 1;
             curves &= curves - 1;
             const uint32_t scnt = __shfl_sync(0xffffffffu, cnt, src), soff = __shfl_sync(0xffffffffu, off, src);
-            const double2 *from = ws.C + (size_t)src * slice_cap;
+            const double2 *from = ws.slices + (size_t)src * slice_cap;
             for (uint32_t k = lane; k < scnt; k += 32) ws.P[base + soff + k] = from[k];
         }
         __syncwarp();
@@ -534,18 +546,31 @@ __global__ void __launch_bounds__(GEOM_THREADS, GEOM_MIN_CTAS) k_figure_path(con
     const uint32_t n_art = (uint32_t)P.s.n_artists;
     // ---- long paths: one per warp
     {
-        WarpScratch ws;
+        WarpScratch wg, wsm;                                             // arrays in global scratch / in shared memory
         const size_t wtid = tid - lane;                                  // the warp's first thread
         uint8_t *sb = (uint8_t *)(P.seq + wtid * P.seq_cap);             // 32 * seq_cap * 40 bytes
-        ws.cap_pts = P.seq_cap * 8u;
-        ws.cap_contour = P.seq_cap * 32u;
-        ws.P = (double2 *)sb;                                            // 16 B * cap_pts
-        ws.d = (double *)(sb + (size_t)16 * ws.cap_pts);                 // 3 * 8 B * cap_pts
-        ws.nx = ws.d + ws.cap_pts;
-        ws.ny = ws.nx + ws.cap_pts;
-        ws.C = (double2 *)(sb + (size_t)40 * ws.cap_pts);                // 16 B * cap_contour  (total 40 * 8 + 16 * 32 = 832 <= 1280 B per seq_cap)
-        ws.stage = P.stage + wtid * P.stage_cap;
-        ws.stage_cap = P.stage_cap;
+        wg.cap_pts = P.seq_cap * 8u;
+        wg.cap_contour = P.seq_cap * 16u;
+        wg.slice_cap = P.seq_cap / 2u;
+        wg.P = (double2 *)sb;                                            // 16 B * cap_pts
+        wg.d = (double *)(sb + (size_t)16 * wg.cap_pts);                 // 3 * 8 B * cap_pts
+        wg.nx = wg.d + wg.cap_pts;
+        wg.ny = wg.nx + wg.cap_pts;
+        wg.C = (double2 *)(sb + (size_t)40 * wg.cap_pts);                // 16 B * cap_contour
+        wg.slices = wg.C + wg.cap_contour;                               // 16 B * 32 * slice_cap   (40 * 8 + 16 * 16 + 16 * 16 = 832 <= 1280 B per seq_cap)
+        wg.stage = P.stage + wtid * P.stage_cap;
+        wg.stage_cap = P.stage_cap;
+        wsm = wg;
+        if (GEOM_SMEM_PTS > 0) {
+            uint8_t *ss = (uint8_t *)(hist + (P.H + 34 > GEOM_CMD_CAP ? P.H + 34 : GEOM_CMD_CAP));
+            wsm.cap_pts = GEOM_SMEM_PTS;
+            wsm.cap_contour = 2u * GEOM_SMEM_PTS;
+            wsm.P = (double2 *)ss;
+            wsm.d = (double *)(ss + (size_t)16 * GEOM_SMEM_PTS);
+            wsm.nx = wsm.d + GEOM_SMEM_PTS;
+            wsm.ny = wsm.nx + GEOM_SMEM_PTS;
+            wsm.C = (double2 *)(ss + (size_t)40 * GEOM_SMEM_PTS);
+        }
         uint32_t *cmd = hist;
         for (;;) {
             uint32_t k = 0;
@@ -582,16 +607,20 @@ __global__ void __launch_bounds__(GEOM_THREADS, GEOM_MIN_CTAS) k_figure_path(con
                 run = false;
             }
             int closed = 0, N = -1;
-            bool parallel = false;
+            bool parallel = false, use_smem = false;
             if (run) {
                 const int ncmd = geom_warp_parse(art.path, cmd, closed, lane);
                 __syncwarp();
                 if (ncmd >= 0) {
-                    N = geom_warp_flatten(art.path, cmd, ncmd, lane, ws, status);
+                    N = geom_warp_flatten(art.path, cmd, ncmd, lane, wsm, status);
+                    use_smem = N >= 0;
+                    if (N == -2) N = geom_warp_flatten(art.path, cmd, ncmd, lane, wg, status);
+                    if (N == -2) status |= geom::GEOM_SEQ_OVERFLOW;
                     parallel = N >= 0;
                     if (N < 0) run = false;                              // scratch overflow: status set, the host takes the batch
                 }
             }
+            WarpScratch &ws = use_smem ? wsm : wg;
             // ---- pass 0: face
             E.reset();
             uint32_t n_edges = 0;
@@ -612,7 +641,7 @@ __global__ void __launch_bounds__(GEOM_THREADS, GEOM_MIN_CTAS) k_figure_path(con
             if (run && art.stroke) {
                 bool done = false;
                 if (parallel && join_style != RIG_JOIN_ROUND && cap_style != RIG_CAP_ROUND) {
-                    // (parse wrote the command list over hist; place_layers above reused it, flatten's output is in global scratch)
+                    // (parse wrote the command list over hist; place_layers above reused it, flatten's output lies behind it)
                     done = geom_warp_stroke(N, closed, art, cap_style, join_style, lane, ws, E, n_edges, status);
                     if (done) geom_warp_reduce_bounds(E, n_edges, lane, ws);
                 }
