@@ -570,7 +570,8 @@ int run_geometry(rig_figure_ctx *c, cudaStream_t st)
     FCK(c, cudaMemcpyAsync(c->d_counters, c->h_init, sizeof(uint32_t) * GC_WORDS, cudaMemcpyHostToDevice, st));
     const uint32_t na = (uint32_t)c->gp.s.n_artists;
     if (na == 0) return RIG_OK;
-    const uint32_t want_warps = c->gp.n_long / 4u + (na - c->gp.n_long + 31u) / 32u;      // a warp takes several long paths in turn
+    static const uint32_t long_div = getenv("RIG_GEOM_LONG_DIV") ? (uint32_t)std::max(1, atoi(getenv("RIG_GEOM_LONG_DIV"))) : 4u;
+    const uint32_t want_warps = c->gp.n_long / long_div + (na - c->gp.n_long + 31u) / 32u;      // a warp takes several long paths in turn
     const uint32_t want = (want_warps + GEOM_WARPS - 1) / GEOM_WARPS;
     const uint32_t grid = std::max(1u, std::min(want, c->geom_threads / GEOM_THREADS));
     TimelineScope tl("k_figure_path", st);
