@@ -137,7 +137,8 @@ def cpu_sample(seed, budget_s=14.0, cores=None):
     cores = cores or os.cpu_count() or 1
     per = 24
     done, t0, backend = 0, time.time(), '?'
-    with mp.get_context('fork').Pool(cores) as pool:
+    # 'spawn': the workers must not inherit this process's CUDA context (the GPU legs ran before the CPU baseline)
+    with mp.get_context('spawn').Pool(cores) as pool:
         while time.time() - t0 < budget_s and done + per * cores <= PANELS_PER_STEP:
             jobs = [(seed, done + i * per, done + (i + 1) * per) for i in range(cores)]
             res = pool.map(_cpu_worker, jobs)
@@ -181,7 +182,7 @@ def fig_cpu_sample(seed, budget_s=14.0, cores=None):
     per = 48
     done, render_s, total_s, png_bytes = 0, 0.0, 0.0, 0
     t0 = time.time()
-    with mp.get_context('fork').Pool(cores) as pool:
+    with mp.get_context('spawn').Pool(cores) as pool:                 # (not fork: see cpu_sample)
         while time.time() - t0 < budget_s:
             first = done % FIG_PER_STEP
             jobs = [(seed, first + i * per, first + (i + 1) * per) for i in range(cores)]
@@ -369,6 +370,35 @@ def figure_leg(env, args, sampler):
                   'hbm_frac_k_figure': n_multi * IMG_BYTES / (multi_cover / 1e3) / 1e9 / fallback_peak()[0],
                   'workload': 'BASELINE configs[2] shape: 2-3 outlined base patches, nested / adjacent / intersecting (synthetic), '
                               'k_figure_path + k_figure, artist arrays resident in HBM'}
+    # ---- the reference CLI's real output size: figsize (8, 8) x dpi 200 = 1600 x 1600 (multigraph_generation/cli.py:24), resident draw
+    big_info = None
+    try:
+        nb = 2048
+        big = synthetic_figure_scene(nb, 1600, 1600, seed=3000, kind='single', first=env.rank * nb)
+        rb = FigureRenderer(1600, 1600, device=env.local, max_images=nb, max_artists=max(big.n_artists, 1))
+        outb = out.view(-1)[:nb * 1600 * 1600 * 3]
+        rb.upload(big, 'rgb')
+        if rb.stats()['geom_resident']:
+            for _ in range(3):
+                rb.draw_resident(outb.data_ptr(), stream=env.st)
+            rb.sync()
+            rb.set_profiling(True)
+            for _ in range(max(2, args.steps // 2)):
+                rb.draw_resident(outb.data_ptr(), stream=env.st)
+            rb.sync()
+            bst = rb.stats()
+            b_cover, b_geom = env.max_over_ranks(bst['cover_ms'] / max(1, bst['timed_launches']), bst['geom_ms'] / max(1, bst['geom_launches']))
+            b_ms = b_cover + b_geom
+            big_bytes = 1600 * 1600 * 3
+            big_info = {'value': env.world * nb / (b_ms / 1e3), 'unit': 'images/s', 'canvas': '1600x1600', 'images_per_step_per_gpu': nb,
+                        'ms_per_step': b_ms, 'figure_ms': b_cover, 'geometry_ms': b_geom, 'edges_per_image': bst['edges'] / nb,
+                        'bytes_per_image': big_bytes, 'hbm_frac': nb * big_bytes / (b_ms / 1e3) / 1e9 / fallback_peak()[0],
+                        'hbm_frac_k_figure': nb * big_bytes / (b_cover / 1e3) / 1e9 / fallback_peak()[0],
+                        'workload': 'single-shape variants at the reference CLI\'s output size (8 in x 200 dpi), k_figure_path + k_figure, '
+                                    'artist arrays resident in HBM'}
+        rb.close()
+    except Exception as e:                                   # (reported, not fatal: the headline is the 512 x 512 workload)
+        big_info = {'error': str(e)}
     del out
     torch.cuda.empty_cache()
 
@@ -421,7 +451,7 @@ def figure_leg(env, args, sampler):
     checksum = int(pinned[::257, 200:312, 200:312, 0].astype('int64').sum())
     res = {
         'value': value, 'ms_per_step': ms_max / args.steps, 'warmup': n_warm, 'clocks': clocks,
-        'launches': stats['kernel_launches'] - launches0, 'stats': stats, 'n': n, 'multi_shape': multi_info,
+        'launches': stats['kernel_launches'] - launches0, 'stats': stats, 'n': n, 'multi_shape': multi_info, 'dpi200': big_info,
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': png_bytes // e2e_steps,
                 'images_per_step_per_gpu': FIG_E2E, 'chunk': e2e_chunk,
                 'png_bytes_per_image': png_bytes / (e2e_steps * FIG_E2E), 'gpu_launches': e2e_launches,
@@ -681,7 +711,7 @@ def run_ours(args):
                 'metric': FIG_METRIC, 'value': fig['value'], 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': fig['warmup'], 'ms_per_step': fig['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': fig['config'], 'e2e': fig['e2e'],
-                'e2e_pixels': fig['e2e_pixels'], 'multi_shape': fig['multi_shape'], 'gpu_launches': fig['launches'],
+                'e2e_pixels': fig['e2e_pixels'], 'multi_shape': fig['multi_shape'], 'dpi200': fig['dpi200'], 'gpu_launches': fig['launches'],
                 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                              'traffic': traffic, 'kernel': 'k_figure', 'peak_source': peak_src, 'launches': stats['timed_launches'],
                              'images_per_launch': per_launch, 'figure_ms_per_step': stats['cover_ms'] / args.steps,

@@ -2,13 +2,13 @@
 //
 //   k_expand  one warp per element: float64 vertex prologue (rotate / translate / wrap copies fused
 //             in), then one lane per polygon edge / stroke segment writes 32-byte draw records.
-//   k_raster  persistent warps; each warp claims bands of 8 canvas rows, keeps the band in shared
-//             memory (3*W*8 bytes, packed RGB), replays the panel's records in draw order with
-//             lanes spread over the iterations that fall inside the band, and hands the finished
-//             band to the TMA engine (cp.async.bulk shared -> global, one contiguous 12 KB write at
-//             W = 512).  Bands no primitive touches are never built: the TMA engine writes them
-//             straight from a constant template held once per CTA, so background pixels cost one
-//             instruction per 12 KB.
+//   k_raster  persistent warps; each warp claims bands of RIG_BAND_ROWS (5) canvas rows, keeps the
+//             band in shared memory (3*W*5 bytes, packed RGB; 27 warps per CTA at W = 512), replays
+//             the panel's records in draw order with lanes spread over the iterations that fall
+//             inside the band, and hands the finished band to the TMA engine (cp.async.bulk shared
+//             -> global, one contiguous 7.5 KB write at W = 512).  Bands no primitive touches are
+//             never built: the TMA engine writes them straight from a constant template held once
+//             per CTA, so background pixels cost one instruction per 7.5 KB.
 //
 // The roofline that bounds k_raster is HBM write bandwidth: 3*W*H bytes per panel leave the SM
 // exactly once, as full 128-byte lines, and nothing is read back.
