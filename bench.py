@@ -416,7 +416,7 @@ def figure_leg(env, args, sampler):
     env.barrier()
     l0 = r2.stats()['kernel_launches'] + enc.stats()['kernel_launches']
     t0 = time.perf_counter()
-    e2e_steps = args.e2e_steps                      # 32 x 32 768 images: a timed region of about a second
+    e2e_steps = args.e2e_steps                      # 48 x 32 768 images: a timed region of more than a second
     digest = 0
     for _ in range(e2e_steps):
         for i0, buf, off in r2.iter_png(sub, enc, e2e_chunk):
@@ -749,7 +749,7 @@ def main():
     ap.add_argument('--workload', default='figure', choices=['figure', 'sequence'],
                     help='figure: BASELINE configs[1] (headline) + the sequence-panel path as a sub-object; sequence: that path only')
     ap.add_argument('--no-sequence', action='store_true', help='figure workload: skip the sequence-panel leg')
-    ap.add_argument('--e2e-steps', type=int, default=32, help='timed passes of the e2e legs over the step scene (about 1 s)')
+    ap.add_argument('--e2e-steps', type=int, default=48, help='timed passes of the e2e legs over the step scene (a timed region of 1 s or more)')
     ap.add_argument('--e2e-chunk', type=int, default=FIG_E2E_CHUNK, help='images rendered + encoded per chunk of the figure e2e leg')
     ap.add_argument('--seq-cpu-budget', type=float, default=10.0, help='seconds of CPU work for the sequence-panel cpu_baseline')
     args = ap.parse_args()
