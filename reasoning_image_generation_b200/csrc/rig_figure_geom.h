@@ -70,7 +70,7 @@ struct Uncertain {
     {
         const double s = v * 256.0, f = s - floor(s);
         libm = true;
-        if (fabs(f - 0.5) < 1e-7 || fabs(v - c1) < 1e-8 || fabs(v - c2) < 1e-8) hit = true;
+        if (fabs(f - 0.5) < 3e-8 || fabs(v - c1) < 1e-8 || fabs(v - c2) < 1e-8) hit = true;      // 10x the bound above
     }
     RIG_HD void quotient(double q)                 // truncated to an int
     {
