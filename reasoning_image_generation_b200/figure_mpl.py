@@ -6,9 +6,12 @@ the same figure exactly what ``RendererAgg.draw_path`` would be handed for each 
 its non-affine and affine parts, line width in pixels, cap / join / snap, RGBA colours with the artist alpha folded in, clip
 rectangle -- in matplotlib's draw order (zorder, then insertion).  `savefig_batch` replaces the per-figure savefig loop.
 
-matplotlib is NOT installed in this image, so this module cannot be exercised here: it is written against
-matplotlib's documented artist API and is gated -- importing it without matplotlib raises ImportError, nothing else in the
-package depends on it, and tests/test_figure_mpl.py skips itself unless matplotlib is importable.
+matplotlib is NOT installed in this image, so this module cannot be exercised against the real library here: it is
+written against matplotlib's documented artist API and is gated -- importing it without matplotlib raises ImportError, nothing
+else in the package depends on it, tests/test_figure_mpl.py skips itself unless matplotlib is importable, and
+tests/test_figure_mpl_walker.py runs its control flow (draw order, what is read, what is refused) against a stand-in.
+Reference bug B1 (`math.lg10`, multi_combinator.py:127,1087) makes the reference's `adjacent` mode raise before it reaches
+savefig; that is host logic the walker never sees (a figure that was never completed is never extracted).
 """
 from __future__ import annotations
 
@@ -42,7 +45,8 @@ def _patch_artist(p: Patch) -> Dict[str, Any]:
     affine = transform.get_affine().get_matrix()
     lw_px = p.get_linewidth() * p.figure.dpi / 72.0
     edge = p.get_edgecolor()           # already carries the artist alpha (Patch._set_edgecolor)
-    if p._edgecolor is None or lw_px == 0 or p.get_linestyle() in ('None', 'none', ' ', ''):
+    # Patch._draw_paths_with_artist_properties: lw = 0 when the edge colour is fully transparent or the line style is 'None'
+    if p._edgecolor is None or edge[3] == 0 or lw_px == 0 or p.get_linestyle() in ('None', 'none', ' ', ''):
         lw_px = 0.0
     face = p.get_facecolor() if p.get_fill() and p.get_facecolor()[3] != 0 else None
     codes = tpath.codes
