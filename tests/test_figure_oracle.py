@@ -135,3 +135,27 @@ def test_layers_blend_in_artist_order(agg):
     # overlap pixel: blue at alpha 128 over red: r = (255*255*(256-128)) // (65280+128) = 127, b = (255*256*128) // 65408 = 127
     assert tuple(im[20 - 9, 8]) == (127, 0, 127)
     assert tuple(im[20 - 4, 4]) == (255, 0, 0)
+
+
+def test_random_fills_cover_their_analytic_area(agg):
+    """Independent of any reading of Agg's sources: an area-coverage rasteriser must lay down as much ink as the polygon has
+    area (shoelace formula), for convex and self-avoiding non-convex polygons at arbitrary sub-pixel positions; and a
+    translucent fill must lay down alpha times that."""
+    rng = np.random.RandomState(11)
+    worst = 0.0
+    for k in range(60):
+        n = int(rng.randint(3, 9))
+        ang = 2 * np.pi * (np.arange(n) + rng.uniform(-0.2, 0.2, n)) / n + rng.uniform(0, 6.28)     # gaps below pi: a simple polygon
+        rad = rng.uniform(8, 28, n) if k % 2 else np.full(n, rng.uniform(8, 28))       # star-shaped (non-convex) / convex
+        cx, cy = rng.uniform(30, 34, 2)
+        pts = np.c_[cx + rad * np.cos(ang), cy + rad * np.sin(ang)]
+        x, y = pts[:, 0], pts[:, 1]
+        area = 0.5 * abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1)))
+        v, c = fp.polyline(pts, True)
+        alpha = 1.0 if k % 3 else 0.5
+        im = _one(agg, 64, 64, vertices=v, codes=c, linewidth=0, facecolor=(0, 0, 0, alpha), snap=False)[:, :, 0]
+        ink = (255 - im.astype(int)).sum() / 255.0
+        want = area * (round(alpha * 255) / 255.0)
+        worst = max(worst, abs(ink - want) / want)
+        assert abs(ink - want) <= 0.01 * want + 0.5, (k, ink, want)
+    assert worst < 0.012
