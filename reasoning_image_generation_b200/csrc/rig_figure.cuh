@@ -6,8 +6,8 @@
 //       scatter   lanes take the layer's edges (16-byte coalesced loads; only the edges the slab directory says can reach
 //                 the band), walk Agg's row / cell split of each edge and add (cover, area) to per-cell accumulators in
 //                 shared memory with atomics -- the sums are commutative, so lane order does not matter;
-//       resolve   row by row, the 32-cell groups that were touched are visited left to right; a warp scan turns the
-//                 cells' covers into the running cover, every lane computes its pixel's 8-bit coverage and blends the
+//       resolve   two rows at a time (one per half-warp), the 16-cell groups that were touched are visited left to right; a scan
+//                 over the half-warp turns the cells' covers into the running cover, every lane computes its pixel's 8-bit coverage and blends the
 //                 layer colour with matplotlib's blender; runs between groups with a non-zero running cover (polygon
 //                 interiors) are filled with their constant coverage; the accumulators are left zeroed;
 //     then fence.proxy.async + one cp.async.bulk shared -> global store of the whole band.
@@ -27,7 +27,8 @@ namespace rig {
 #define FIG_ACC_CELLS 256
 #endif
 constexpr int FIG_ROWS = FIG_BAND_ROWS;
-constexpr int FIG_ACC = FIG_ACC_CELLS;     // accumulator columns per row; wider layers are resolved in column chunks (multiple of 32, <= 1024)
+constexpr int FIG_ACC = FIG_ACC_CELLS;     // accumulator columns per row; wider layers are resolved in column chunks (multiple of 32, <= 512)
+static_assert(FIG_ACC % 32 == 0 && FIG_ACC <= 512, "one touched-group bit per 16 cells must fit a 32-bit mask");
 constexpr int FIG_MAX_WARPS = 32;
 constexpr uint32_t FIG_NO_ROWS = 0x80007fffu;   // ymin = 32767, ymax = -32768: overlaps no band (a "1 > 0" range would overlap rows 0..1)
 
@@ -55,7 +56,7 @@ inline size_t figure_smem_bytes(int W, int nwarps) { return (size_t)3 * W * FIG_
 
 struct FigAcc {
     int *cover, *area;
-    unsigned *gmask;     // per band row: bit g = cells [x0 + 32 g, x0 + 32 g + 32) were touched
+    unsigned *gmask;     // per band row: bit g = cells [x0 + 16 g, x0 + 16 g + 16) were touched
     int *carry_in;       // per band row: cover of the cells left of x0
     int x0, r0, off, row_i;
     __device__ __forceinline__ void row(int ey)
@@ -71,7 +72,7 @@ struct FigAcc {
         if (cx >= FIG_ACC) return;
         atomicAdd(cover + off + cx, dc);
         atomicAdd(area + off + cx, da);
-        atomicOr(gmask + row_i, 1u << (cx >> 5));
+        atomicOr(gmask + row_i, 1u << (cx >> 4));
     }
 };
 
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(FIG_MAX_WARPS * 32, 1) k_figure(const FigurePa
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int half = lane >> 4, hl = lane & 15;
     const int W = P.W;
     const uint32_t band_bytes = (uint32_t)(3 * W * FIG_ROWS);
     uint8_t *tmpl = smem;
@@ -239,40 +241,48 @@ __global__ void __launch_bounds__(FIG_MAX_WARPS * 32, 1) k_figure(const FigurePa
                     // ---- resolve
                     const bool last_chunk = x0 + FIG_ACC > Lxmax;
                     const int fill_end = last_chunk ? W : x0 + FIG_ACC;
-                    for (int y = ya; y <= yb; y++) {
-                        const int ri = y - r0, ro = ri * FIG_ACC;
-                        uint32_t gm = gmask[ri];
-                        int carry = carry_in[ri];
-                        if (gm == 0u && carry == 0) continue;
+                    // two rows at a time, one per half-warp, 16-cell groups: a band is two rows, and the cells an outline touches in a
+                    // row rarely fill a 32-cell group, so the halves resolve both rows in the passes one row used to take
+                    for (int y0 = ya; y0 <= yb; y0 += 2) {
+                        const int y = y0 + half;
+                        const bool rowok = y <= yb;
+                        const int ri = rowok ? y - r0 : 0, ro = ri * FIG_ACC;
+                        uint32_t gm = rowok ? gmask[ri] : 0u;
+                        int carry = rowok ? carry_in[ri] : 0;
+                        if (!__any_sync(0xffffffffu, gm != 0u || carry != 0)) continue;
                         __syncwarp();
-                        if (lane == 0) { gmask[ri] = 0u; carry_in[ri] = 0; }
+                        if (hl == 0 && rowok) { gmask[ri] = 0u; carry_in[ri] = 0; }
                         uint8_t *rowpx = mine + (size_t)ri * W * 3;
                         int prev_end = x0;
-                        while (gm) {
-                            const int g = __ffs(gm) - 1;
-                            gm &= gm - 1;
-                            const int xs = x0 + g * 32;
-                            if (carry != 0 && xs > prev_end) {          // interior run at constant coverage
+                        while (__any_sync(0xffffffffu, gm != 0u)) {
+                            const bool on = gm != 0u;
+                            const int g = on ? __ffs(gm) - 1 : 0;
+                            if (on) gm &= gm - 1;
+                            const int xs = x0 + g * 16;
+                            if (on && carry != 0 && xs > prev_end) {    // interior run at constant coverage
                                 const uint32_t al = fig_alpha(carry, 0);
-                                for (int x = prev_end + lane; x < xs; x += 32) fig_put3(rowpx + x * 3, fig_blend_px_m(fig_get3(rowpx + x * 3), L.rgba, al, magic));
+                                for (int x = prev_end + hl; x < xs; x += 16) fig_put3(rowpx + x * 3, fig_blend_px_m(fig_get3(rowpx + x * 3), L.rgba, al, magic));
                             }
-                            const int x = xs + lane;
-                            const int c = cover[ro + g * 32 + lane], a = area[ro + g * 32 + lane];
-                            if (c | a) { cover[ro + g * 32 + lane] = 0; area[ro + g * 32 + lane] = 0; }
+                            const int x = xs + hl;
+                            int c = 0, a = 0;
+                            if (on) {
+                                c = cover[ro + g * 16 + hl]; a = area[ro + g * 16 + hl];
+                                if (c | a) { cover[ro + g * 16 + hl] = 0; area[ro + g * 16 + hl] = 0; }
+                            }
                             int ci = c;
 #pragma unroll
-                            for (int o = 1; o < 32; o <<= 1) {
-                                const int t = __shfl_up_sync(0xffffffffu, ci, o);
-                                if (lane >= o) ci += t;
+                            for (int o = 1; o < 16; o <<= 1) {
+                                const int t = __shfl_up_sync(0xffffffffu, ci, o, 16);
+                                if (hl >= o) ci += t;
                             }
                             const uint32_t al = fig_alpha(carry + ci, a);
-                            if (x < W && al) fig_put3(rowpx + x * 3, fig_blend_px_m(fig_get3(rowpx + x * 3), L.rgba, al, magic));
-                            carry += __shfl_sync(0xffffffffu, ci, 31);
-                            prev_end = xs + 32;
+                            if (on && x < W && al) fig_put3(rowpx + x * 3, fig_blend_px_m(fig_get3(rowpx + x * 3), L.rgba, al, magic));
+                            const int tot = __shfl_sync(0xffffffffu, ci, 15, 16);
+                            if (on) { carry += tot; prev_end = xs + 16; }
                         }
-                        if (carry != 0 && prev_end < fill_end) {        // interior continues to the next chunk / the right canvas edge
+                        if (rowok && carry != 0 && prev_end < fill_end) {   // interior continues to the next chunk / the right canvas edge
                             const uint32_t al = fig_alpha(carry, 0);
-                            for (int x = prev_end + lane; x < fill_end; x += 32) fig_put3(rowpx + x * 3, fig_blend_px_m(fig_get3(rowpx + x * 3), L.rgba, al, magic));
+                            for (int x = prev_end + hl; x < fill_end; x += 16) fig_put3(rowpx + x * 3, fig_blend_px_m(fig_get3(rowpx + x * 3), L.rgba, al, magic));
                         }
                     }
                     __syncwarp();
