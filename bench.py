@@ -466,7 +466,10 @@ def figure_leg(env, args, sampler):
         'config': {'workload': FIG_WORKLOAD, 'images_per_step_per_gpu': n, 'l2': 'outputs (25.8 GB/step) exceed L2; no flush needed',
                    'artists_per_step_per_gpu': scene.n_artists, 'vertices_per_step_per_gpu': scene.n_vertices, 'edges_per_image': per_img_edges,
                    'resident_input': 'artist arrays (draw_path arguments), %d bytes per image' % (h2d // FIG_E2E),
-                   'layers_per_image': stats['layers'] / n, 'out_layout': 'RGB', 'checksum': checksum_dev},
+                   'layers_per_image': stats['layers'] / n, 'out_layout': 'RGB', 'checksum': checksum_dev,
+                   'parity': 'pixels bit-exact against oracle/aggdraw.c (the restated matplotlib -> Agg pipeline) in tests/; oracle-exact, '
+                             'matplotlib parity ' + ('checked against tests/golden/figure_mpl.npz' if os.path.exists(os.path.join(ROOT, 'tests', 'golden', 'figure_mpl.npz'))
+                                                     else 'UNVERIFIED (no matplotlib in the build image; tests/golden/make_figure_golden.py is the pin)')},
     }
     pin.close()
     r.close()
