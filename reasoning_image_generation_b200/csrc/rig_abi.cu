@@ -613,6 +613,13 @@ int rig_set_profiling(rig_ctx *c, int on)
     if (!c) return RIG_E_INVALID;
     c->profiling = on != 0;
     if (on) {
+        // events for the launches to come are created now, not between the timed launches
+        if (cudaSetDevice(c->device) == cudaSuccess)
+            while (c->ev_pool.size() < 512) {
+                cudaEvent_t e = nullptr;
+                if (cudaEventCreate(&e) != cudaSuccess) break;
+                c->ev_pool.push_back(e);
+            }
         c->stats.expand_ms = c->stats.raster_ms = 0;
         c->stats.timed_launches = 0;
         c->stats.timed_panels = 0;

@@ -1041,6 +1041,13 @@ int rig_figure_set_profiling(rig_figure_ctx *c, int on)
     if (!c) return RIG_E_INVALID;
     c->profiling = on != 0;
     if (on) {
+        // events for the launches to come are created now, not between the timed launches
+        FCK(c, cudaSetDevice(c->device));
+        while (c->ev_pool.size() < 512) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreate(&e) != cudaSuccess) break;
+            c->ev_pool.push_back(e);
+        }
         c->stats.cover_ms = 0;
         c->stats.timed_launches = 0;
         c->stats.timed_images = 0;
