@@ -10,13 +10,16 @@
 // them decides a rounding, and the host then runs its own pipeline for the batch.
 //
 // Work decomposition
-//   * one THREAD per artist (a stroker is a sequential machine: a join needs the de-duplicated neighbours, the clipper the
-//     previous point).  Artists are handed out 32 at a time from a global counter in an order the host chose so that the lanes of
-//     a warp hold paths of the same length (same patch type: same control flow, little divergence).
-//   * a thread's stroke-vertex sequence and its unsorted edges live in thread-private global scratch (L1/L2 resident).
-//   * after each pass (faces, then strokes) the WARP places the lanes' layers: one atomicAdd reserves the edges and directory
-//     entries of all 32 layers, then per layer a stable counting sort by first row (shared-memory histogram, match_any ranks)
-//     moves the edges from the owner's scratch to their final place with coalesced 16-byte accesses and writes the slab directory.
+//   * short paths (fewer than GEOM_LONG_MIN_VERTICES vertices: lines, rectangles, small polygons): one THREAD per artist, 32 at a
+//     time per warp.  The host hands the artists out sorted by path length, so the lanes of a warp run the same patch type and
+//     diverge little.  A thread's stroke-vertex sequence and its unsorted edges live in thread-private global scratch.
+//   * long paths (curve outlines): one WARP per artist -- see "warp-cooperative route" below: lanes over curve commands, vertices,
+//     joins and contour segments, prefix sums in place of the serial order.  (The first version ran every artist on one thread:
+//     the 32 longest outlines then kept one warp busy for 1.8 M cycles while the SMs idled.)
+//   * after each pass (faces, then strokes) the WARP places its layers: ONE 64-bit atomicAdd reserves the edges and directory
+//     entries, then per layer a stable counting sort by first row (shared-memory histogram, match_any ranks) moves the edges from
+//     the scratch to their final place with coalesced 16-byte accesses and writes the slab directory; layers of at most 32 edges
+//     are copied as they are (one chunk of k_figure's edge loop: their order changes nothing).
 // Layer slots are fixed by the host (artist_layer[a] + 0 / 1), so image_layer_begin needs no device-wide scan; a pass that
 // leaves no edge keeps its slot as an empty layer (ymin > ymax), which k_figure's band test skips.
 #pragma once
