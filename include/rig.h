@@ -145,6 +145,11 @@ void rig_pinned_free(void *p);
  * (`size` must equal the value returned when out == NULL).  Needs no GPU.                          */
 size_t rig_debug_shape_tables(void *out, size_t size);
 
+/* Debugging aid, off unless the environment has RIG_TIMELINE set when the library is loaded: every kernel launch and large copy
+ * of every context in the process is bracketed by two CUDA events; rig_timeline_dump synchronises the device and writes
+ * "name,stream,start_ms,end_ms" (relative to the first event) to `path`.  tools/e2e_timeline.py reads it.                    */
+int rig_timeline_dump(const char *path);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,7 +57,7 @@ class RigStats(ctypes.Structure):
 EXPORTS = (
     'rig_create', 'rig_destroy', 'rig_last_error', 'rig_render_batch', 'rig_scene_upload',
     'rig_render_resident', 'rig_render_resident_hashed', 'rig_sync', 'rig_get_stats', 'rig_set_profiling', 'rig_debug_shape_tables',
-    'rig_hash_batch', 'rig_dedup', 'rig_hash_words', 'rig_int_pipe_peak', 'rig_pinned_alloc', 'rig_pinned_free',
+    'rig_hash_batch', 'rig_dedup', 'rig_hash_words', 'rig_int_pipe_peak', 'rig_pinned_alloc', 'rig_pinned_free', 'rig_timeline_dump',
 )
 
 _lib = None
