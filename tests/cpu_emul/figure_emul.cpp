@@ -38,8 +38,27 @@ void blend(uint8_t *px, uint32_t rgba, uint32_t al)
 
 // acc_cells: accumulator columns per row (multiple of 32); layers wider than that are resolved in column chunks with a
 // carry-in, as k_figure does with FIG_ACC_CELLS
+static void emul_render(int W, int H, int n_layers, const uint32_t *layers, const int32_t *edges, int band_rows, int acc_cells, int group,
+                        uint8_t *rgb);
+
 extern "C" void figure_emul_render(int W, int H, int n_layers, const uint32_t *layers, const int32_t *edges, int band_rows, int acc_cells,
                                    uint8_t *rgb)
+{
+    emul_render(W, H, n_layers, layers, edges, band_rows, acc_cells, 0, rgb);
+}
+
+// The resolve step organised as k_figure organises it: only the `group`-cell groups (16 in the kernel) that the scatter touched are
+// visited, left to right; between them the running cover is constant, so a non-zero cover there is an interior run filled at
+// constant coverage, and so is what follows the last group up to the chunk's end / the canvas edge.  (The kernel resolves the band's
+// two rows at once, one per half-warp; rows are independent, so a serial emulation visits them in turn.)
+extern "C" void figure_emul_render_grouped(int W, int H, int n_layers, const uint32_t *layers, const int32_t *edges, int band_rows,
+                                           int acc_cells, int group, uint8_t *rgb)
+{
+    emul_render(W, H, n_layers, layers, edges, band_rows, acc_cells, group, rgb);
+}
+
+static void emul_render(int W, int H, int n_layers, const uint32_t *layers, const int32_t *edges, int band_rows, int acc_cells, int group,
+                        uint8_t *rgb)
 {
     memset(rgb, 255, (size_t)W * H * 3);
     std::vector<int> cover((size_t)band_rows * acc_cells), area((size_t)band_rows * acc_cells), carry_in(band_rows);
@@ -60,7 +79,29 @@ extern "C" void figure_emul_render(int W, int H, int n_layers, const uint32_t *l
                     fig_edge_rows(ed, r0, r1, acc);
                 }
                 const int fill_end = x0 + acc_cells > xmax ? W : x0 + acc_cells;
-                for (int y = (ymin > r0 ? ymin : r0); y <= (ymax < r1 ? ymax : r1); y++) {
+                for (int y = (ymin > r0 ? ymin : r0); group > 0 && y <= (ymax < r1 ? ymax : r1); y++) {
+                    const size_t ro = (size_t)(y - r0) * acc_cells;
+                    int carry = carry_in[y - r0], prev_end = x0;
+                    for (int g = 0; g < acc_cells / group; g++) {
+                        bool touched = false;                   // (the kernel's scatter sets a bit per group it adds to)
+                        for (int k = 0; k < group; k++) touched |= (cover[ro + g * group + k] | area[ro + g * group + k]) != 0;
+                        if (!touched) continue;
+                        const int xs = x0 + g * group;
+                        if (carry != 0)
+                            for (int x = prev_end; x < xs; x++) blend(rgb + ((size_t)y * W + x) * 3, L[3], fig_alpha(carry, 0));
+                        int ci = 0;
+                        for (int k = 0; k < group; k++) {
+                            ci += cover[ro + g * group + k];
+                            const uint32_t al = fig_alpha(carry + ci, area[ro + g * group + k]);
+                            if (al && xs + k < W) blend(rgb + ((size_t)y * W + xs + k) * 3, L[3], al);
+                        }
+                        carry += ci;
+                        prev_end = xs + group;
+                    }
+                    if (carry != 0)
+                        for (int x = prev_end; x < fill_end; x++) blend(rgb + ((size_t)y * W + x) * 3, L[3], fig_alpha(carry, 0));
+                }
+                for (int y = (ymin > r0 ? ymin : r0); group == 0 && y <= (ymax < r1 ? ymax : r1); y++) {
                     int run = carry_in[y - r0];
                     int last = x0;          // first pixel not yet decided
                     for (int cx = 0; cx < acc_cells; cx++) {

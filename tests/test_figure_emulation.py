@@ -139,3 +139,32 @@ def test_division_free_blend_is_exact(femul):
     exhaustively (every destination value x colour value x alpha) against fixed_blender_rgba_plain's division."""
     femul.figure_emul_check_magic.restype = ctypes.c_long
     assert femul.figure_emul_check_magic() == 0
+
+
+def test_grouped_resolve_as_the_kernel_organises_it(agg, femul):
+    """k_figure visits only the touched 16-cell groups of a row and fills the runs between them at constant coverage (its two
+    half-warps take the band's two rows; rows are independent).  The same organisation on the CPU, for the kernel's group size and
+    two others, with accumulators narrower than the shapes (column chunks with a carry-in) and fills that run to the canvas edge."""
+    femul.figure_emul_render_grouped.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_void_p]
+    femul.figure_emul_render_grouped.restype = None
+    rng = np.random.RandomState(9)
+    sb = FigureSceneBuilder(320, 96)
+    for i in range(24):
+        for _ in range(int(rng.randint(1, 5))):
+            n = int(rng.randint(3, 7))
+            pts = rng.uniform(-30, 350, size=(n, 2)) * [1.0, 0.3]
+            v, c = fp.polyline(pts, True)
+            sb.add_artist(vertices=v, codes=c, linewidth=float(rng.choice([0.0, 1.3, 4.0])), edgecolor=tuple(rng.uniform(0, 1, 3)) + (0.9,),
+                          facecolor=tuple(rng.uniform(0, 1, 4)) if rng.randint(2) else None, snap=False)
+        sb.end_image()
+    scenes = [sb.finish(), synthetic_figure_scene(12, 512, 512, seed=3, kind='single'), synthetic_figure_scene(8, 512, 512, seed=4, kind='multi')]
+    for sc in scenes:
+        ref = agg.render(sc, sc.W, sc.H)
+        layers, edges = host_edges(sc)
+        for group, acc_cells in ((16, 256), (16, 64), (32, 256), (8, 32)):
+            out = np.zeros((sc.n_images, sc.H, sc.W, 3), np.uint8)
+            for i in range(sc.n_images):
+                L = np.ascontiguousarray(layers[layers[:, 0] == i])
+                femul.figure_emul_render_grouped(sc.W, sc.H, len(L), L.ctypes.data, edges.ctypes.data, 2, acc_cells, group, out[i].ctypes.data)
+            assert int((out != ref).any(axis=3).sum()) == 0, (sc.W, group, acc_cells)
